@@ -1,0 +1,354 @@
+// ipt_device.cuh — device-side building blocks of the B200 radiance path: vectors, the counter-based RNG,
+// nearest-hit tests for spheres and finite rectangles, the three scatter rules, and the ray-record codec.
+// Templated on the arithmetic type R: float is the product path, double is the parity mode (IPT_FLAG_FP64).
+//
+// What is computed follows the reference (file:line cited at each function, paths relative to the
+// AdamStudies-PWR/Improved-Path-Tracer tree); how it is computed does not: no virtual objects, no per-thread
+// scene copies, no recursion — rays are records in a queue and every function here is a pure function of a record.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ipt {
+
+// ---------------------------------------------------------------------------------------------- constants
+#define IPT_MARGIN 1e-4          /* scene/cuda/objects/Constants.hpp:8  */
+#define IPT_INF 1e20             /* Renderer.cu:29                       */
+#define IPT_VIEWPORT_DISTANCE 140.0  /* Renderer.cu:28                   */
+static constexpr uint32_t NODE_CAMERA = 0xFFFFu;
+static constexpr uint32_t CTR_TAG = 0x49505442u;  // "IPTB"
+static constexpr uint32_t NO_OBJECT = 0xFFFFFFFFu;
+static constexpr uint32_t RECT_BIT = 0x80000000u;
+
+// ray meta word: depth[0:8) lane[8:10) probe[10] onSurf[11] sample[12:28)
+static constexpr uint32_t META_PROBE = 1u << 10;
+static constexpr uint32_t META_ONSURF = 1u << 11;
+__host__ __device__ inline uint32_t make_meta(uint32_t depth, uint32_t lane, bool probe, bool onSurf, uint32_t sample)
+{
+    return depth | (lane << 8) | (probe ? META_PROBE : 0u) | (onSurf ? META_ONSURF : 0u) | (sample << 12);
+}
+
+// ---------------------------------------------------------------------------------------------- vectors
+template <typename R> struct V3 { R x, y, z; };
+template <typename R> struct alignas(sizeof(R) * 4) R4 { R x, y, z, w; };
+
+template <typename R> __device__ __forceinline__ V3<R> mk(R x, R y, R z) { V3<R> v; v.x = x; v.y = y; v.z = z; return v; }
+template <typename R> __device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return mk<R>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return mk<R>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, R s) { return mk<R>(a.x * s, a.y * s, a.z * s); }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a) { return mk<R>(-a.x, -a.y, -a.z); }
+template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename R> __device__ __forceinline__ V3<R> mul(V3<R> a, V3<R> b) { return mk<R>(a.x * b.x, a.y * b.y, a.z * b.z); }
+template <typename R> __device__ __forceinline__ V3<R> xyz(const R4<R>& q) { return mk<R>(q.x, q.y, q.z); }
+
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }  // Vec3.hpp:48-51: v * (1/sqrt(v.v))
+__device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return a / b; }
+template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * rsqrt_(dot(a, a)); }
+
+// ---------------------------------------------------------------------------------------------- RNG
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  One block = the four uniforms one scatter event can use,
+// addressed by (pixel, sample, lane<<8|depth): no generator state travels with a ray, and the image does not
+// depend on how rays are scheduled, batched, tiled or split over GPUs.  The reference seeds one XORWOW stream per
+// CUDA thread (Renderer.cu:95-97) and walks it through ~1900 pixels, which no parallel schedule can reproduce;
+// parity with it is therefore statistical, and exact against the oracle run on this same counter stream.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// 24-bit uniform in (0,1): ((x>>8)+0.5)/2^24 — exactly representable in fp32 and fp64, so both precisions and the
+// CPU oracle see the same numbers.  2u-1 is exact as well (odd multiple of 2^-24).
+template <typename R> __device__ __forceinline__ R u24(uint32_t x) { return ((R)(x >> 8) + (R)0.5) * (R)(1.0 / 16777216.0); }
+template <typename R> __device__ __forceinline__ R s24(uint32_t x) { return (R)2 * u24<R>(x) - (R)1; }  // CudaUtils.hpp:14-17
+
+// ---------------------------------------------------------------------------------------------- ray record
+template <typename R> struct Ray {
+    V3<R> o, d, thr;
+    uint32_t pixel, meta, self;
+};
+
+// Queue = structure of arrays of 16-byte planes: a warp reads/writes 512 contiguous bytes per plane (128-bit,
+// fully coalesced).  fp32: 3 planes (48 B/ray); fp64: 6 planes (96 B/ray).
+template <typename R> struct QPlanes;
+template <> struct QPlanes<float> { static constexpr int N = 3; };
+template <> struct QPlanes<double> { static constexpr int N = 6; };
+
+struct Queue {
+    uint4* base;        // plane p of ray i at base[p * capacity + i]
+    uint32_t capacity;
+};
+
+__device__ __forceinline__ void q_store(const Queue& q, uint32_t i, const Ray<float>& r)
+{
+    q.base[i] = make_uint4(__float_as_uint(r.o.x), __float_as_uint(r.o.y), __float_as_uint(r.o.z), __float_as_uint(r.d.x));
+    q.base[q.capacity + i] = make_uint4(__float_as_uint(r.d.y), __float_as_uint(r.d.z), __float_as_uint(r.thr.x), __float_as_uint(r.thr.y));
+    q.base[2u * q.capacity + i] = make_uint4(__float_as_uint(r.thr.z), r.pixel, r.meta, r.self);
+}
+__device__ __forceinline__ void q_load(const Queue& q, uint32_t i, Ray<float>& r)
+{
+    const uint4 a = q.base[i], b = q.base[q.capacity + i], c = q.base[2u * q.capacity + i];
+    r.o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+    r.d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+    r.thr = mk<float>(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+    r.pixel = c.y; r.meta = c.z; r.self = c.w;
+}
+__device__ __forceinline__ uint4 pack2(double a, double b)
+{
+    const unsigned long long x = (unsigned long long)__double_as_longlong(a), y = (unsigned long long)__double_as_longlong(b);
+    return make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)y, (uint32_t)(y >> 32));
+}
+__device__ __forceinline__ void unpack2(uint4 v, double& a, double& b)
+{
+    a = __longlong_as_double((long long)(((unsigned long long)v.y << 32) | v.x));
+    b = __longlong_as_double((long long)(((unsigned long long)v.w << 32) | v.z));
+}
+__device__ __forceinline__ void q_store(const Queue& q, uint32_t i, const Ray<double>& r)
+{
+    const size_t c = q.capacity;
+    q.base[i] = pack2(r.o.x, r.o.y);
+    q.base[c + i] = pack2(r.o.z, r.d.x);
+    q.base[2 * c + i] = pack2(r.d.y, r.d.z);
+    q.base[3 * c + i] = pack2(r.thr.x, r.thr.y);
+    uint4 e = pack2(r.thr.z, 0.0);
+    e.z = r.pixel; e.w = r.meta;
+    q.base[4 * c + i] = e;
+    q.base[5 * c + i] = make_uint4(r.self, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void q_load(const Queue& q, uint32_t i, Ray<double>& r)
+{
+    const size_t c = q.capacity;
+    unpack2(q.base[i], r.o.x, r.o.y);
+    unpack2(q.base[c + i], r.o.z, r.d.x);
+    unpack2(q.base[2 * c + i], r.d.y, r.d.z);
+    unpack2(q.base[3 * c + i], r.thr.x, r.thr.y);
+    const uint4 e = q.base[4 * c + i];
+    double dummy;
+    unpack2(e, r.thr.z, dummy);
+    r.pixel = e.z; r.meta = e.w;
+    r.self = q.base[5 * c + i].x;
+}
+
+// ---------------------------------------------------------------------------------------------- scene view
+// Geometry "slots": 4 x R4 per primitive.
+//   sphere    : g[0] = {cx, cy, cz, r}
+//   rectangle : g[0] = {n.xyz, D}  g[1] = {u.xyz, u.c}  g[2] = {v.xyz, v.c}  g[3] = {u_lo, u_hi, v_lo, v_hi}
+// slot_obj[s] = object (JSON) index, bit 31 set for rectangles.
+// mat[2k] = {color.rgb, reflection}, mat[2k+1] = {emission.rgb, any(emission != 0)} per OBJECT k.
+template <typename R> struct SceneView {
+    const R4<R>* geom;
+    const uint32_t* slot_obj;
+    const R4<R>* mat;
+    uint32_t n_slots, n_spheres;   // brute-force layout: spheres occupy slots [0, n_spheres), rectangles the rest
+    uint32_t n_objects;
+    const float4* nodes;           // BVH: 4 x float4 per node (see unpack in traverse), may be null
+    uint32_t n_nodes;
+};
+
+template <typename R> struct Hit {
+    R t;
+    uint32_t slot;      // NO_OBJECT = miss
+    uint32_t obj;       // object index | RECT_BIT
+};
+
+// Self-hit policy.  The reference rejects self intersections only through `t > 1e-4` (Sphere.cu:36-37, Plane.cu:58),
+// which fp32 cannot resolve at |x| ~ 1e3.  In fp32 a ray therefore carries the object it starts on and
+//   * never re-tests the rectangle it starts on (its only root is t ~ 0),
+//   * on the sphere it starts on, when the start point is known to lie ON the surface (the ray that produced the hit
+//     had unit length, so P = o + d t is a surface point), uses the exact second root t = -2 (op.d) of
+//     t^2 + 2 b t + (op.op - r^2) = 0 with op.op - r^2 = 0 — the same root the reference's formula returns.
+// In fp64 (parity mode) the literal tests are used.  Validated in SURVEY.md App. D (D10).
+template <typename R> struct SelfRule { static constexpr bool enabled = false; };
+template <> struct SelfRule<float> { static constexpr bool enabled = true; };
+
+// Sphere.cu:25-39.  Formula kept as is for non-unit directions (refracted rays are not normalised, AObject.hpp:59).
+template <typename R>
+__device__ __forceinline__ void test_sphere(const R4<R> s, uint32_t slot, uint32_t obj, const V3<R> o, const V3<R> d,
+                                            uint32_t self, bool onSurf, Hit<R>& best)
+{
+    const V3<R> op = o - xyz(s);
+    const R b = dot(op, d);
+    R t;
+    if (SelfRule<R>::enabled && obj == self && onSurf) {
+        t = (R)-2 * b;
+        if (!(t > (R)IPT_MARGIN)) return;
+    } else {
+        const R delta = b * b - dot(op, op) + s.w * s.w;
+        if (delta < (R)0) return;
+        const R sq = sqrt(delta);
+        t = -b - sq;
+        if (!(t > (R)IPT_MARGIN)) {
+            t = -b + sq;
+            if (!(t > (R)IPT_MARGIN)) return;
+        }
+    }
+    // Renderer.cu:235: `temp && temp < distance`, objects scanned in index order -> lowest index wins ties
+    if (t < best.t || (t == best.t && obj < best.obj)) { best.t = t; best.slot = slot; best.obj = obj; }
+}
+
+// Plane.cu:47-68 with the bounds test of :87-100 solved for the hit position (see ipt_abi.h / DESIGN.md §4).
+template <typename R>
+__device__ __forceinline__ void test_rect(const R4<R>* g, uint32_t slot, uint32_t obj, const V3<R> o, const V3<R> d,
+                                          uint32_t self, Hit<R>& best)
+{
+    if (SelfRule<R>::enabled && obj == self) return;
+    const R4<R> pl = g[0];
+    const R den = pl.x * d.x + pl.y * d.y + pl.z * d.z;
+    if (den == (R)0) return;                                   // Plane.cu:55
+    const R t = div_(pl.w - (pl.x * o.x + pl.y * o.y + pl.z * o.z), den);
+    if (!(t > (R)IPT_MARGIN)) return;                          // Plane.cu:58 (NaN fails too)
+    if (!(t < best.t || (t == best.t && obj < best.obj))) return;
+    const V3<R> P = o + d * t;
+    const R4<R> gu = g[1], gv = g[2], bd = g[3];
+    const R su = fabs(gu.x * P.x + gu.y * P.y + gu.z * P.z - gu.w);
+    const R sv = fabs(gv.x * P.x + gv.y * P.y + gv.z * P.z - gv.w);
+    if (su >= bd.x && su <= bd.y && sv >= bd.z && sv <= bd.w) { best.t = t; best.slot = slot; best.obj = obj; }
+}
+
+// Renderer.cu:227-243 over a brute-force slot list (every lane of a warp walks the same slots: broadcast reads).
+template <typename R>
+__device__ __forceinline__ Hit<R> nearest_brute(const SceneView<R>& sc, const V3<R> o, const V3<R> d, uint32_t self, bool onSurf)
+{
+    Hit<R> best;
+    best.t = (R)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+    const uint32_t ns = sc.n_spheres, n = sc.n_slots;
+#pragma unroll 2
+    for (uint32_t s = 0; s < ns; s++) test_sphere<R>(sc.geom[4 * s], s, sc.slot_obj[s], o, d, self, onSurf, best);
+#pragma unroll 2
+    for (uint32_t s = ns; s < n; s++) test_rect<R>(sc.geom + 4 * s, s, sc.slot_obj[s], o, d, self, best);
+    return best;
+}
+
+// BVH2 traversal: nodes are four float4 (128-bit loads); boxes are fp32 and padded by the builder, the slab test is
+// conservative (fp64 rays are tested against the fp32 boxes in fp64).  `top` points at a shared-memory copy of the
+// first n_top nodes (the builder emits nodes breadth-first, so these are the top levels every ray visits).
+template <typename R>
+__device__ __forceinline__ Hit<R> nearest_bvh(const SceneView<R>& sc, const float4* top, uint32_t n_top, const V3<R> o,
+                                              const V3<R> d, uint32_t self, bool onSurf)
+{
+    Hit<R> best;
+    best.t = (R)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+    const R ix = (R)1 / d.x, iy = (R)1 / d.y, iz = (R)1 / d.z;   // +-inf for zero components: slab test handles it
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    const R slack = (R)1.0000004;   // 3 ulp(fp32) on the far distance: never cull a box the exact test would keep
+    for (;;) {
+        if (node >= 0) {
+            const float4* p = ((uint32_t)node < n_top) ? (top + 4 * node) : (sc.nodes + 4 * (size_t)node);
+            float4 a, b, c, e;
+            if ((uint32_t)node < n_top) { a = p[0]; b = p[1]; c = p[2]; e = p[3]; }
+            else { a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); e = __ldg(p + 3); }
+            // a = lo0.xyz hi0.x | b = hi0.yz lo1.xy | c = lo1.z hi1.xyz | e = child0 child1 (int bits)
+            R t0x = ((R)a.x - o.x) * ix, t1x = ((R)a.w - o.x) * ix;
+            R t0y = ((R)a.y - o.y) * iy, t1y = ((R)b.x - o.y) * iy;
+            R t0z = ((R)a.z - o.z) * iz, t1z = ((R)b.y - o.z) * iz;
+            R n0 = fmax(fmax(fmin(t0x, t1x), fmin(t0y, t1y)), fmax(fmin(t0z, t1z), (R)0));
+            R f0 = fmin(fmin(fmax(t0x, t1x), fmax(t0y, t1y)), fmin(fmax(t0z, t1z), best.t)) * slack;
+            t0x = ((R)b.z - o.x) * ix; t1x = ((R)c.y - o.x) * ix;
+            t0y = ((R)b.w - o.y) * iy; t1y = ((R)c.z - o.y) * iy;
+            t0z = ((R)c.x - o.z) * iz; t1z = ((R)c.w - o.z) * iz;
+            R n1 = fmax(fmax(fmin(t0x, t1x), fmin(t0y, t1y)), fmax(fmin(t0z, t1z), (R)0));
+            R f1 = fmin(fmin(fmax(t0x, t1x), fmax(t0y, t1y)), fmin(fmax(t0z, t1z), best.t)) * slack;
+            const bool h0 = n0 <= f0, h1 = n1 <= f1;
+            const int c0 = __float_as_int(e.x), c1 = __float_as_int(e.y);
+            if (h0 && h1) {
+                const bool swap = n1 < n0;
+                stack[sp++] = swap ? c0 : c1;
+                node = swap ? c1 : c0;
+            } else if (h0) node = c0;
+            else if (h1) node = c1;
+            else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            // leaf: ~node = first_slot * 16 + (count - 1)
+            const uint32_t code = (uint32_t)(~node);
+            const uint32_t first = code >> 4, cnt = (code & 15u) + 1u;
+            for (uint32_t s = first; s < first + cnt; s++) {
+                const uint32_t obj = __ldg(sc.slot_obj + s);
+                if (obj & RECT_BIT) test_rect<R>(sc.geom + 4 * (size_t)s, s, obj, o, d, self, best);
+                else test_sphere<R>(sc.geom[4 * (size_t)s], s, obj, o, d, self, onSurf, best);
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------- scatter
+// AObject.hpp:30-33: in - (n * (in.n)) * 2
+template <typename R> __device__ __forceinline__ V3<R> reflect_dir(V3<R> in, V3<R> n) { return in - n * dot(in, n) * (R)2; }
+
+// AObject.hpp:35-45: cube-normalised direction, flipped into n's hemisphere.  Draws 0,1,2 of the event's block.
+template <typename R> __device__ __forceinline__ V3<R> diffuse_dir(V3<R> n, uint4 rnd)
+{
+    V3<R> v = normalize(mk<R>(s24<R>(rnd.x), s24<R>(rnd.y), s24<R>(rnd.z)));   // never (0,0,0): s24 is an odd multiple of 2^-24
+    return dot(v, n) < (R)0 ? -v : v;
+}
+
+// AObject.hpp:47-60: eta = 1/1.5 in both directions, not normalised; returns false on total internal reflection.
+template <typename R> __device__ __forceinline__ bool refract_dir(V3<R> in, V3<R> n, V3<R>& out)
+{
+    const R index = (R)(1.0 / 1.5);
+    const R cosI = fabs(dot(n, in));
+    const R sin2 = (index * index) * ((R)1 - cosI * cosI);
+    if (sin2 > (R)1) return false;
+    const R cosT = sqrt((R)1 - sin2);
+    out = in * index + n * (index * cosI - cosT);
+    return !(out.x == (R)0 && out.y == (R)0 && out.z == (R)0);   // AObject.hpp:117 compares the result with Vec3()
+}
+
+// Result of shading one hit: up to two continuation rays (the reference's RayData, RayData.hpp:12-28).
+template <typename R> struct Spawn {
+    V3<R> d0, d1;
+    R w0, w1;
+    bool has0, has1;
+};
+
+// Sphere.cu:41-56, Plane.cu:70-84, AObject.hpp:83-135.  `g0` is the first geometry vector of the hit slot.
+template <typename R>
+__device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int reflection, V3<R> P, V3<R> in, uint32_t depth, uint4 rnd)
+{
+    V3<R> raw, n;
+    if (isRect) {
+        const V3<R> pn = xyz(g0);
+        n = dot(in, pn) < (R)0 ? pn : -pn;      // Plane.cu:73: opposes the incoming ray
+        raw = n;                                // Plane.cu:79
+    } else {
+        raw = normalize(P - xyz(g0));           // Sphere.cu:44
+        n = dot(in, raw) < (R)0 ? -raw : raw;   // Sphere.cu:45: points ALONG the incoming ray (into the surface)
+    }
+    Spawn<R> s;
+    s.has0 = true; s.has1 = false; s.w0 = (R)1; s.w1 = (R)0;
+    s.d1 = mk<R>(0, 0, 0);
+    if (reflection == 0) {                      // AObject.hpp:104-108
+        s.d0 = diffuse_dir(n, rnd);
+    } else if (reflection == 1) {               // AObject.hpp:83-102
+        const V3<R> spec = reflect_dir(in, n);
+        const V3<R> diff = diffuse_dir(n, rnd);
+        if (depth < 2) { s.d0 = spec; s.w0 = (R)0.92; s.d1 = diff; s.w1 = (R)0.08; s.has1 = true; }
+        else s.d0 = (u24<R>(rnd.w) > (R)0.9) ? diff : spec;
+    } else if (reflection == 2) {               // AObject.hpp:110-135
+        const V3<R> spec = reflect_dir(in, n);
+        V3<R> refr;
+        if (!refract_dir(in, raw, refr)) s.d0 = spec;
+        else if (depth < 2) { s.d0 = refr; s.w0 = (R)0.95; s.d1 = spec; s.w1 = (R)0.05; s.has1 = true; }
+        else s.d0 = (u24<R>(rnd.w) > (R)0.95) ? spec : refr;
+    } else {                                    // "Uknown reflection type": zero ray with weight 0 -> nothing to trace
+        s.has0 = false;
+        s.d0 = mk<R>(0, 0, 0);
+    }
+    return s;
+}
+
+}  // namespace ipt

@@ -1,0 +1,287 @@
+// ipt_kernels.cuh — the wavefront kernels of the B200 radiance path.
+//
+// One *batch* is a contiguous range of camera samples.  A batch is advanced one bounce per kernel launch
+// ("pass"): pass p reads the ray queue written by pass p-1, finds the nearest hit, accumulates emission, scatters,
+// and appends the continuation rays to the other queue with warp-level compaction (ballot + popc + ONE atomic per
+// warp).  Pass 0 generates the camera rays in registers instead of reading a queue.  Every launch is a persistent
+// grid (a fixed number of CTAs per SM) whose warps pull chunks of rays from a global work counter, so launch
+// geometry never depends on the (device-resident) queue length and the host never synchronises inside a render.
+//
+// Reference being replaced: the single kernel cudaMain<<<22,22>>> (Renderer.cu:254-265) in which each of 484 threads
+// walks ~1900 pixels x spp x bounces serially with recursion (firstLayer/secondLayer/deepLayers, :149-225).
+#pragma once
+#include "ipt_device.cuh"
+
+namespace ipt {
+
+enum { MODE_BRUTE = 0, MODE_BVH = 1 };
+
+static constexpr int BLOCK_THREADS = 256;
+static constexpr int GRAB = 128;          // rays a warp claims per atomic on the work counter (4 iterations of 32)
+static constexpr int BVH_TOP_NODES = 512; // top of the BVH staged in shared memory (32 KB)
+
+// counters[] layout (uint32): [CNT + p] rays queued for pass p, [WORK + p] work-claim counter of pass p
+static constexpr int MAX_PASSES = 256;
+static constexpr int CNT = 0, WORK = MAX_PASSES;
+static constexpr int N_COUNTERS = 2 * MAX_PASSES;
+
+template <typename R> struct KParams {
+    SceneView<R> sc;
+    // camera, RenderController.cu:39 + Renderer.cu:112-147
+    V3<R> camO, camD, camX, camZ;
+    R fov;                      // (R)0.0009f  (Renderer.cu:27 is a float constant)
+    uint32_t W, H, spp, maxDepth;
+    uint32_t depth;             // depth of every ray in this pass
+    uint32_t flags;
+    uint32_t key0, key1;
+    // tile schedule of this rank: local tile lt -> global tile id tile_ids[lt]
+    const uint32_t* tile_ids;
+    uint32_t n_tiles_local, tiles_x, tile_w, tile_h;
+    uint32_t mt_x, mt_per_tile; // micro-tiles (8x4 pixels) per tile row / per tile
+    // batch
+    uint32_t base_mt, base_sample, n_first;   // pass 0: first micro-tile, first sample, number of sample ids in the batch
+    Queue qin, qout;
+    uint32_t* counters;
+    unsigned long long* traced; // total nearest-hit queries (stats)
+    unsigned long long* frame;  // 3 x 64-bit accumulators per pixel (fixed point, or fp64 bits with IPT_FLAG_FLOAT_ACCUM)
+    double fixed_scale;
+};
+
+// Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
+// integer atomic, so the frame is bit-identical for any scheduling, batch size, tile size or GPU count.
+template <typename R>
+__device__ __forceinline__ void accumulate(const KParams<R>& p, uint32_t pixel, V3<R> v)
+{
+    unsigned long long* f = p.frame + 3ull * pixel;
+    if (p.flags & 0x4u) {   // IPT_FLAG_FLOAT_ACCUM
+        atomicAdd(reinterpret_cast<double*>(f), (double)v.x);
+        atomicAdd(reinterpret_cast<double*>(f) + 1, (double)v.y);
+        atomicAdd(reinterpret_cast<double*>(f) + 2, (double)v.z);
+    } else {
+        atomicAdd(f, (unsigned long long)__double2ll_rn((double)v.x * p.fixed_scale));
+        atomicAdd(f + 1, (unsigned long long)__double2ll_rn((double)v.y * p.fixed_scale));
+        atomicAdd(f + 2, (unsigned long long)__double2ll_rn((double)v.z * p.fixed_scale));
+    }
+}
+
+// Sample id -> (pixel, sample).  Ids are ordered micro-tile major: 32 consecutive ids are one 8x4 pixel block at
+// one sample index (a warp's camera rays are neighbours), consecutive groups walk the samples of that block.
+template <typename R>
+__device__ __forceinline__ bool decode_sample(const KParams<R>& p, uint32_t sid, uint32_t& px, uint32_t& pz, uint32_t& sample)
+{
+    const uint32_t g = sid >> 5, l = sid & 31u;
+    const uint32_t s = p.base_sample + g;
+    sample = s % p.spp;
+    const uint32_t mt = p.base_mt + s / p.spp;
+    const uint32_t lt = mt / p.mt_per_tile, m = mt % p.mt_per_tile;
+    if (lt >= p.n_tiles_local) return false;
+    const uint32_t tile = p.tile_ids[lt];
+    const uint32_t tx = tile % p.tiles_x, tz = tile / p.tiles_x;
+    px = tx * p.tile_w + (m % p.mt_x) * 8u + (l & 7u);
+    pz = tz * p.tile_h + (m / p.mt_x) * 4u + (l >> 3);
+    return px < p.W && pz < p.H;
+}
+
+// Renderer.cu:112-147: per-pixel gaze (not jittered), +-1 pixel box jitter on the origin only.
+template <typename R>
+__device__ __forceinline__ void camera_ray(const KParams<R>& p, uint32_t px, uint32_t pz, uint32_t sample, Ray<R>& r)
+{
+    const R corr = (p.W % 2 == 0) ? (R)0.5 : (R)0;   // :118-119 — the z axis also tests the WIDTH's parity
+    const R stepX = (px < p.W / 2) ? (R)(p.W / 2 - px) - corr : ((R)p.W / (R)2 - (R)px - (R)1) + ((corr == (R)0) ? (R)1 : corr);
+    const R stepZ = (pz < p.H / 2) ? (R)(p.H / 2 - pz) - corr : ((R)p.H / (R)2 - (R)pz - (R)1) + ((corr == (R)0) ? (R)1 : corr);
+    r.d = normalize(p.camD + p.camX * stepX * p.fov + p.camZ * stepZ * p.fov);                       // :127
+    const uint32_t pixel = pz * p.W + px;
+    const uint4 rnd = philox4x32_10(pixel, sample, NODE_CAMERA, CTR_TAG, p.key0, p.key1);
+    const R jx = s24<R>(rnd.x), jz = s24<R>(rnd.y);                                                   // :133-134
+    const V3<R> tent = p.camX * jx + p.camZ * jz;                                                     // :135
+    const V3<R> origin = p.camO + p.camX * stepX + p.camZ * stepZ + tent;                             // :138
+    r.o = origin + p.camD * (R)IPT_VIEWPORT_DISTANCE;                                                 // :139
+    r.thr = mk<R>(1, 1, 1);
+    r.pixel = pixel;
+    r.meta = make_meta(0, 0, false, false, sample);
+    r.self = NO_OBJECT;
+}
+
+// Copies `n16` 16-byte words from global to shared memory with the whole CTA (128-bit, coalesced).
+__device__ __forceinline__ void stage(uint4* dst, const uint4* src, uint32_t n16)
+{
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// One bounce of one batch.  FIRST: rays are generated from sample ids instead of read from qin.
+template <typename R, int MODE, bool FIRST>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant__ KParams<R> p)
+{
+    extern __shared__ uint4 smem[];
+    SceneView<R> sc = p.sc;
+    const float4* top = nullptr;
+    uint32_t n_top = 0;
+    if (MODE == MODE_BRUTE) {
+        // whole scene -> shared memory: geometry slots, slot->object ids, materials
+        constexpr uint32_t W16 = sizeof(R4<R>) / 16;
+        const uint32_t ng = sc.n_slots * 4 * W16, nm = sc.n_objects * 2 * W16, ni = (sc.n_slots + 3) / 4;
+        stage(smem, reinterpret_cast<const uint4*>(p.sc.geom), ng);
+        stage(smem + ng, reinterpret_cast<const uint4*>(p.sc.mat), nm);
+        stage(smem + ng + nm, reinterpret_cast<const uint4*>(p.sc.slot_obj), ni);
+        sc.geom = reinterpret_cast<const R4<R>*>(smem);
+        sc.mat = reinterpret_cast<const R4<R>*>(smem + ng);
+        sc.slot_obj = reinterpret_cast<const uint32_t*>(smem + ng + nm);
+    } else {
+        n_top = sc.n_nodes < (uint32_t)BVH_TOP_NODES ? sc.n_nodes : (uint32_t)BVH_TOP_NODES;
+        stage(smem, reinterpret_cast<const uint4*>(p.sc.nodes), n_top * 4);
+        top = reinterpret_cast<const float4*>(smem);
+    }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.depth];
+    const uint32_t depth = p.depth;
+    uint32_t* work = p.counters + WORK + depth;
+    uint32_t* out_count = p.counters + CNT + depth + 1;
+    unsigned long long my_traced = 0;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, (uint32_t)GRAB);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_in) break;
+#pragma unroll 1
+        for (uint32_t k = 0; k < GRAB; k += 32) {
+            const uint32_t i = base + k + lane;
+            bool live = i < n_in;
+            Ray<R> r;
+            if (FIRST) {
+                uint32_t px = 0, pz = 0, sample = 0;
+                live = live && decode_sample(p, i, px, pz, sample);
+                if (live) camera_ray(p, px, pz, sample, r);
+            } else if (live) {
+                q_load(p.qin, i, r);
+            }
+            bool has0 = false, has1 = false;
+            Ray<R> o0, o1;
+            if (live) {
+                const bool onSurf = (r.meta & META_ONSURF) != 0;
+                const Hit<R> h = (MODE == MODE_BRUTE) ? nearest_brute<R>(sc, r.o, r.d, r.self, onSurf)
+                                                      : nearest_bvh<R>(sc, top, n_top, r.o, r.d, r.self, onSurf);
+                if (h.slot != NO_OBJECT) {
+                    const bool isRect = (h.obj & RECT_BIT) != 0;
+                    const uint32_t obj = h.obj & ~RECT_BIT;
+                    const R4<R> m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
+                    if (m1.w != (R)0) accumulate(p, r.pixel, mul(r.thr, xyz(m1)));   // E of every hit counts (Renderer.cu:170,193,211)
+                    const bool probe = (r.meta & META_PROBE) != 0;
+                    // Continuation exists iff another hit would still be evaluated: depth+1 < maxDepth (:161,:184,:201).
+                    // Paths whose throughput is exactly 0 and the second branch of a depth-0 split after its first hit
+                    // contribute exactly 0 and are not traced.
+                    if (!probe && depth + 1 < p.maxDepth) {
+                        V3<R> nthr = mul(r.thr, xyz(m0));
+                        if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0) {
+                            const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
+                            const V3<R> P = r.o + r.d * h.t;                                       // :156,:179,:207
+                            const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.key0, p.key1);
+                            const Spawn<R> sp = scatter<R>(isRect, sc.geom[4 * (size_t)h.slot], (int)m0.w, P, r.d, depth, rnd);
+                            bool alive = sp.has0;
+                            if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension, off by default)
+                                const R q = fmin((R)1, fmax((R)0.05, fmax(nthr.x, fmax(nthr.y, nthr.z))));
+                                const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.key0, p.key1);
+                                if (u24<R>(rr.x) >= q) alive = false;
+                                else nthr = nthr * ((R)1 / q);
+                            }
+                            const bool onS = isRect || fabs(dot(r.d, r.d) - (R)1) < (R)1e-3;
+                            if (alive) {
+                                has0 = true;
+                                o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.obj;
+                                o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
+                            }
+                            if (sp.has1) {
+                                // depth 0: the second ray is an emission probe of the next surface (its deeper recursion
+                                // folds to 0 in the reference, Renderer.cu:173,216); depth 1: a full second path (lane 1)
+                                has1 = true;
+                                o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.obj;
+                                o1.meta = make_meta(depth + 1, depth == 0 ? 2u : 1u, depth == 0, onS, sample);
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- compaction: one atomic per warp
+            const uint32_t m_live = __ballot_sync(0xffffffffu, live);
+            const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
+            my_traced += __popc(m_live);
+            const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
+            if (tot) {
+                uint32_t ob = 0;
+                if (lane == 0) ob = atomicAdd(out_count, tot);
+                ob = __shfl_sync(0xffffffffu, ob, 0);
+                if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
+                if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
+            }
+        }
+    }
+    if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
+}
+
+// Frame accumulators -> mean radiance per pixel (Renderer.cu:142-144), for the tiles this rank owns.  `dst32/dst64`
+// may point into another GPU's frame (NVLink peer access): the gather to rank 0 is these stores.
+struct ResolveParams {
+    const unsigned long long* frame;
+    float* dst32;
+    double* dst64;
+    const uint32_t* tile_ids;
+    uint32_t n_tiles_local, tiles_x, tile_w, tile_h, W, H;
+    double inv;          // 1 / (fixed_scale * spp)  or 1 / spp with float accumulation
+    uint32_t float_accum;
+};
+
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ ResolveParams p)
+{
+    const uint32_t per_tile = p.tile_w * p.tile_h;
+    const unsigned long long total = (unsigned long long)p.n_tiles_local * per_tile;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t lt = (uint32_t)(i / per_tile), in = (uint32_t)(i % per_tile);
+        const uint32_t tile = p.tile_ids[lt];
+        const uint32_t px = (tile % p.tiles_x) * p.tile_w + in % p.tile_w, pz = (tile / p.tiles_x) * p.tile_h + in / p.tile_w;
+        if (px >= p.W || pz >= p.H) continue;
+        const size_t pixel = (size_t)pz * p.W + px;
+        for (int c = 0; c < 3; c++) {
+            const unsigned long long a = p.frame[3 * pixel + c];
+            const double v = p.float_accum ? __longlong_as_double((long long)a) * p.inv : (double)(long long)a * p.inv;
+            if (p.dst64) p.dst64[3 * pixel + c] = v;
+            if (p.dst32) p.dst32[3 * pixel + c] = (float)v;
+        }
+    }
+}
+
+// Function-level access for parity tests: nearest hit of explicit rays through the same device functions.
+template <typename R, int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_trace(SceneView<R> scv, const double* rays, uint32_t n, int32_t* out_obj, double* out_t)
+{
+    extern __shared__ uint4 smem[];
+    SceneView<R> sc = scv;
+    const float4* top = nullptr;
+    uint32_t n_top = 0;
+    if (MODE == MODE_BRUTE) {
+        constexpr uint32_t W16 = sizeof(R4<R>) / 16;
+        const uint32_t ng = sc.n_slots * 4 * W16, ni = (sc.n_slots + 3) / 4;
+        stage(smem, reinterpret_cast<const uint4*>(scv.geom), ng);
+        stage(smem + ng, reinterpret_cast<const uint4*>(scv.slot_obj), ni);
+        sc.geom = reinterpret_cast<const R4<R>*>(smem);
+        sc.slot_obj = reinterpret_cast<const uint32_t*>(smem + ng);
+    } else {
+        n_top = sc.n_nodes < (uint32_t)BVH_TOP_NODES ? sc.n_nodes : (uint32_t)BVH_TOP_NODES;
+        stage(smem, reinterpret_cast<const uint4*>(scv.nodes), n_top * 4);
+        top = reinterpret_cast<const float4*>(smem);
+    }
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3<R> o = mk<R>((R)rays[6 * i], (R)rays[6 * i + 1], (R)rays[6 * i + 2]);
+        const V3<R> d = mk<R>((R)rays[6 * i + 3], (R)rays[6 * i + 4], (R)rays[6 * i + 5]);
+        const Hit<R> h = (MODE == MODE_BRUTE) ? nearest_brute<R>(sc, o, d, NO_OBJECT, false)
+                                              : nearest_bvh<R>(sc, top, n_top, o, d, NO_OBJECT, false);
+        out_obj[i] = h.slot == NO_OBJECT ? -1 : (int32_t)(h.obj & ~RECT_BIT);
+        out_t[i] = (double)h.t;
+    }
+}
+
+}  // namespace ipt

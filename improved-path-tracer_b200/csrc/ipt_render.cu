@@ -1,0 +1,610 @@
+// ipt_render.cu — implementation of the C ABI in include/ipt_abi.h on top of the kernels in ipt_kernels.cuh.
+// Host side of the boundary the reference crosses in RenderContoller::start() (RenderController.cu:36-70):
+// allocate, upload, launch, copy back — here as a resident context per GPU, with no synchronisation between
+// the launches of a render and no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ipt_abi.h"
+#include "ipt_kernels.cuh"
+
+using namespace ipt;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::string g_err_shared;   // last error of any thread (ipt_render uses worker threads)
+static void set_err(const std::string& s)
+{
+    g_err = s;
+    g_err_shared = s;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                \
+            return e_ == cudaErrorMemoryAllocation ? IPT_ERR_OUT_OF_MEMORY : IPT_ERR_CUDA;              \
+        }                                                                                               \
+    } while (0)
+
+extern "C" int ipt_abi_version(void) { return IPT_ABI_VERSION; }
+extern "C" const char* ipt_last_error(void) { return g_err.empty() ? g_err_shared.c_str() : g_err.c_str(); }
+
+extern "C" int ipt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* ipt_device_name(int device)
+{
+    static thread_local char name[256];
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return ""; }
+    std::snprintf(name, sizeof(name), "%s", prop.name);
+    return name;
+}
+
+// Static interleaved tile schedule: diagonal interleave, so every tile row and every tile column is spread over
+// all ranks (the literal 4K config puts all the work in the middle third of the frame).
+extern "C" uint32_t ipt_tile_owner(uint32_t tile_x, uint32_t tile_y, uint32_t /*tiles_x*/, uint32_t world)
+{
+    return world <= 1 ? 0u : (tile_x + tile_y) % world;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+struct ipt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // scene
+    bool have_scene = false;
+    uint32_t W = 0, H = 0, n_slots = 0, n_spheres = 0, n_objects = 0, n_nodes = 0;
+    double cam[9] = {0};
+    double max_emission = 0, max_color = 0;
+    void *geom32 = nullptr, *geom64 = nullptr, *mat32 = nullptr, *mat64 = nullptr;
+    uint32_t* slot_obj = nullptr;
+    float4* nodes = nullptr;
+    // render state
+    uint4* q[2] = {nullptr, nullptr};
+    size_t q_bytes = 0;
+    uint32_t* counters = nullptr;
+    unsigned long long* traced = nullptr;
+    unsigned long long* frame = nullptr;
+    size_t frame_pixels = 0;
+    float* out32 = nullptr;
+    double* out64 = nullptr;
+    float* gather32 = nullptr;   // where resolve writes (own frame unless a gather target is set)
+    double* gather64 = nullptr;
+    void* ipc_mapped = nullptr;
+    uint32_t* tile_ids = nullptr;
+    size_t tile_cap = 0;
+    std::vector<uint32_t> tile_host;
+    uint32_t tile_key[5] = {0, 0, 0, 0, 0};
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    ipt_stats last = {};
+};
+
+static int ensure_pinned(ipt_ctx* c, size_t bytes)
+{
+    if (c->pinned_bytes >= bytes) return IPT_OK;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr; c->pinned_bytes = 0;
+    CK(cudaMallocHost(&c->pinned, bytes));
+    c->pinned_bytes = bytes;
+    return IPT_OK;
+}
+
+extern "C" ipt_ctx* ipt_ctx_create(int device)
+{
+    int n = ipt_device_count();
+    if (n <= 0) { set_err("CUDA capable device not found! Cannot continue"); return nullptr; }
+    if (device < 0 || device >= n) { set_err("ipt_ctx_create: no such device"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); cudaGetLastError(); return nullptr; }
+    ipt_ctx* c = new ipt_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 8) != cudaSuccess) {
+        set_err(std::string("ipt_ctx_create: ") + cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    return c;
+}
+
+static void free_scene(ipt_ctx* c)
+{
+    cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes);
+    c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr;
+    c->have_scene = false;
+}
+
+extern "C" void ipt_ctx_destroy(ipt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
+    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->tile_ids);
+    if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+// Host -> device copy of the scene.  Builds the slot arrays (BVH leaf order, or spheres then rectangles), the
+// fp32 and fp64 copies, and the packed BVH nodes in one pinned staging buffer, then issues the copies.
+extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
+{
+    if (!c || !s) { set_err("ipt_ctx_set_scene: null argument"); return IPT_ERR_BAD_ARGUMENT; }
+    if (s->n_objects == 0 || s->n_objects != s->n_spheres + s->n_rects || s->width == 0 || s->height == 0) {
+        set_err("ipt_ctx_set_scene: empty or inconsistent scene");
+        return IPT_ERR_BAD_ARGUMENT;
+    }
+    if (s->n_objects >= 0x7FFFFFFFu) { set_err("ipt_ctx_set_scene: too many objects"); return IPT_ERR_BAD_ARGUMENT; }
+    const bool bvh = s->n_bvh_nodes > 0;
+    if (bvh && (s->n_bvh_slots != s->n_objects || !s->bvh_nodes || !s->bvh_slot_prim)) {
+        set_err("ipt_ctx_set_scene: BVH must reference every primitive exactly once");
+        return IPT_ERR_BAD_ARGUMENT;
+    }
+    CK(cudaSetDevice(c->device));
+    cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+    CK(cudaEventRecord(e0, c->stream));
+    const uint32_t n = s->n_objects, ns = s->n_spheres;
+    const size_t slot_pad = ((size_t)n + 3) / 4 * 4;
+    const size_t b_geom64 = (size_t)n * 16 * 8, b_geom32 = (size_t)n * 16 * 4, b_mat64 = (size_t)n * 8 * 8, b_mat32 = (size_t)n * 8 * 4;
+    const size_t b_slot = slot_pad * 4, b_nodes = (size_t)s->n_bvh_nodes * 64;
+    const size_t total = b_geom64 + b_geom32 + b_mat64 + b_mat32 + b_slot + b_nodes;
+    int rc = ensure_pinned(c, total);
+    if (rc) return rc;
+    char* pin = (char*)c->pinned;
+    double* g64 = (double*)pin;
+    float* g32 = (float*)(pin + b_geom64);
+    double* m64 = (double*)(pin + b_geom64 + b_geom32);
+    float* m32 = (float*)(pin + b_geom64 + b_geom32 + b_mat64);
+    uint32_t* so = (uint32_t*)(pin + b_geom64 + b_geom32 + b_mat64 + b_mat32);
+    float* nd = (float*)(pin + b_geom64 + b_geom32 + b_mat64 + b_mat32 + b_slot);
+    std::memset(g64, 0, b_geom64);
+    std::memset(so, 0xFF, b_slot);
+    for (uint32_t slot = 0; slot < n; slot++) {
+        uint32_t prim = bvh ? s->bvh_slot_prim[slot] : (slot < ns ? slot : (RECT_BIT | (slot - ns)));
+        const bool rect = (prim & RECT_BIT) != 0;
+        const uint32_t idx = prim & ~RECT_BIT;
+        if ((rect && idx >= s->n_rects) || (!rect && idx >= ns)) { set_err("ipt_ctx_set_scene: bad BVH slot"); return IPT_ERR_BAD_ARGUMENT; }
+        double* g = g64 + (size_t)slot * 16;
+        if (rect) {
+            std::memcpy(g, s->rect_plane + 4 * (size_t)idx, 32);
+            std::memcpy(g + 4, s->rect_u + 4 * (size_t)idx, 32);
+            std::memcpy(g + 8, s->rect_v + 4 * (size_t)idx, 32);
+            std::memcpy(g + 12, s->rect_bounds + 4 * (size_t)idx, 32);
+            so[slot] = s->rect_object[idx] | RECT_BIT;
+        } else {
+            std::memcpy(g, s->sphere_cxyzr + 4 * (size_t)idx, 32);
+            so[slot] = s->sphere_object[idx];
+        }
+        if ((so[slot] & ~RECT_BIT) >= n) { set_err("ipt_ctx_set_scene: object index out of range"); return IPT_ERR_BAD_ARGUMENT; }
+    }
+    for (size_t i = 0; i < (size_t)n * 16; i++) g32[i] = (float)g64[i];
+    double maxE = 0, maxC = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        double* m = m64 + (size_t)k * 8;
+        bool anyE = false;
+        for (int j = 0; j < 3; j++) {
+            m[j] = s->mat_color[3 * (size_t)k + j];
+            m[4 + j] = s->mat_emission[3 * (size_t)k + j];
+            anyE = anyE || m[4 + j] != 0.0;
+            maxE = std::max(maxE, std::fabs(m[4 + j]));
+            maxC = std::max(maxC, std::fabs(m[j]));
+        }
+        m[3] = (double)s->mat_reflection[k];
+        m[7] = anyE ? 1.0 : 0.0;
+    }
+    for (size_t i = 0; i < (size_t)n * 8; i++) m32[i] = (float)m64[i];
+    for (uint32_t i = 0; i < s->n_bvh_nodes; i++) {
+        const ipt_bvh_node& b = s->bvh_nodes[i];
+        float* o = nd + (size_t)i * 16;
+        o[0] = b.lo0[0]; o[1] = b.lo0[1]; o[2] = b.lo0[2]; o[3] = b.hi0[0];
+        o[4] = b.hi0[1]; o[5] = b.hi0[2]; o[6] = b.lo1[0]; o[7] = b.lo1[1];
+        o[8] = b.lo1[2]; o[9] = b.hi1[0]; o[10] = b.hi1[1]; o[11] = b.hi1[2];
+        int32_t ch[2];
+        for (int k = 0; k < 2; k++) {
+            if (b.child[k] >= 0) {
+                if ((uint32_t)b.child[k] >= s->n_bvh_nodes) { set_err("ipt_ctx_set_scene: bad BVH child"); return IPT_ERR_BAD_ARGUMENT; }
+                ch[k] = b.child[k];
+            } else {
+                const uint32_t first = (uint32_t)(~b.child[k]), cnt = b.count[k];
+                if (cnt < 1 || cnt > 16 || (size_t)first + cnt > n || first >= (1u << 27)) { set_err("ipt_ctx_set_scene: bad BVH leaf"); return IPT_ERR_BAD_ARGUMENT; }
+                ch[k] = ~(int32_t)((first << 4) | (cnt - 1));
+            }
+        }
+        std::memcpy(o + 12, ch, 8);
+        o[14] = 0; o[15] = 0;
+    }
+    free_scene(c);
+    CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
+    CK(cudaMalloc(&c->mat64, b_mat64)); CK(cudaMalloc(&c->mat32, b_mat32));
+    CK(cudaMalloc(&c->slot_obj, b_slot));
+    if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
+    CK(cudaMemcpyAsync(c->geom64, g64, b_geom64, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->geom32, g32, b_geom32, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->mat64, m64, b_mat64, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
+    if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->last.upload_ms = ms;
+    c->last.h2d_bytes = total;
+    c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
+    std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
+    c->max_emission = maxE; c->max_color = maxC;
+    c->have_scene = true;
+    // frame buffers
+    const size_t px = (size_t)c->W * c->H;
+    if (px != c->frame_pixels) {
+        if (c->gather32 == c->out32) { c->gather32 = nullptr; c->gather64 = nullptr; }
+        cudaFree(c->frame); cudaFree(c->out32); cudaFree(c->out64);
+        c->frame = nullptr; c->out32 = nullptr; c->out64 = nullptr; c->frame_pixels = 0;
+        CK(cudaMalloc(&c->frame, px * 24)); CK(cudaMalloc(&c->out32, px * 12)); CK(cudaMalloc(&c->out64, px * 24));
+        CK(cudaMemsetAsync(c->out32, 0, px * 12, c->stream)); CK(cudaMemsetAsync(c->out64, 0, px * 24, c->stream));
+        c->frame_pixels = px;
+        if (!c->gather32) { c->gather32 = c->out32; c->gather64 = c->out64; }
+    }
+    return IPT_OK;
+}
+
+template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
+
+template <typename R, int MODE, bool FIRST>
+static int launch_bounce(ipt_ctx* c, const KParams<R>& kp, size_t smem, int* grid_cache)
+{
+    auto kern = k_bounce<R, MODE, FIRST>;
+    if (*grid_cache == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, smem));
+        if (per_sm < 1) { set_err("kernel does not fit on an SM (scene too large for shared memory: build a BVH)"); return IPT_ERR_BAD_ARGUMENT; }
+        *grid_cache = per_sm * c->sm_count;
+    }
+    kern<<<*grid_cache, BLOCK_THREADS, smem, c->stream>>>(kp);
+    return IPT_OK;
+}
+
+static int build_tiles(ipt_ctx* c, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t world, uint32_t* tiles_x_out)
+{
+    const uint32_t tiles_x = (c->W + tile_w - 1) / tile_w, tiles_y = (c->H + tile_h - 1) / tile_h;
+    *tiles_x_out = tiles_x;
+    const uint32_t key[5] = {tile_w, tile_h, rank, world, tiles_x * 65536u + tiles_y};
+    if (std::memcmp(key, c->tile_key, sizeof(key)) == 0 && c->tile_ids) return IPT_OK;
+    c->tile_host.clear();
+    for (uint32_t ty = 0; ty < tiles_y; ty++)
+        for (uint32_t tx = 0; tx < tiles_x; tx++)
+            if (ipt_tile_owner(tx, ty, tiles_x, world) == rank) c->tile_host.push_back(ty * tiles_x + tx);
+    const size_t nb = std::max<size_t>(c->tile_host.size(), 1) * 4;
+    if (nb > c->tile_cap) {
+        cudaFree(c->tile_ids); c->tile_ids = nullptr; c->tile_cap = 0;
+        CK(cudaMalloc(&c->tile_ids, nb));
+        c->tile_cap = nb;
+    }
+    if (!c->tile_host.empty())
+        CK(cudaMemcpyAsync(c->tile_ids, c->tile_host.data(), c->tile_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // tile_host may be rebuilt by the next call
+    std::memcpy(c->tile_key, key, sizeof(key));
+    return IPT_OK;
+}
+
+template <typename R>
+static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint32_t tile_h, uint32_t tiles_x, ipt_stats* st)
+{
+    const bool bvh = c->n_nodes > 0;
+    KParams<R> kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.sc.geom = (const R4<R>*)(sizeof(R) == 4 ? c->geom32 : c->geom64);
+    kp.sc.mat = (const R4<R>*)(sizeof(R) == 4 ? c->mat32 : c->mat64);
+    kp.sc.slot_obj = c->slot_obj;
+    kp.sc.n_slots = c->n_slots; kp.sc.n_spheres = c->n_spheres; kp.sc.n_objects = c->n_objects;
+    kp.sc.nodes = c->nodes; kp.sc.n_nodes = c->n_nodes;
+    // camera: vecZ = normalize(direction x orientation) in fp64 on the host (RenderController.cu:39)
+    const double* D = c->cam + 3; const double* X = c->cam + 6;
+    double Z[3] = {D[1] * X[2] - D[2] * X[1], D[2] * X[0] - D[0] * X[2], D[0] * X[1] - D[1] * X[0]};
+    const double zl = 1.0 / std::sqrt(Z[0] * Z[0] + Z[1] * Z[1] + Z[2] * Z[2]);
+    for (double& z : Z) z *= zl;
+    kp.camO = hv<R>(c->cam); kp.camD = hv<R>(D); kp.camX = hv<R>(X); kp.camZ = hv<R>(Z);
+    kp.fov = (R)0.0009f;
+    kp.W = c->W; kp.H = c->H; kp.spp = prm.samples; kp.maxDepth = prm.max_depth;
+    kp.flags = prm.flags;
+    kp.key0 = (uint32_t)prm.seed; kp.key1 = (uint32_t)(prm.seed >> 32);
+    kp.tile_ids = c->tile_ids; kp.n_tiles_local = (uint32_t)c->tile_host.size(); kp.tiles_x = tiles_x;
+    kp.tile_w = tile_w; kp.tile_h = tile_h; kp.mt_x = tile_w / 8; kp.mt_per_tile = (tile_w / 8) * (tile_h / 4);
+    kp.counters = c->counters; kp.traced = c->traced; kp.frame = c->frame;
+
+    // fixed-point scale: largest power of two such that spp * (bound on one sample's radiance) fits in 62 bits
+    bool float_accum = (prm.flags & IPT_FLAG_FLOAT_ACCUM) != 0;
+    double scale = 1.0;
+    {
+        const double mc = std::max(1.0, c->max_color);
+        double bound = std::max(c->max_emission, 1e-30) * 2.0 * (prm.max_depth + 1.0) * std::pow(mc, (double)prm.max_depth);
+        bound *= (double)prm.samples;
+        const int bits = 62 - (int)std::ceil(std::log2(bound));
+        if (!std::isfinite(bound) || bits < 16) float_accum = true;
+        else scale = std::ldexp(1.0, std::min(bits, 40));
+    }
+    if (float_accum) kp.flags |= IPT_FLAG_FLOAT_ACCUM; else kp.flags &= ~IPT_FLAG_FLOAT_ACCUM;
+    kp.fixed_scale = scale;
+
+    // batches
+    const uint64_t total_mt = (uint64_t)kp.n_tiles_local * kp.mt_per_tile;
+    const uint64_t total_groups = total_mt * prm.samples;
+    uint64_t B = prm.batch_samples ? prm.batch_samples : (1u << 22);
+    B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
+    B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
+    const uint32_t cap = (uint32_t)(2 * B);
+    const size_t q_bytes = (size_t)cap * 16 * QPlanes<R>::N;
+    if (q_bytes > c->q_bytes) {
+        cudaFree(c->q[0]); cudaFree(c->q[1]); c->q[0] = c->q[1] = nullptr; c->q_bytes = 0;
+        CK(cudaMalloc(&c->q[0], q_bytes)); CK(cudaMalloc(&c->q[1], q_bytes));
+        c->q_bytes = q_bytes;
+    }
+    const size_t smem = bvh ? (size_t)std::min<uint32_t>(c->n_nodes, BVH_TOP_NODES) * 64
+                            : ((size_t)c->n_slots * 4 + (size_t)c->n_objects * 2) * sizeof(R4<R>) + ((size_t)c->n_slots + 3) / 4 * 16;
+    if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
+
+    CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
+    CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    int grid_first = 0, grid_next = 0;
+    uint64_t launches = 0, batches = 0;
+    const uint64_t groups_per_batch = B / 32;
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += groups_per_batch) {
+        kp.base_mt = (uint32_t)(g0 / prm.samples);
+        kp.base_sample = (uint32_t)(g0 % prm.samples);
+        kp.n_first = (uint32_t)(std::min<uint64_t>(groups_per_batch, total_groups - g0) * 32);
+        CK(cudaMemsetAsync(c->counters, 0, N_COUNTERS * sizeof(uint32_t), c->stream));
+        for (uint32_t d = 0; d < prm.max_depth; d++) {
+            kp.depth = d;
+            kp.qin = Queue{c->q[(d + 1) & 1], cap};
+            kp.qout = Queue{c->q[d & 1], cap};
+            int rc;
+            if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
+            else rc = bvh ? launch_bounce<R, MODE_BVH, false>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false>(c, kp, smem, &grid_next);
+            if (rc) return rc;
+            launches++;
+        }
+        batches++;
+    }
+    // resolve (and gather: dst may be a peer GPU's frame)
+    ResolveParams rp;
+    rp.frame = c->frame; rp.dst32 = c->gather32; rp.dst64 = c->gather64; rp.tile_ids = c->tile_ids;
+    rp.n_tiles_local = kp.n_tiles_local; rp.tiles_x = tiles_x; rp.tile_w = tile_w; rp.tile_h = tile_h; rp.W = c->W; rp.H = c->H;
+    rp.inv = 1.0 / (scale * (double)prm.samples); rp.float_accum = float_accum ? 1u : 0u;
+    if (float_accum) rp.inv = 1.0 / (double)prm.samples;
+    k_resolve<<<c->sm_count * 4, 256, 0, c->stream>>>(rp);
+    launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    unsigned long long traced = 0;
+    CK(cudaMemcpy(&traced, c->traced, 8, cudaMemcpyDeviceToHost));
+    c->last.render_ms = ms; c->last.traced_bounces = traced; c->last.kernel_launches = launches; c->last.batches = batches;
+    uint64_t npx = 0;
+    for (uint32_t t : c->tile_host) {
+        const uint32_t x0 = (t % tiles_x) * tile_w, z0 = (t / tiles_x) * tile_h;
+        npx += (uint64_t)(std::min(c->W, x0 + tile_w) - x0) * (std::min(c->H, z0 + tile_h) - z0);
+    }
+    c->last.samples = npx * prm.samples;
+    if (st) *st = c->last;
+    return IPT_OK;
+}
+
+extern "C" int ipt_ctx_render(ipt_ctx* c, const ipt_params* prm, ipt_stats* st)
+{
+    if (!c || !prm) { set_err("ipt_ctx_render: null argument"); return IPT_ERR_BAD_ARGUMENT; }
+    if (!c->have_scene) { set_err("ipt_ctx_render: no scene set"); return IPT_ERR_BAD_ARGUMENT; }
+    if (prm->samples < 1 || prm->samples > 65535 || prm->max_depth < 1 || prm->max_depth > 255) {
+        set_err("ipt_ctx_render: samples must be 1..65535 and max_depth 1..255");
+        return IPT_ERR_BAD_ARGUMENT;
+    }
+    const uint32_t tile_w = prm->tile_w ? prm->tile_w : 64, tile_h = prm->tile_h ? prm->tile_h : 32;
+    const uint32_t world = prm->world ? prm->world : 1;
+    if (tile_w % 8 || tile_h % 4 || prm->rank >= world) { set_err("ipt_ctx_render: tile size must be a multiple of 8x4, rank < world"); return IPT_ERR_BAD_ARGUMENT; }
+    CK(cudaSetDevice(c->device));
+    uint32_t tiles_x = 0;
+    int rc = build_tiles(c, tile_w, tile_h, prm->rank, world, &tiles_x);
+    if (rc) return rc;
+    return (prm->flags & IPT_FLAG_FP64) ? render_typed<double>(c, *prm, tile_w, tile_h, tiles_x, st)
+                                        : render_typed<float>(c, *prm, tile_w, tile_h, tiles_x, st);
+}
+
+extern "C" int ipt_ctx_download(ipt_ctx* c, float* out32, double* out64)
+{
+    if (!c || !c->have_scene) { set_err("ipt_ctx_download: no frame"); return IPT_ERR_BAD_ARGUMENT; }
+    CK(cudaSetDevice(c->device));
+    const size_t px = c->frame_pixels;
+    const size_t need = (out32 ? px * 12 : 0) + (out64 ? px * 24 : 0);
+    int rc = ensure_pinned(c, std::max<size_t>(need, 16));
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    char* pin = (char*)c->pinned;
+    if (out32) CK(cudaMemcpyAsync(pin, c->out32, px * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (out64) CK(cudaMemcpyAsync(pin + (out32 ? px * 12 : 0), c->out64, px * 24, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (out32) std::memcpy(out32, pin, px * 12);
+    if (out64) std::memcpy(out64, pin + (out32 ? px * 12 : 0), px * 24);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last.download_ms = ms;
+    c->last.d2h_bytes = need;
+    return IPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ gather targets
+extern "C" int ipt_ctx_export_frame(ipt_ctx* c, void* handle64)
+{
+    if (!c || !c->out32 || !handle64) { set_err("ipt_ctx_export_frame: no frame"); return IPT_ERR_BAD_ARGUMENT; }
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->out32));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+    return IPT_OK;
+}
+
+extern "C" int ipt_ctx_set_gather_target_ipc(ipt_ctx* c, const void* handle64)
+{
+    if (!c || !handle64) { set_err("ipt_ctx_set_gather_target_ipc: null argument"); return IPT_ERR_BAD_ARGUMENT; }
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
+    c->ipc_mapped = p;
+    c->gather32 = (float*)p;
+    c->gather64 = nullptr;   // the fp32 frame is what crosses NVLink between processes
+    return IPT_OK;
+}
+
+extern "C" int ipt_ctx_set_gather_target(ipt_ctx* c, ipt_ctx* owner)
+{
+    if (!c || !owner || !owner->out32) { set_err("ipt_ctx_set_gather_target: owner has no frame"); return IPT_ERR_BAD_ARGUMENT; }
+    if (c == owner || c->device == owner->device) { c->gather32 = owner->out32; c->gather64 = owner->out64; return IPT_OK; }
+    CK(cudaSetDevice(c->device));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, c->device, owner->device));
+    if (!can) { set_err("no peer access between the two devices"); return IPT_ERR_CUDA; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_err(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return IPT_ERR_CUDA; }
+    cudaGetLastError();
+    c->gather32 = owner->out32; c->gather64 = owner->out64;
+    return IPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one-shot render
+extern "C" int ipt_render(const ipt_scene* scene, const ipt_params* params, int n_gpus, float* out32, double* out64, ipt_stats* stats)
+{
+    if (!scene || !params) { set_err("ipt_render: null argument"); return IPT_ERR_BAD_ARGUMENT; }
+    const int ndev = ipt_device_count();
+    if (ndev <= 0) { set_err("CUDA capable device not found! Cannot continue"); return IPT_ERR_NO_DEVICE; }
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > ndev || n_gpus > 8) { set_err("ipt_render: n_gpus exceeds the devices present (max 8)"); return IPT_ERR_BAD_ARGUMENT; }
+    std::vector<ipt_ctx*> ctx(n_gpus, nullptr);
+    std::vector<int> rcs(n_gpus, 0);
+    std::vector<ipt_stats> sts(n_gpus);
+    int rc = IPT_OK;
+    for (int g = 0; g < n_gpus && rc == IPT_OK; g++) {
+        ctx[g] = ipt_ctx_create(g);
+        if (!ctx[g]) rc = IPT_ERR_CUDA;
+    }
+    bool host_merge = false;
+    if (rc == IPT_OK) {
+        // upload (one host thread per GPU), set gather targets, render
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpus; g++) th.emplace_back([&, g] { rcs[g] = ipt_ctx_set_scene(ctx[g], scene); });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < n_gpus; g++) if (rcs[g]) rc = rcs[g];
+    }
+    if (rc == IPT_OK) {
+        for (int g = 1; g < n_gpus; g++)
+            if (ipt_ctx_set_gather_target(ctx[g], ctx[0]) != IPT_OK) host_merge = true;
+        if (host_merge) for (int g = 1; g < n_gpus; g++) { ctx[g]->gather32 = ctx[g]->out32; ctx[g]->gather64 = ctx[g]->out64; }
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpus; g++)
+            th.emplace_back([&, g] {
+                ipt_params p = *params;
+                p.rank = (uint32_t)g; p.world = (uint32_t)n_gpus;
+                rcs[g] = ipt_ctx_render(ctx[g], &p, &sts[g]);
+            });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < n_gpus; g++) if (rcs[g]) rc = rcs[g];
+    }
+    if (rc == IPT_OK && (out32 || out64)) {
+        rc = ipt_ctx_download(ctx[0], out32, out64);
+        if (rc == IPT_OK && host_merge && n_gpus > 1) {
+            // no peer access: fetch every other GPU's frame and copy its tiles on the host
+            const size_t px = (size_t)scene->width * scene->height;
+            std::vector<float> t32(out32 ? px * 3 : 0);
+            std::vector<double> t64(out64 ? px * 3 : 0);
+            const uint32_t tw = params->tile_w ? params->tile_w : 64, thh = params->tile_h ? params->tile_h : 32;
+            const uint32_t tiles_x = (scene->width + tw - 1) / tw;
+            for (int g = 1; g < n_gpus && rc == IPT_OK; g++) {
+                rc = ipt_ctx_download(ctx[g], out32 ? t32.data() : nullptr, out64 ? t64.data() : nullptr);
+                for (uint32_t z = 0; z < scene->height && rc == IPT_OK; z++)
+                    for (uint32_t x = 0; x < scene->width; x++)
+                        if (ipt_tile_owner(x / tw, z / thh, tiles_x, n_gpus) == (uint32_t)g) {
+                            const size_t i = ((size_t)z * scene->width + x) * 3;
+                            for (int k = 0; k < 3; k++) { if (out32) out32[i + k] = t32[i + k]; if (out64) out64[i + k] = t64[i + k]; }
+                        }
+            }
+        }
+    }
+    if (rc == IPT_OK && stats) {
+        *stats = sts[0];
+        stats->samples = 0; stats->traced_bounces = 0; stats->kernel_launches = 0; stats->batches = 0; stats->render_ms = 0;
+        for (int g = 0; g < n_gpus; g++) {
+            stats->samples += sts[g].samples; stats->traced_bounces += sts[g].traced_bounces;
+            stats->kernel_launches += sts[g].kernel_launches; stats->batches += sts[g].batches;
+            stats->render_ms = std::max(stats->render_ms, sts[g].render_ms);
+            stats->per_gpu_render_ms[g] = sts[g].render_ms; stats->per_gpu_bounces[g] = sts[g].traced_bounces;
+        }
+        stats->download_ms = ctx[0]->last.download_ms; stats->d2h_bytes = ctx[0]->last.d2h_bytes;
+    }
+    for (int g = 0; g < n_gpus; g++) ipt_ctx_destroy(ctx[g]);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ trace (tests)
+extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_t flags, int32_t* out_obj, double* out_t)
+{
+    if (!c || !c->have_scene || !rays || !out_obj || !out_t) { set_err("ipt_ctx_trace: bad argument"); return IPT_ERR_BAD_ARGUMENT; }
+    if (n == 0) return IPT_OK;
+    CK(cudaSetDevice(c->device));
+    double* d_rays = nullptr; int32_t* d_obj = nullptr; double* d_t = nullptr;
+    CK(cudaMalloc(&d_rays, (size_t)n * 48)); CK(cudaMalloc(&d_obj, (size_t)n * 4)); CK(cudaMalloc(&d_t, (size_t)n * 8));
+    CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
+    const bool bvh = c->n_nodes > 0, f64 = (flags & IPT_FLAG_FP64) != 0;
+    const size_t esz = f64 ? 32 : 16;
+    const size_t smem = bvh ? (size_t)std::min<uint32_t>(c->n_nodes, BVH_TOP_NODES) * 64 : (size_t)c->n_slots * 4 * esz + ((size_t)c->n_slots + 3) / 4 * 16;
+    const int grid = c->sm_count * 2;
+    auto fill = [&](auto& sv, auto tag) {
+        using R = decltype(tag);
+        sv.geom = (const R4<R>*)(f64 ? c->geom64 : c->geom32); sv.mat = (const R4<R>*)(f64 ? c->mat64 : c->mat32);
+        sv.slot_obj = c->slot_obj; sv.n_slots = c->n_slots; sv.n_spheres = c->n_spheres; sv.n_objects = c->n_objects;
+        sv.nodes = c->nodes; sv.n_nodes = c->n_nodes;
+    };
+    if (f64) {
+        SceneView<double> sv; fill(sv, double());
+        if (bvh) { CK(cudaFuncSetAttribute(k_trace<double, MODE_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_trace<double, MODE_BVH><<<grid, BLOCK_THREADS, smem, c->stream>>>(sv, d_rays, n, d_obj, d_t); }
+        else { CK(cudaFuncSetAttribute(k_trace<double, MODE_BRUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_trace<double, MODE_BRUTE><<<grid, BLOCK_THREADS, smem, c->stream>>>(sv, d_rays, n, d_obj, d_t); }
+    } else {
+        SceneView<float> sv; fill(sv, float());
+        if (bvh) { CK(cudaFuncSetAttribute(k_trace<float, MODE_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_trace<float, MODE_BVH><<<grid, BLOCK_THREADS, smem, c->stream>>>(sv, d_rays, n, d_obj, d_t); }
+        else { CK(cudaFuncSetAttribute(k_trace<float, MODE_BRUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_trace<float, MODE_BRUTE><<<grid, BLOCK_THREADS, smem, c->stream>>>(sv, d_rays, n, d_obj, d_t); }
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_obj, d_obj, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_t, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_rays); cudaFree(d_obj); cudaFree(d_t);
+    return IPT_OK;
+}

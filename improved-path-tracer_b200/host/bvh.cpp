@@ -1,0 +1,170 @@
+// bvh.cpp — host BVH builder (binned SAH, 2-wide, 64-byte nodes emitted breadth-first).
+// New work: the reference has no acceleration structure, its nearest hit is a linear scan over all objects
+// (Renderer.cu:227-243).  The BVH must return the same nearest hit as that scan, so boxes are conservative:
+// padded for the +-5e-5 edge tolerance of Plane.cu:87-100, for the MARGIN = 1e-4 near-surface roots of
+// Sphere.cu:36-37 and for fp32 rounding of the bounds themselves.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <queue>
+
+#include "host_scene.hpp"
+
+namespace {
+
+struct Box {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    void grow(const double* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    void grow(const Box& b) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    double area() const
+    {
+        const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return (x < 0 || y < 0 || z < 0) ? 0.0 : 2 * (x * y + y * z + z * x);
+    }
+};
+
+struct Prim { Box box; double c[3]; uint32_t ref; };
+
+struct BNode { Box box; int left = -1, right = -1; uint32_t first = 0, count = 0; };
+
+struct Builder {
+    std::vector<Prim>& prims;
+    std::vector<BNode> nodes;
+    uint32_t leaf_size;
+
+    int build(uint32_t first, uint32_t count)
+    {
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        Box box, cb;
+        for (uint32_t i = first; i < first + count; i++) { box.grow(prims[i].box); cb.grow(prims[i].c); }
+        nodes[id].box = box;
+        if (count <= leaf_size) { nodes[id].first = first; nodes[id].count = count; return id; }
+        // binned SAH over the centroid bounds, 16 bins per axis
+        constexpr int NB = 16;
+        int bestAxis = -1, bestSplit = -1;
+        double bestCost = DBL_MAX;
+        for (int ax = 0; ax < 3; ax++) {
+            const double ext = cb.hi[ax] - cb.lo[ax];
+            if (!(ext > 0)) continue;
+            Box bb[NB]; uint32_t bc[NB] = {0};
+            const double k = NB * (1 - 1e-9) / ext;
+            for (uint32_t i = first; i < first + count; i++) {
+                const int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cb.lo[ax]) * k)));
+                bb[b].grow(prims[i].box); bc[b]++;
+            }
+            double rightArea[NB]; uint32_t rightCnt[NB];
+            Box acc; uint32_t cnt = 0;
+            for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); cnt += bc[b]; rightArea[b] = acc.area(); rightCnt[b] = cnt; }
+            acc = Box(); cnt = 0;
+            for (int b = 0; b < NB - 1; b++) {
+                acc.grow(bb[b]); cnt += bc[b];
+                if (cnt == 0 || rightCnt[b + 1] == 0) continue;
+                const double cost = acc.area() * cnt + rightArea[b + 1] * rightCnt[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b; }
+            }
+        }
+        uint32_t mid;
+        if (bestAxis < 0) {
+            mid = first + count / 2;   // all centroids coincide: split by index
+        } else {
+            const double ext = cb.hi[bestAxis] - cb.lo[bestAxis], k = NB * (1 - 1e-9) / ext, lo = cb.lo[bestAxis];
+            auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
+                return std::min(NB - 1, std::max(0, (int)((p.c[bestAxis] - lo) * k))) <= bestSplit;
+            });
+            mid = (uint32_t)(it - prims.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        const int l = build(first, mid - first);
+        const int r = build(mid, first + count - mid);
+        nodes[id].left = l; nodes[id].right = r;
+        return id;
+    }
+};
+
+inline float down(double v, double pad) { return std::nextafterf((float)(v - pad), -INFINITY); }
+inline float up(double v, double pad) { return std::nextafterf((float)(v + pad), INFINITY); }
+
+void put_box(const Box& b, float* lo, float* hi)
+{
+    for (int k = 0; k < 3; k++) {
+        const double pad = 2e-3 + 2e-6 * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+        lo[k] = down(b.lo[k], pad); hi[k] = up(b.hi[k], pad);
+    }
+}
+
+}  // namespace
+
+extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_t brute_max)
+{
+    if (!s) return -1;
+    s->bvh_nodes.clear(); s->bvh_slot_prim.clear();
+    const uint32_t ns = (uint32_t)s->sphere_object.size(), nr = (uint32_t)s->rect_object.size(), n = ns + nr;
+    if (n <= brute_max) { s->refresh_view(); return 0; }
+    leaf_size = std::min(16u, std::max(1u, leaf_size));
+    std::vector<Prim> prims(n);
+    for (uint32_t i = 0; i < ns; i++) {
+        const double* c = &s->sphere_cxyzr[4 * (size_t)i];
+        const double r = std::fabs(c[3]);
+        Prim& p = prims[i];
+        for (int k = 0; k < 3; k++) { p.box.lo[k] = c[k] - r; p.box.hi[k] = c[k] + r; p.c[k] = c[k]; }
+        p.ref = i;
+    }
+    for (uint32_t j = 0; j < nr; j++) {
+        const double *c = &s->rect_center[3 * (size_t)j], *N = &s->rect_north[3 * (size_t)j], *E = &s->rect_east[3 * (size_t)j];
+        Prim& p = prims[ns + j];
+        for (int sn = -1; sn <= 1; sn += 2)
+            for (int se = -1; se <= 1; se += 2) {
+                double q[3];
+                for (int k = 0; k < 3; k++) q[k] = c[k] + sn * N[k] + se * E[k];
+                p.box.grow(q);
+            }
+        for (int k = 0; k < 3; k++) p.c[k] = c[k];
+        p.ref = 0x80000000u | j;
+    }
+    Builder b{prims, {}, leaf_size};
+    b.nodes.reserve(2 * (size_t)n / leaf_size + 16);
+    const int root = b.build(0, n);
+    s->bvh_slot_prim.resize(n);
+    for (uint32_t i = 0; i < n; i++) s->bvh_slot_prim[i] = prims[i].ref;
+
+    auto leaf_code = [](const BNode& nd) { return ~(int32_t)nd.first; };
+    if (b.nodes[root].left < 0) {
+        // the whole scene is one leaf: a root whose second child is an empty (inverted) box
+        ipt_bvh_node o;
+        std::memset(&o, 0, sizeof(o));
+        put_box(b.nodes[root].box, o.lo0, o.hi0);
+        for (int k = 0; k < 3; k++) { o.lo1[k] = FLT_MAX; o.hi1[k] = -FLT_MAX; }
+        o.child[0] = leaf_code(b.nodes[root]); o.count[0] = b.nodes[root].count;
+        o.child[1] = ~0; o.count[1] = 1;
+        s->bvh_nodes.push_back(o);
+        s->refresh_view();
+        return 1;
+    }
+    // breadth-first numbering of the inner nodes: the top levels get the lowest indices (they are staged in shared memory)
+    std::vector<int> order, index(b.nodes.size(), -1);
+    std::queue<int> q;
+    q.push(root);
+    while (!q.empty()) {
+        const int id = q.front(); q.pop();
+        index[id] = (int)order.size();
+        order.push_back(id);
+        const BNode& nd = b.nodes[id];
+        if (b.nodes[nd.left].left >= 0) q.push(nd.left);
+        if (b.nodes[nd.right].left >= 0) q.push(nd.right);
+    }
+    s->bvh_nodes.resize(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        const BNode& nd = b.nodes[order[i]];
+        ipt_bvh_node& o = s->bvh_nodes[i];
+        std::memset(&o, 0, sizeof(o));
+        const BNode &l = b.nodes[nd.left], &r = b.nodes[nd.right];
+        put_box(l.box, o.lo0, o.hi0);
+        put_box(r.box, o.lo1, o.hi1);
+        if (l.left >= 0) o.child[0] = index[nd.left]; else { o.child[0] = leaf_code(l); o.count[0] = l.count; }
+        if (r.left >= 0) o.child[1] = index[nd.right]; else { o.child[1] = leaf_code(r); o.count[1] = r.count; }
+    }
+    s->refresh_view();
+    return (int)s->bvh_nodes.size();
+}

@@ -1,0 +1,316 @@
+// scene_loader.cpp — scene ingest of the host layer: the reference's scenes/*.json schema (SceneData.cpp:61-225)
+// -> flattened structure-of-arrays buffers (include/ipt_abi.h: ipt_scene).
+//
+// The reference parses with nlohmann::json into an AoS std::vector<ObjectData> and every CUDA thread then rebuilds
+// polymorphic objects from it (Renderer.cu:69-86, Plane.cu:32-45).  Here a small pull parser reads the file once
+// without building a DOM (a 1M-object scene is a ~200 MB file) and the per-rectangle constants are computed once,
+// in fp64, on the host.
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_scene.hpp"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ JSON pull parser
+struct Reader {
+    const char* p;
+    const char* end;
+    bool ok = true;
+
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    bool eat(char c) { ws(); if (p < end && *p == c) { p++; return true; } return false; }
+    char peek() { ws(); return p < end ? *p : '\0'; }
+    bool fail() { ok = false; return false; }
+
+    bool string(std::string& out)
+    {
+        out.clear();
+        if (!eat('"')) return fail();
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                if (++p >= end) return fail();
+                switch (*p) {
+                    case 'n': out += '\n'; break; case 't': out += '\t'; break; case 'r': out += '\r'; break;
+                    case 'b': out += '\b'; break; case 'f': out += '\f'; break;
+                    case 'u': out += '?'; p += (end - p > 4) ? 4 : 0; break;   // keys/types of the schema are ASCII
+                    default: out += *p;
+                }
+                p++;
+            } else out += *p++;
+        }
+        if (p >= end) return fail();
+        p++;
+        return true;
+    }
+    bool number(double& v)
+    {
+        ws();
+        const char* q = p;
+        if (q < end && *q == '+') q++;
+        auto r = std::from_chars(q, end, v);
+        if (r.ec != std::errc()) return fail();
+        p = r.ptr;
+        return true;
+    }
+    bool skip()   // any value
+    {
+        const char c = peek();
+        if (c == '"') { std::string s; return string(s); }
+        if (c == '{') {
+            p++;
+            if (eat('}')) return true;
+            do { std::string k; if (!string(k) || !eat(':') || !skip()) return fail(); } while (eat(','));
+            return eat('}') || fail();
+        }
+        if (c == '[') {
+            p++;
+            if (eat(']')) return true;
+            do { if (!skip()) return fail(); } while (eat(','));
+            return eat(']') || fail();
+        }
+        if (c == 't' && end - p >= 4 && !std::memcmp(p, "true", 4)) { p += 4; return true; }
+        if (c == 'f' && end - p >= 5 && !std::memcmp(p, "false", 5)) { p += 5; return true; }
+        if (c == 'n' && end - p >= 4 && !std::memcmp(p, "null", 4)) { p += 4; return true; }
+        double d;
+        return number(d);
+    }
+};
+
+struct Vec3Opt {
+    bool present = false;        // key exists
+    bool has[3] = {false, false, false};
+    double v[3] = {0, 0, 0};
+    bool valid2() const { return present && has[0] && has[1]; }   // validateVec3tor checks xx, yy (and yy again): SceneData.cpp:30-33
+    bool valid3() const { return valid2() && has[2]; }
+};
+
+bool read_vec(Reader& r, Vec3Opt& out)
+{
+    out = Vec3Opt();
+    out.present = true;
+    if (r.peek() != '{') return r.skip();   // present but not an object: fails validation later
+    r.p++;
+    if (r.eat('}')) return true;
+    do {
+        std::string k;
+        if (!r.string(k) || !r.eat(':')) return r.fail();
+        const int i = k == "xx" ? 0 : k == "yy" ? 1 : k == "zz" ? 2 : -1;
+        if (i >= 0 && (r.peek() == '-' || r.peek() == '+' || (r.peek() >= '0' && r.peek() <= '9'))) {
+            if (!r.number(out.v[i])) return false;
+            out.has[i] = true;
+        } else if (!r.skip()) return false;
+    } while (r.eat(','));
+    return r.eat('}') || r.fail();
+}
+
+struct ObjTmp {
+    bool hasType = false, typeIsString = false, hasRefl = false, hasRadius = false;
+    std::string type;
+    double refl = 0, radius = 0;
+    Vec3Opt color, emission, position, north, east;
+};
+
+bool read_object(Reader& r, ObjTmp& o)
+{
+    o = ObjTmp();
+    if (r.peek() != '{') return r.skip();
+    r.p++;
+    if (r.eat('}')) return true;
+    do {
+        std::string k;
+        if (!r.string(k) || !r.eat(':')) return r.fail();
+        if (k == "type") { o.hasType = true; if (r.peek() == '"') { o.typeIsString = true; if (!r.string(o.type)) return false; } else if (!r.skip()) return false; }
+        else if (k == "reflection") { o.hasRefl = true; const char c = r.peek(); if (c == '-' || (c >= '0' && c <= '9')) { if (!r.number(o.refl)) return false; } else if (!r.skip()) return false; }
+        else if (k == "radius") { o.hasRadius = true; const char c = r.peek(); if (c == '-' || (c >= '0' && c <= '9')) { if (!r.number(o.radius)) return false; } else if (!r.skip()) return false; }
+        else if (k == "color") { if (!read_vec(r, o.color)) return false; }
+        else if (k == "emission") { if (!read_vec(r, o.emission)) return false; }
+        else if (k == "position") { if (!read_vec(r, o.position)) return false; }
+        else if (k == "north") { if (!read_vec(r, o.north)) return false; }
+        else if (k == "east") { if (!read_vec(r, o.east)) return false; }
+        else if (!r.skip()) return false;
+    } while (r.eat(','));
+    return r.eat('}') || r.fail();
+}
+
+void msg(char* out, size_t n, const char* s)
+{
+    if (out && n) std::snprintf(out, n, "%s", s);
+}
+
+inline void norm3(double* v)   // Vec3.hpp:48-51: v * (1/sqrt(v.v))
+{
+    const double s = 1 / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] *= s; v[1] *= s; v[2] *= s;
+}
+inline void cross3(const double* a, const double* b, double* o)   // Vec3.hpp:69-72
+{
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+}  // namespace
+
+// Appends one primitive in object (JSON) order.  The rectangle constants restate Plane.cu:32-45 (normal) and solve
+// Plane.cu:87-100 for the hit position: with s = signed distance of the hit from the centre line along the in-plane
+// axis perpendicular to an edge pair, h = half the distance between the two edge lines and L = the side length the
+// reference compares against, the reference's test "d(bottom)+d(top) == L +- 1e-4" reads |L - 2 max(h,|s|)| <= 1e-4,
+// i.e. lo <= |s| <= hi with hi = (L+1e-4)/2 and lo = 0 when north is perpendicular to east (L = 2h), else (L-1e-4)/2.
+void ipt_host_scene::add(int type, double radius, const double* north, const double* east, const double* position,
+                         const double* emission, const double* color, int reflection)
+{
+    const uint32_t obj = (uint32_t)mat_reflection.size();
+    for (int i = 0; i < 3; i++) { mat_color.push_back(color[i]); mat_emission.push_back(emission[i]); }
+    mat_reflection.push_back(reflection);
+    if (type == 0) {
+        sphere_cxyzr.insert(sphere_cxyzr.end(), {position[0], position[1], position[2], radius});
+        sphere_object.push_back(obj);
+        return;
+    }
+    const double M = 1e-4;   // scene/cuda/objects/Constants.hpp:8
+    double n[3], u[3], v[3];
+    cross3(north, east, n);
+    norm3(n);                                   // Plane.cu:36
+    cross3(east, n, u); norm3(u);               // in-plane, perpendicular to east  ("vertical" distances, Plane.cu:89-92)
+    cross3(north, n, v); norm3(v);              // in-plane, perpendicular to north ("horizontal" distances, :94-97)
+    const double L_v = 2 * std::sqrt(dot3(north, north));   // distanceVertical_   = |bottomLeft - topLeft|     (:44)
+    const double L_h = 2 * std::sqrt(dot3(east, east));     // distanceHorizontal_ = |bottomLeft - bottomRight| (:43)
+    const double h_u = std::fabs(dot3(north, u)), h_v = std::fabs(dot3(east, v));
+    const double u_lo = (L_v - 2 * h_u <= M) ? 0.0 : (L_v - M) / 2, u_hi = (L_v + M) / 2;
+    const double v_lo = (L_h - 2 * h_v <= M) ? 0.0 : (L_h - M) / 2, v_hi = (L_h + M) / 2;
+    rect_plane.insert(rect_plane.end(), {n[0], n[1], n[2], dot3(n, position)});
+    rect_u.insert(rect_u.end(), {u[0], u[1], u[2], dot3(u, position)});
+    rect_v.insert(rect_v.end(), {v[0], v[1], v[2], dot3(v, position)});
+    rect_bounds.insert(rect_bounds.end(), {u_lo, u_hi, v_lo, v_hi});
+    rect_object.push_back(obj);
+    rect_center.insert(rect_center.end(), {position[0], position[1], position[2]});
+    rect_north.insert(rect_north.end(), {north[0], north[1], north[2]});
+    rect_east.insert(rect_east.end(), {east[0], east[1], east[2]});
+}
+
+void ipt_host_scene::refresh_view()
+{
+    view.n_spheres = (uint32_t)sphere_object.size();
+    view.n_rects = (uint32_t)rect_object.size();
+    view.n_objects = (uint32_t)mat_reflection.size();
+    view.sphere_cxyzr = sphere_cxyzr.data(); view.sphere_object = sphere_object.data();
+    view.rect_plane = rect_plane.data(); view.rect_u = rect_u.data(); view.rect_v = rect_v.data();
+    view.rect_bounds = rect_bounds.data(); view.rect_object = rect_object.data();
+    view.mat_color = mat_color.data(); view.mat_emission = mat_emission.data(); view.mat_reflection = mat_reflection.data();
+    view.n_bvh_nodes = (uint32_t)bvh_nodes.size(); view.n_bvh_slots = (uint32_t)bvh_slot_prim.size();
+    view.bvh_nodes = bvh_nodes.empty() ? nullptr : bvh_nodes.data();
+    view.bvh_slot_prim = bvh_slot_prim.empty() ? nullptr : bvh_slot_prim.data();
+}
+
+extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, size_t message_len)
+{
+    msg(message, message_len, "");
+    std::FILE* f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }   // SceneData.cpp:66-70
+    std::string buf;
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (sz > 0) { buf.resize((size_t)sz); if (std::fread(&buf[0], 1, (size_t)sz, f) != (size_t)sz) buf.clear(); }
+    std::fclose(f);
+
+    Reader r{buf.data(), buf.data() + buf.size()};
+    bool hasW = false, hasH = false, hasCamera = false, hasObjects = false, objectsIsArray = false;
+    double W = 0, H = 0;
+    Vec3Opt camDir, camPos, camOri;
+    std::vector<ObjTmp> objs;
+    // Malformed JSON makes the reference abort with an uncaught nlohmann exception; here it is a load failure.
+    bool parsed = r.eat('{');
+    if (parsed && !r.eat('}')) {
+        do {
+            std::string k;
+            if (!r.string(k) || !r.eat(':')) { parsed = false; break; }
+            if (k == "width") { hasW = true; if (!r.number(W)) { parsed = false; break; } }
+            else if (k == "height") { hasH = true; if (!r.number(H)) { parsed = false; break; } }
+            else if (k == "camera") {
+                hasCamera = true;
+                if (r.peek() != '{') { if (!r.skip()) { parsed = false; break; } continue; }
+                r.p++;
+                if (r.eat('}')) continue;
+                bool okc = true;
+                do {
+                    std::string ck;
+                    if (!r.string(ck) || !r.eat(':')) { okc = false; break; }
+                    if (ck == "direction") okc = read_vec(r, camDir);
+                    else if (ck == "position") okc = read_vec(r, camPos);
+                    else if (ck == "orientation") okc = read_vec(r, camOri);
+                    else okc = r.skip();
+                } while (okc && r.eat(','));
+                if (!okc || !r.eat('}')) { parsed = false; break; }
+            } else if (k == "objects") {
+                hasObjects = true;
+                if (r.peek() != '[') { if (!r.skip()) { parsed = false; break; } continue; }
+                objectsIsArray = true;
+                r.p++;
+                if (r.eat(']')) continue;
+                bool oko = true;
+                do { objs.emplace_back(); oko = read_object(r, objs.back()); } while (oko && r.eat(','));
+                if (!oko || !r.eat(']')) { parsed = false; break; }
+            } else if (!r.skip()) { parsed = false; break; }
+        } while (r.eat(','));
+        if (parsed && !r.eat('}')) parsed = false;
+    }
+    if (!parsed || !r.ok) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }
+
+    // validation in the reference's order: basic data, camera, objects (SceneData.cpp:72-94)
+    if (!hasH || !hasW) { msg(message, message_len, "Missing height or witdh data!"); return nullptr; }            // :98-111
+    if (!hasCamera) { msg(message, message_len, "No camera data!"); return nullptr; }                              // :119-123
+    if (!camDir.present || !camPos.present || !camOri.present) { msg(message, message_len, "Camera data could not be read!"); return nullptr; }   // :126-131
+    if (!camDir.valid3() || !camPos.valid3() || !camOri.valid3()) { msg(message, message_len, "Camera data could not be parsed!"); return nullptr; }   // :137-141 (zz is read unchecked upstream)
+    if (!hasObjects) { msg(message, message_len, "No objects data!"); return nullptr; }                            // :152-156
+    (void)objectsIsArray;
+
+    auto* s = new ipt_host_scene();
+    s->view.width = (uint32_t)W; s->view.height = (uint32_t)H;
+    norm3(camDir.v); norm3(camOri.v);                                                                             // :143-145
+    std::memcpy(s->view.cam_origin, camPos.v, 24); std::memcpy(s->view.cam_dir, camDir.v, 24); std::memcpy(s->view.cam_orient, camOri.v, 24);
+    const double zero[3] = {0, 0, 0};
+    for (const ObjTmp& o : objs) {
+        const char* err = nullptr;
+        if (!o.color.present || !o.emission.present || !o.position.present || !o.hasRefl || !o.hasType ||
+            !o.color.valid3() || !o.emission.valid3() || !o.position.valid3())
+            err = "Could not validate object data!";                                                               // :35-51,:160-164
+        else if (!o.typeIsString || (o.type != "sphere" && o.type != "plane")) err = "Unknown object type";        // :166-177
+        else if (o.type == "sphere" && !o.hasRadius) err = "Broken sphere object! ";                               // :185-189
+        else if (o.type == "plane" && (!o.north.present || !o.east.present)) err = "Broken plane object! ";        // :205-209
+        else if (o.type == "plane" && (!o.north.valid3() || !o.east.valid3())) err = "Broken plane object! ";
+        if (err) { msg(message, message_len, err); delete s; return nullptr; }
+        if (o.type == "sphere") s->add(0, o.radius, zero, zero, o.position.v, o.emission.v, o.color.v, (int)o.refl);
+        else s->add(1, 0.0, o.north.v, o.east.v, o.position.v, o.emission.v, o.color.v, (int)o.refl);
+    }
+    if (s->mat_reflection.empty()) { msg(message, message_len, "Object list empty! Cannot build scene"); delete s; return nullptr; }   // :87-91
+    s->refresh_view();
+    return s;
+}
+
+extern "C" ipt_host_scene* ipt_host_from_objects(const void* objects, uint32_t n, uint32_t width, uint32_t height, const double* cam)
+{
+    if (!objects || !cam || n == 0) return nullptr;
+    auto* s = new ipt_host_scene();
+    s->view.width = width; s->view.height = height;
+    std::memcpy(s->view.cam_origin, cam, 24); std::memcpy(s->view.cam_dir, cam + 3, 24); std::memcpy(s->view.cam_orient, cam + 6, 24);
+    const char* base = (const char*)objects;
+    for (uint32_t i = 0; i < n; i++) {
+        const char* o = base + (size_t)i * 144;   // ObjectData.hpp:15-31
+        int32_t type, refl;
+        double radius, north[3], east[3], pos[3], emi[3], col[3];
+        std::memcpy(&type, o, 4); std::memcpy(&radius, o + 8, 8); std::memcpy(north, o + 16, 24); std::memcpy(east, o + 40, 24);
+        std::memcpy(pos, o + 64, 24); std::memcpy(emi, o + 88, 24); std::memcpy(col, o + 112, 24); std::memcpy(&refl, o + 136, 4);
+        s->add(type == 0 ? 0 : 1, radius, north, east, pos, emi, col, refl);
+    }
+    s->refresh_view();
+    return s;
+}
+
+extern "C" void ipt_host_free_scene(ipt_host_scene* s) { delete s; }
+extern "C" const ipt_scene* ipt_host_scene_view(const ipt_host_scene* s) { return s ? &s->view : nullptr; }
+extern "C" void ipt_host_set_size(ipt_host_scene* s, uint32_t w, uint32_t h) { if (s) { s->view.width = w; s->view.height = h; } }
