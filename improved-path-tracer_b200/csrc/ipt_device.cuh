@@ -64,10 +64,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     }
     return make_uint4(c0, c1, c2, c3);
 }
-// 24-bit uniform in (0,1): ((x>>8)+0.5)/2^24 — exactly representable in fp32 and fp64, so both precisions and the
-// CPU oracle see the same numbers.  2u-1 is exact as well (odd multiple of 2^-24).
-template <typename R> __device__ __forceinline__ R u24(uint32_t x) { return ((R)(x >> 8) + (R)0.5) * (R)(1.0 / 16777216.0); }
-template <typename R> __device__ __forceinline__ R s24(uint32_t x) { return (R)2 * u24<R>(x) - (R)1; }  // CudaUtils.hpp:14-17
+// Random reals, exactly representable in fp32 AND fp64 so both precisions and the CPU oracle see the same numbers:
+//   s24(x) in (-1,1): the odd multiple (2k+1-2^24)/2^24 of 2^-24, k = x>>8  — the reference's one_one() = 2u-1
+//                     (CudaUtils.hpp:14-17) at 24-bit resolution; never 0, so AObject.hpp:38's retry loop never runs
+//   u23(x) in (0,1) : (2k+1)/2^24, k = x>>9 — the uniform of the stochastic lobe pick (AObject.hpp:94,127)
+template <typename R> __device__ __forceinline__ R s24(uint32_t x) { return ((R)((int)(x >> 8) - 8388608) + (R)0.5) * (R)(1.0 / 8388608.0); }
+template <typename R> __device__ __forceinline__ R u23(uint32_t x) { return ((R)(x >> 9) + (R)0.5) * (R)(1.0 / 8388608.0); }
 
 // ---------------------------------------------------------------------------------------------- ray record
 template <typename R> struct Ray {
@@ -337,13 +339,13 @@ __device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int ref
         const V3<R> spec = reflect_dir(in, n);
         const V3<R> diff = diffuse_dir(n, rnd);
         if (depth < 2) { s.d0 = spec; s.w0 = (R)0.92; s.d1 = diff; s.w1 = (R)0.08; s.has1 = true; }
-        else s.d0 = (u24<R>(rnd.w) > (R)0.9) ? diff : spec;
+        else s.d0 = (u23<R>(rnd.w) > (R)0.9) ? diff : spec;
     } else if (reflection == 2) {               // AObject.hpp:110-135
         const V3<R> spec = reflect_dir(in, n);
         V3<R> refr;
         if (!refract_dir(in, raw, refr)) s.d0 = spec;
         else if (depth < 2) { s.d0 = refr; s.w0 = (R)0.95; s.d1 = spec; s.w1 = (R)0.05; s.has1 = true; }
-        else s.d0 = (u24<R>(rnd.w) > (R)0.95) ? spec : refr;
+        else s.d0 = (u23<R>(rnd.w) > (R)0.95) ? spec : refr;
     } else {                                    // "Uknown reflection type": zero ray with weight 0 -> nothing to trace
         s.has0 = false;
         s.d0 = mk<R>(0, 0, 0);

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                             if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension, off by default)
                                 const R q = fmin((R)1, fmax((R)0.05, fmax(nthr.x, fmax(nthr.y, nthr.z))));
                                 const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.key0, p.key1);
-                                if (u24<R>(rr.x) >= q) alive = false;
+                                if (u23<R>(rr.x) >= q) alive = false;
                                 else nthr = nthr * ((R)1 / q);
                             }
                             const bool onS = isRect || fabs(dot(r.d, r.d) - (R)1) < (R)1e-3;

@@ -373,7 +373,10 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     int grid_first = 0, grid_next = 0;
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
-    for (uint64_t g0 = 0; g0 < total_groups; g0 += groups_per_batch) {
+    // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
+    // rectangle and the frame stays black.  Kept: such frames are resolved from zeroed accumulators without tracing.
+    const bool tiny = c->W <= 22 && c->H <= 22;
+    for (uint64_t g0 = 0; g0 < total_groups && !tiny; g0 += groups_per_batch) {
         kp.base_mt = (uint32_t)(g0 / prm.samples);
         kp.base_sample = (uint32_t)(g0 % prm.samples);
         kp.n_first = (uint32_t)(std::min<uint64_t>(groups_per_batch, total_groups - g0) * 32);

@@ -119,8 +119,9 @@ def lib():
         L.or_scatter.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_ulonglong, dp]
         L.or_scatter.restype = None
         L.or_philox4x32_10.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        L.or_uniform24.argtypes = [ctypes.c_uint32]
-        L.or_uniform24.restype = ctypes.c_double
+        for f in (L.or_sym24, L.or_uniform23):
+            f.argtypes = [ctypes.c_uint32]
+            f.restype = ctypes.c_double
         L.or_to_rgb.argtypes = [ctypes.c_double]
         L.or_to_rgb.restype = ctypes.c_int
         _lib = L

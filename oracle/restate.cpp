@@ -74,7 +74,9 @@ inline void philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4])
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-inline double u24(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); }  // in (0,1), exact in fp32 too
+// Random reals of the counter stream, exactly representable in fp32 and fp64 (the B200 kernels compute the same values):
+inline double s24(uint32_t x) { return ((double)((int)(x >> 8) - 8388608) + 0.5) * (1.0 / 8388608.0); }  // (-1,1), odd multiple of 2^-24
+inline double u23(uint32_t x) { return ((double)(x >> 9) + 0.5) * (1.0 / 8388608.0); }                    // (0,1)
 
 const uint32_t NODE_CAMERA = 0xFFFFu;
 const uint32_t CTR_TAG = 0x49505442u;  // "IPTB"
@@ -96,7 +98,7 @@ struct Rng {
     // Renderer.cu:133-134: xFactor first, then zFactor
     void jitter(double& jx, double& jz)
     {
-        if (mode == OR_RNG_COUNTER) { block(NODE_CAMERA); jx = 2 * u24(blk[0]) - 1; jz = 2 * u24(blk[1]) - 1; }
+        if (mode == OR_RNG_COUNTER) { block(NODE_CAMERA); jx = s24(blk[0]); jz = s24(blk[1]); }
         else { jx = one_one_ref(); jz = one_one_ref(); }
     }
     // AObject.hpp:40 Vec3(one_one, one_one, one_one): g++ evaluates the arguments right to left (zz, yy, xx),
@@ -104,12 +106,12 @@ struct Rng {
     V dir3()
     {
         V v;
-        if (mode == OR_RNG_COUNTER) { v.x = 2 * u24(blk[0]) - 1; v.y = 2 * u24(blk[1]) - 1; v.z = 2 * u24(blk[2]) - 1; }
+        if (mode == OR_RNG_COUNTER) { v.x = s24(blk[0]); v.y = s24(blk[1]); v.z = s24(blk[2]); }
         else { v.z = one_one_ref(); v.y = one_one_ref(); v.x = one_one_ref(); }
         return v;
     }
     // AObject.hpp:94,127 curand_uniform_double for the stochastic lobe pick; counter stream: draw 3 of the block
-    double choice() { return mode == OR_RNG_COUNTER ? u24(blk[3]) : curand_uniform_double(&st); }
+    double choice() { return mode == OR_RNG_COUNTER ? u23(blk[3]) : curand_uniform_double(&st); }
 };
 
 // ------------------------------------------------------------------------------------------------ objects
@@ -515,7 +517,8 @@ void or_scatter(int kind, const double* geom, int reflection, const double* P, c
 }
 
 void or_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out) { philox(counter, key, out); }
-double or_uniform24(uint32_t x) { return u24(x); }
+double or_sym24(uint32_t x) { return s24(x); }
+double or_uniform23(uint32_t x) { return u23(x); }
 
 // Image.cpp:19-22
 int or_to_rgb(double x) { return std::clamp(int(x * 255), 0, 255); }

@@ -65,9 +65,10 @@ double or_plane_intersect(const double* north, const double* east, const double*
 void or_scatter(int kind, const double* geom, int reflection, const double* P, const double* incoming, int depth,
                 unsigned long long subsequence, double* out16);
 
-/* Philox4x32-10 block function (counter[4], key[2]) -> out[4]; and the 24-bit uniform the framework defines. */
+/* Philox4x32-10 block function (counter[4], key[2]) -> out[4]; and the two 32-bit -> real maps of the counter stream. */
 void or_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out);
-double or_uniform24(uint32_t x);
+double or_sym24(uint32_t x);     /* (-1,1): odd multiple of 2^-24 */
+double or_uniform23(uint32_t x); /* (0,1)  : odd multiple of 2^-24 */
 
 /* Image.cpp:19-22 toRgb: clamp(int(x*255), 0, 255). */
 int or_to_rgb(double x);

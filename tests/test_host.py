@@ -1,0 +1,327 @@
+"""CPU tests of the C++ host layer and of the C-ABI library surface (no GPU, no compute calls)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from scene_util import synthetic_scene, vec, write_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pyipt):
+    declared = set()
+    for h in ("ipt_abi.h", "ipt_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(ipt_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 25
+    assert declared == set(pyipt.ABI_SYMBOLS) | set(pyipt.HOST_SYMBOLS)
+    L = pyipt.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ipt_abi_version() == 1
+
+
+def test_no_torch_and_no_oracle_in_the_product():
+    """The shared library and its sources reference neither torch nor anything under oracle/."""
+    pkg = os.path.join(ROOT, "improved-path-tracer_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".py", "Makefile")):
+                text = open(os.path.join(d, f)).read()
+                assert "oracle" not in text.replace("the oracle run on", "").replace("CPU oracle see", "").lower() or f in ("ipt_device.cuh",), f
+                assert "torch" not in text, f
+    out = subprocess.run(["ldd", os.path.join(pkg, "libipt_b200.so")], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out
+
+
+def test_loader_matches_python_json(pyipt, oracle):
+    for name in ("spheres", "mirrors", "maze"):
+        hs = pyipt.HostScene.load(oracle.scene_path(name))
+        sc = oracle.Scene.load(name)
+        a = hs.arrays()
+        v = hs.view.contents
+        assert (v.width, v.height, v.n_objects) == (sc.width, sc.height, len(sc.objects))
+        assert np.array_equal(list(v.cam_origin), sc.cam_pos) and np.array_equal(list(v.cam_dir), sc.cam_dir) and np.array_equal(list(v.cam_orient), sc.cam_orient)
+        assert np.array_equal(a["mat_color"], [o["color"] for o in sc.objects])
+        assert np.array_equal(a["mat_emission"], [o["emission"] for o in sc.objects])
+        assert np.array_equal(a["mat_reflection"], [o["reflection"] for o in sc.objects])
+        sph = [i for i, o in enumerate(sc.objects) if o["type"] == 0]
+        rec = [i for i, o in enumerate(sc.objects) if o["type"] == 1]
+        assert list(a["sphere_object"]) == sph and list(a["rect_object"]) == rec   # object (JSON) order kept
+        for k, i in enumerate(sph):
+            assert np.array_equal(a["sphere_cxyzr"][k], list(sc.objects[i]["position"]) + [sc.objects[i]["radius"]])
+        for k, i in enumerate(rec):
+            N, E, c = (np.array(sc.objects[i][q]) for q in ("north", "east", "position"))
+            n = np.cross(N, E); n = n * (1 / np.sqrt(n @ n))
+            assert np.allclose(a["rect_plane"][k], [*n, n @ c], rtol=0, atol=1e-12)
+            u, vv, b = a["rect_u"][k], a["rect_v"][k], a["rect_bounds"][k]
+            assert abs(u[:3] @ E) < 1e-9 and abs(u[:3] @ n) < 1e-12 and abs(np.linalg.norm(u[:3]) - 1) < 1e-12
+            assert abs(vv[:3] @ N) < 1e-9 and abs(vv[:3] @ n) < 1e-12
+            assert np.allclose(b, [0, np.linalg.norm(N) + 5e-5, 0, np.linalg.norm(E) + 5e-5], rtol=0, atol=1e-9)
+        assert a["n_bvh_nodes"] == 0   # <= 64 primitives: brute force from shared memory
+
+
+def test_rect_bounds_reproduce_reference_test(pyipt, oracle, tmp_path):
+    """The flattened bounds test == Plane.cu:87-100 (through the oracle's literal restatement) on random hits,
+    for orthogonal, rotated and NON-orthogonal rectangles."""
+    rng = np.random.default_rng(1)
+    scene = synthetic_scene(0, 0)
+    rects = []
+    for i in range(40):
+        a = rng.normal(size=3); a /= np.linalg.norm(a)
+        b = np.cross(a, rng.normal(size=3)); b /= np.linalg.norm(b)
+        north, east = a * rng.uniform(5, 300), b * rng.uniform(5, 300)
+        if i % 4 == 0:
+            east = east + rng.uniform(0.01, 0.6) * north   # non-orthogonal
+        rects.append((rng.uniform(-200, 1200, 3), north, east))
+    scene["objects"] = [{"type": "plane", "position": vec(c), "north": vec(n), "east": vec(e), "color": vec((.5, .5, .5)), "emission": vec((0, 0, 0)), "reflection": 0} for c, n, e in rects]
+    path = write_scene(tmp_path / "rects.json", scene)
+    a = pyipt.HostScene.load(path).arrays()
+    dp = ctypes.POINTER(ctypes.c_double)
+    P = lambda x: np.ascontiguousarray(x, dtype=np.float64).ctypes.data_as(dp)
+    agree = total = hits = 0
+    for k, (c, north, east) in enumerate(rects):
+        for _ in range(200):
+            target = c + north * rng.uniform(-1.2, 1.2) + east * rng.uniform(-1.2, 1.2)
+            o = target + rng.normal(size=3) * 300
+            d = target - o; d /= np.linalg.norm(d)
+            t_ref = oracle.lib().or_plane_intersect(P(north), P(east), P(c), P(o), P(d))
+            pl, u, v, b = a["rect_plane"][k], a["rect_u"][k], a["rect_v"][k], a["rect_bounds"][k]
+            den = pl[:3] @ d
+            t = (pl[3] - pl[:3] @ o) / den if den != 0 else 0.0
+            ok = t > 1e-4
+            if ok:
+                hit = o + d * t
+                su, sv = abs(u[:3] @ hit - u[3]), abs(v[:3] @ hit - v[3])
+                ok = b[0] <= su <= b[1] and b[2] <= sv <= b[3]
+            total += 1
+            agree += (ok == (t_ref != 0.0))
+            hits += t_ref != 0.0
+            if ok and t_ref != 0.0:
+                assert abs(t - t_ref) <= 1e-9 * max(1.0, abs(t_ref))
+    assert agree == total and hits > 0.2 * total
+
+
+LOAD_ERRORS = [
+    (lambda s: s.pop("width"), "Missing height or witdh data!"),
+    (lambda s: s.pop("camera"), "No camera data!"),
+    (lambda s: s["camera"].pop("orientation"), "Camera data could not be read!"),
+    (lambda s: s["camera"]["position"].pop("yy"), "Camera data could not be parsed!"),
+    (lambda s: s.pop("objects"), "No objects data!"),
+    (lambda s: s["objects"][2].pop("color"), "Could not validate object data!"),
+    (lambda s: s["objects"][1]["emission"].pop("xx"), "Could not validate object data!"),
+    (lambda s: s["objects"][0].update(type="cube"), "Unknown object type"),
+    (lambda s: s["objects"][6].pop("radius"), "Broken sphere object! "),
+    (lambda s: s["objects"][0].pop("north"), "Broken plane object! "),
+    (lambda s: s.update(objects=[]), "Object list empty! Cannot build scene"),
+]
+
+
+@pytest.mark.parametrize("case", range(len(LOAD_ERRORS)))
+def test_loader_messages(pyipt, tmp_path, case):
+    """SceneData.cpp's messages, in the reference's validation order."""
+    mutate, message = LOAD_ERRORS[case]
+    scene = synthetic_scene(3, 0)
+    mutate(scene)
+    path = write_scene(tmp_path / "bad.json", scene)
+    with pytest.raises(pyipt.IptError) as e:
+        pyipt.HostScene.load(path)
+    assert str(e.value) == message
+
+
+def test_loader_missing_and_malformed_file(pyipt, tmp_path):
+    with pytest.raises(pyipt.IptError) as e:
+        pyipt.HostScene.load(str(tmp_path / "nope.json"))
+    assert str(e.value) == "Could not load provided json file!"
+    p = tmp_path / "broken.json"
+    p.write_text('{"width": 10, "height": ')
+    with pytest.raises(pyipt.IptError):
+        pyipt.HostScene.load(str(p))
+
+
+def test_loader_ignores_unknown_keys_and_key_order(pyipt, tmp_path):
+    scene = synthetic_scene(5, 2)
+    a = pyipt.HostScene.load(write_scene(tmp_path / "a.json", scene)).arrays()
+    scene2 = {"objects": [dict(reversed(list(o.items())), extra={"a": [1, {"b": None}], "s": "x\\\"y"}) for o in scene["objects"]],
+              "note": "ignored", "height": scene["height"], "camera": scene["camera"], "width": scene["width"]}
+    b = pyipt.HostScene.load(write_scene(tmp_path / "b.json", scene2)).arrays()
+    for k in ("sphere_cxyzr", "rect_plane", "rect_bounds", "mat_color", "mat_reflection"):
+        assert np.array_equal(a[k], b[k])
+
+
+def test_from_objects_equals_loader(pyipt, oracle):
+    """ipt_host_from_objects (the reference's ObjectData[] AoS) flattens to the same arrays as the JSON loader."""
+    sc = oracle.Scene.load("mirrors")
+    cs = sc.c_scene()
+    raw = ctypes.string_at(cs.objects, 144 * cs.n_objects)
+    a = pyipt.HostScene.from_objects(raw, cs.n_objects, sc.width, sc.height, list(cs.camera)).arrays()
+    b = pyipt.HostScene.load(oracle.scene_path("mirrors")).arrays()
+    for k in ("sphere_cxyzr", "sphere_object", "rect_plane", "rect_u", "rect_v", "rect_bounds", "rect_object", "mat_color", "mat_emission", "mat_reflection"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_bvh_is_a_valid_partition(pyipt, tmp_path):
+    scene = synthetic_scene(700, 3)
+    hs = pyipt.HostScene.load(write_scene(tmp_path / "s.json", scene), leaf_size=4, brute_max=64)
+    a = hs.arrays()
+    n = len(scene["objects"])
+    assert a["n_bvh_nodes"] > n // 8
+    slots = a["bvh_slot_prim"]
+    ns = len(a["sphere_object"])
+    flat = np.where(slots & 0x80000000, (slots & 0x7fffffff) + ns, slots)
+    assert sorted(flat.tolist()) == list(range(n))             # every primitive exactly once
+    # primitive boxes
+    lo, hi = np.zeros((n, 3)), np.zeros((n, 3))
+    k_s = k_r = 0
+    for o in scene["objects"]:
+        c = np.array([o["position"][q] for q in ("xx", "yy", "zz")])
+        if o["type"] == "sphere":
+            lo[k_s], hi[k_s] = c - o["radius"], c + o["radius"]; k_s += 1
+        else:
+            N = np.array([o["north"][q] for q in ("xx", "yy", "zz")]); E = np.array([o["east"][q] for q in ("xx", "yy", "zz")])
+            corners = np.array([c + sn * N + se * E for sn in (-1, 1) for se in (-1, 1)])
+            lo[ns + k_r], hi[ns + k_r] = corners.min(0), corners.max(0); k_r += 1
+    seen = np.zeros(n, bool)
+
+    def walk(i, blo, bhi):
+        nd = a["bvh_nodes"][i]
+        for k, (clo, chi) in enumerate(((nd.lo0, nd.hi0), (nd.lo1, nd.hi1))):
+            clo, chi = np.array(clo[:], dtype=np.float64), np.array(chi[:], dtype=np.float64)
+            assert np.all(clo >= blo - 1e-3) and np.all(chi <= bhi + 1e-3) or blo is None
+            ch = nd.child[k]
+            if ch >= 0:
+                assert ch > i                                   # breadth-first numbering
+                walk(ch, clo, chi)
+            else:
+                first, cnt = ~ch, nd.count[k]
+                assert 1 <= cnt <= 4
+                for s in range(first, first + cnt):
+                    p = flat[s]
+                    assert not seen[p]
+                    seen[p] = True
+                    assert np.all(lo[p] >= clo) and np.all(hi[p] <= chi)   # conservative boxes
+
+    walk(0, np.full(3, -np.inf), np.full(3, np.inf))
+    assert seen.all()
+
+
+def test_to_rgb_matches_reference_mapping(pyipt, oracle):
+    """Image.cpp:19-22 through the oracle's restatement."""
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-0.5, 1.5, 2000), [0.0, 1.0, 1 / 255, 254.999 / 255, 20.0, 8.0e6, -8.0e6, 0.999999]])
+    for x in xs:
+        assert pyipt.lib().ipt_host_to_rgb(float(x)) == oracle.lib().or_to_rgb(float(x))
+    # int(x*255) overflows (undefined behaviour upstream) beyond |x| ~ 8.4e6 and for NaN: defined here as saturation / 0
+    assert pyipt.lib().ipt_host_to_rgb(float("nan")) == 0 and pyipt.lib().ipt_host_to_rgb(1e12) == 255 and pyipt.lib().ipt_host_to_rgb(-1e12) == 0
+
+
+def test_png_roundtrip(pyipt, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    img = rng.uniform(-0.2, 1.4, (37, 53, 3)).astype(np.float32)
+    p = str(tmp_path / "x.png")
+    assert pyipt.lib().ipt_host_write_png(p.encode(), img.ctypes.data, 53, 37) == 0
+    got = np.asarray(Image.open(p))
+    assert got.shape == (37, 53, 3) and got.dtype == np.uint8
+    want = np.clip((img.astype(np.float64) * 255).astype(np.int64), 0, 255)
+    assert np.array_equal(got, want)
+
+
+def test_time_string_and_benchmark_record(pyipt, tmp_path):
+    buf = ctypes.create_string_buffer(64)
+    cases = {0: "00:00:00.0", 5007: "00:00:05.7", 59999: "00:00:59.999", 3723456: "01:02:03.456", 36000000 + 61001: "10:01:01.1"}
+    for ms, want in cases.items():
+        pyipt.lib().ipt_host_time_string(ms, buf, 64)
+        assert buf.value.decode() == want                       # Measurements.cpp:21-41: ms not zero-padded
+    f = str(tmp_path / "benchmark.txt").encode()
+    pyipt.lib().ipt_host_append_benchmark(f, b"spheresD10S40", b"00:00:05.7")
+    pyipt.lib().ipt_host_append_benchmark(f, b"mazeD10S40", b"00:01:00.12")
+    assert open(f).read() == "spheresD10S40;00:00:05.7;mazeD10S40;00:01:00.12;"   # no newline (Measurements.cpp:53)
+
+
+def _cli(pyipt, args, capfd):
+    argv = (ctypes.c_char_p * (len(args) + 1))(b"tracer", *[a.encode() for a in args])
+    out = pyipt.Cli()
+    ok = pyipt.lib().ipt_host_parse_cli(len(args) + 1, argv, ctypes.byref(out))
+    import sys
+    sys.stdout.flush()
+    return ok, out, capfd.readouterr().out
+
+
+def test_cli_grammar(pyipt, oracle, capfd, tmp_path):
+    """InputParser.cpp:72-258 accept/reject table."""
+    scene = oracle.scene_path("spheres")
+    ok, o, _ = _cli(pyipt, [scene], capfd)
+    assert ok == 1 and (o.samples, o.max_depth, o.scene_name) == (40, 10, b"spheres")
+    ok, o, _ = _cli(pyipt, ["-d=32", "--samples=1024", scene], capfd)
+    assert ok == 1 and (o.samples, o.max_depth) == (1024, 32)
+    ok, o, _ = _cli(pyipt, ["s=-8", scene], capfd)                 # one dash ANYWHERE in the token counts (:136-142)
+    assert ok == 1 and o.samples == 8
+    ok, o, _ = _cli(pyipt, ["-s=4", "-s=9", scene], capfd)          # repeats allowed, last wins
+    assert ok == 1 and o.samples == 9
+    dotted = tmp_path / "my.scene.v2.json"
+    dotted.write_text("{}")
+    ok, o, _ = _cli(pyipt, [str(dotted)], capfd)
+    assert ok == 1 and o.scene_name == b"my.scene.v2"               # up to the LAST dot (:41-55)
+    rejects = [
+        ([], "Got 0 arguments! Expected between 1 and 3 arguments"),
+        (["-s=4", "-d=4", "-d=5", scene], "Got 4 arguments! Expected between 1 and 3 arguments"),
+        (["/no/such/file.json"], "Path does not exist"),
+        ([str(tmp_path)], "Not a file"),
+        (["s=4", scene], "Arguments can have 1 or 2 (-)! Please check your input"),
+        (["---s=4", scene], "Arguments can have 1 or 2 (-)! Please check your input"),
+        (["-s", scene], "Cannot parse argument: s"),
+        (["-s=4=5", scene], "Cannot parse argument: s=4=5"),
+        (["-x=4", scene], "Unknown short argument: x=4"),
+        (["--s=4", scene], "Unknown long argument: s=4"),
+        (["-samples=4", scene], "Unknown short argument: samples=4"),
+        (["-s=3", scene], "Number of samples out of range!"),
+        (["-s=65536", scene], "Number of samples out of range!"),
+        (["-s=99999999999", scene], "Number of samples out of range!"),
+        (["-s=abc", scene], "Could not convert samples to number!"),
+        (["-d=2", scene], "Depth out of range!"),
+        (["-d=256", scene], "Depth out of range!"),
+        (["--depth=x", scene], "Could not convert depth to number!"),
+        ([scene, "-s=4"], "Path does not exist"),                   # the path must be the LAST argument (:93)
+    ]
+    for args, cause in rejects:
+        ok, _, out = _cli(pyipt, args, capfd)
+        assert ok == 0, args
+        lines = out.splitlines()
+        assert lines[0] == "Error parsing input!" and lines[1] == "Cause: " + cause and lines[2] == "Usage:", (args, out)
+        assert lines[3] == "tracer [arguments] [path_to_scene]"
+    ok, _, out = _cli(pyipt, ["--help"], capfd)
+    assert ok == 0 and out.startswith("tracer [arguments] [path_to_scene]") and "between 4 and 65535" in out and "between 3 and 255" in out
+
+
+def test_tile_schedule_is_a_balanced_partition(pyipt):
+    L = pyipt.lib()
+    for world in (1, 2, 3, 4, 8):
+        for tiles_x, tiles_y in ((20, 23), (60, 68), (7, 5)):
+            owners = np.array([[L.ipt_tile_owner(x, y, tiles_x, world) for x in range(tiles_x)] for y in range(tiles_y)])
+            assert owners.min() == 0 and owners.max() == world - 1
+            counts = np.bincount(owners.ravel(), minlength=world)
+            assert counts.max() - counts.min() <= max(tiles_x, tiles_y)
+            if world > 1 and tiles_x >= world:   # every tile row is spread over all ranks
+                assert all(len(set(r)) == world for r in owners)
+
+
+def test_no_device_fails_loudly(pyipt, oracle):
+    """Without a CUDA device nothing renders and nothing falls back: IPT_ERR_NO_DEVICE, and `tracer` prints the
+    reference's message and exits 0 (CudaUtils.cu:13-17, main.cu:24-27)."""
+    if pyipt.lib().ipt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"))
+    with pytest.raises(pyipt.IptError) as e:
+        pyipt.render(hs, 4, 3)
+    assert "(-1)" in str(e.value) and "CUDA capable device not found" in str(e.value)
+    with pytest.raises(pyipt.IptError):
+        pyipt.Context(0)
+    r = subprocess.run([os.path.join(ROOT, "improved-path-tracer_b200", "tracer"), oracle.scene_path("spheres")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "CUDA capable device not found! Cannot continue"
