@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s (and Gbounces/s) of the per-pixel radiance path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one full render of the workload's frame (all samples of all pixels) through the C ABI of
+libipt_b200.so.  At N > 1 the frame's tiles are interleaved statically over the ranks (one process per GPU), every
+rank renders its tiles, and the finished tiles are written into rank 0's frame over NVLink peer access (CUDA IPC);
+there is no collective on the data path, so torch.distributed is used only for the barrier and the max over ranks.
+`value` is device-resident (scene already in HBM, CUDA-event time of the kernels, max over ranks); `e2e` is the same
+metric through the host-buffer path: scene upload from pinned host memory + kernels + gather + frame download.
+
+--impl reference times the reference's own CPU routine (oracle/_ref: its unmodified Renderer.cu compiled for the
+host) on all host cores, on a bounded sample of the same workload.  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "improved-path-tracer_b200"))
+
+# BASELINE.json configs.  flops = algorithmic fp32 flops per bounce (19 S + 31 R + 60, brute force)
+WORKLOADS = {
+    "spheres4k": dict(scene="spheres", width=3840, height=2160, depth=32, spp=1024, flops=303,
+                      desc="scenes/spheres.json at 3840x2160 -d=32 -s=1024 (BASELINE configs[3], literal reading)"),
+    "spheres": dict(scene="spheres", width=None, height=None, depth=10, spp=40, flops=303, desc="scenes/spheres.json -d=10 -s=40 (configs[0])"),
+    "mirrors": dict(scene="mirrors", width=None, height=None, depth=10, spp=40, flops=453, desc="scenes/mirrors.json -d=10 -s=40 (configs[1])"),
+    "maze": dict(scene="maze", width=None, height=None, depth=10, spp=40, flops=1786, desc="scenes/maze.json -d=10 -s=40 (configs[2])"),
+}
+BYTES_PER_BOUNCE = 96          # fused extend+shade wavefront: 48 B ray record read + 48 B written
+FP32_LANES_PER_SM = 128
+
+
+def scene_file(name):
+    p = os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".json")
+    if not os.path.isfile(p):
+        raise SystemExit(f"{p} missing: run `python -c 'import __graft_entry__ as g; g.build()'` where the reference is mounted")
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+def run_reference(args, wl, rank):
+    """The reference's own per-pixel routine on the host cores: a bounded sample of the workload per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    if not O.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_host.so not built"}))
+        return
+    cores = os.cpu_count() or 1
+    W, H = wl["width"] or 1280, wl["height"] or 720
+    n_cells = O.ref().ref_num_cells(W, H)
+    # bounded sample: every `stride`-th reference cell (a cell = one reference CUDA thread's pixel rectangle,
+    # Renderer.cu:33-53), reduced spp; throughput in samples/s does not depend on spp
+    stride, spp = args.ref_stride, args.ref_spp
+    cells = list(range(0, n_cells, stride))
+    px_per_cell = (W * H) / n_cells
+
+    import numpy as np
+    path = O.scene_path(wl["scene"]).encode()
+    out = np.zeros((H, W, 3))
+
+    # run the sampled cells in parallel: one thread per cell through a pool of `cores` workers
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one_step_parallel():
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(lambda c: O.ref().ref_render_cells(path, spp, wl["depth"], W if wl["width"] else 0, H if wl["height"] else 0,
+                                                          c, c + 1, 1, out.ctypes.data), cells))
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        one_step_parallel()
+    times = [one_step_parallel() for _ in range(args.steps)]
+    samples = len(cells) * px_per_cell * spp
+    ms = 1e3 * sum(times) / len(times)
+    value = samples / (ms * 1e-3) / 1e6
+    sample_desc = f"every {stride}th of the reference's {n_cells} thread cells ({len(cells)} cells, {int(samples)} samples) at {spp} spp, depth {wl['depth']}"
+    line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": wl["desc"], "sample": sample_desc},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(wl, seconds_budget=20.0):
+    """Rank 0, N=1: the reference's host-compiled routine (kind "reference") on a bounded sample, all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import oracle as O
+        if not O.ref_available():
+            raise RuntimeError("oracle/_ref not built")
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor
+        cores = os.cpu_count() or 1
+        W, H = wl["width"] or 1280, wl["height"] or 720
+        n_cells = O.ref().ref_num_cells(W, H)
+        path = O.scene_path(wl["scene"]).encode()
+        out = np.zeros((H, W, 3))
+        spp = 4
+        cells = list(range(0, n_cells, max(1, n_cells // (4 * cores))))
+
+        def run(c):
+            O.ref().ref_render_cells(path, spp, wl["depth"], W if wl["width"] else 0, H if wl["height"] else 0, c, c + 1, 1, out.ctypes.data)
+
+        t0 = time.perf_counter()
+        done = 0
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            for _ in ex.map(run, cells):
+                done += 1
+        dt = time.perf_counter() - t0
+        # scale spp so that the sample takes ~seconds_budget, then time that
+        spp = int(max(4, min(256, spp * seconds_budget / max(dt, 1e-3))))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(run, cells))
+        dt = time.perf_counter() - t0
+        samples = len(cells) * (W * H / n_cells) * spp
+        return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                "sample": f"{len(cells)} of the reference's {n_cells} thread cells (evenly strided over the frame) at {spp} spp, depth {wl['depth']}: {int(samples)} samples in {dt:.1f} s, fp64"}
+    except Exception as e:   # the baseline is reported, never required for the GPU number
+        return {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("IPT_BENCH_WORKLOAD", "spheres4k"), choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (the line then says so)")
+    ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--fp64", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-stride", type=int, default=11)
+    ap.add_argument("--ref-spp", type=int, default=8)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.spp:
+        wl["spp"] = args.spp
+        wl["desc"] += f" [spp overridden to {args.spp}]"
+    if args.depth:
+        wl["depth"] = args.depth
+        wl["desc"] += f" [depth overridden to {args.depth}]"
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    import numpy as np
+    import pyipt
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        token = torch.zeros(1, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.all_reduce(token)
+            torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    if pyipt.lib().ipt_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device — there is no CPU path to time (use --impl reference for the CPU baseline)")
+
+    hs = pyipt.HostScene.load(scene_file(wl["scene"]), width=wl["width"], height=wl["height"])
+    W, H = hs.width, hs.height
+    ctx = pyipt.Context(local)
+    ctx.set_scene(hs)
+    flags = pyipt.FLAG_FP64 if args.fp64 else 0
+    gather = "single GPU"
+    if world > 1:
+        # rank 0's fp32 frame is the gather target of every rank: its CUDA IPC handle goes round once
+        handle = [ctx.export_frame() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            ctx.set_gather_target_ipc(handle[0])
+        gather = "tiles stored into rank 0's frame over NVLink peer access (CUDA IPC), no collective"
+
+    def step():
+        return ctx.render(wl["spp"], wl["depth"], seed=123456, flags=flags, rank=rank, world=world, batch=args.batch)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms, bounces, samples, launches = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        st = step()
+        dev_ms += st["render_ms"]; bounces += st["traced_bounces"]; samples += st["samples"]; launches += st["kernel_launches"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.result()
+    ms_dev = allmax(dev_ms) / args.steps                 # CUDA events on the rendering stream, max over ranks
+    ms_wall = allmax(t_wall * 1e3) / args.steps
+    tot_samples = allsum(samples) / args.steps
+    tot_bounces = allsum(bounces) / args.steps
+    tot_launches = int(allsum(launches))
+    my_bounces_per_step = bounces / args.steps
+
+    # ---- end to end through host buffers: upload from pinned memory + kernels + gather + download, every step
+    frame = np.zeros((H, W, 3), dtype=np.float32)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        ctx.set_scene(hs)
+        st = step()
+        barrier()
+        if rank == 0:
+            ctx.download(out=frame)
+    barrier()
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
+    h2d = int(ctx_last(pyipt, ctx, "h2d"))
+    d2h = int(frame.nbytes)
+
+    if rank == 0:
+        sm_count = 148
+        clk = (clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
+        # per-GPU figures of rank 0 (the kernels are the same on every rank)
+        r0_ms = dev_ms / args.steps
+        ach_fp32 = my_bounces_per_step * wl["flops"] / (r0_ms * 1e-3) / 1e12
+        ach_hbm = my_bounces_per_step * BYTES_PER_BOUNCE / (r0_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            traffic = tr.get(args.workload, {}).get("dram_bytes_per_bounce")
+        except Exception:
+            pass
+        roof_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_fp32 / fp32_peak,
+                     "traffic": None, "peak_source": "148 SM x 128 lanes x 2 x max SM clock (no measured fp32 figure in MEASURED_PEAKS.json)",
+                     "frac_at_observed_clock": ach_fp32 / (sm_count * FP32_LANES_PER_SM * 2 * clk * 1e6 / 1e12),
+                     "algorithmic_flops_per_bounce": wl["flops"]}
+        roof_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak,
+                    "traffic": None if traffic is None else traffic * my_bounces_per_step / max(1, launches / args.steps),
+                    "peak_source": hbm_src, "algorithmic_bytes_per_bounce": BYTES_PER_BOUNCE,
+                    "kernel": "k_bounce (one launch per bounce per batch); achieved = bounces x bytes / sum of launch durations"}
+        binding = roof_hbm if roof_hbm["frac"] >= roof_fp32["frac"] else roof_fp32
+        line = {
+            "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
+            "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "ms_per_step_wall": ms_wall,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],
+                       "samples_per_step": int(tot_samples), "traced_bounces_per_step": int(tot_bounces),
+                       "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
+                       "l2": "inputs larger than L2: each wavefront batch streams 2 x 403 MB ray queues", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
+            "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": tot_launches,
+            "clocks": clocks,
+            "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctx_last(pyipt, ctx, what):
+    # bytes uploaded by the last ipt_ctx_set_scene: geometry (fp64+fp32), materials, slot ids, BVH nodes
+    v = ctx.scene.view.contents
+    n = v.n_objects
+    return n * (16 * 8 + 16 * 4 + 8 * 8 + 8 * 4) + ((n + 3) // 4) * 16 + v.n_bvh_nodes * 64
+
+
+if __name__ == "__main__":
+    main()

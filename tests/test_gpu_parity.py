@@ -1,0 +1,320 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI with host buffers, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star: "per-pixel agreement within 1e-3 relative when its per-pixel RNG seeding is
+reproduced, otherwise a statistical test"):
+  * fp64 parity mode vs the oracle on the same counter-based stream: pixels equal to 1e-9 relative; radiance is a
+    piecewise-constant function of the path, so pixels agree exactly unless a discrete event (which object / which
+    side) flips through a 1e-16 rounding difference — allowed on <= 0.01 % of pixels.
+  * fp32 product path vs the same oracle image: >= 99 % of pixels within 1e-3 relative (fp32 rounding flips discrete
+    events on a few paths; SURVEY.md App. D measured 95-98 % *identical* pixels for a plain fp32 transcription), and
+    the image mean within 1e-3 relative.
+  * against the reference's own random stream (one XORWOW stream per reference thread — not reproducible by any
+    parallel schedule): mean within 3 sigma, RMSE against a 65535-spp reference image falling as 1/sqrt(spp).
+"""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from scene_util import synthetic_scene, write_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def frac_within(img, ref, rel, floor=1e-3):
+    return float(np.mean(np.all(np.abs(img - ref) <= rel * np.maximum(floor, np.abs(ref)), axis=2)))
+
+
+@pytest.fixture(scope="module")
+def ctx(pyipt):
+    c = pyipt.Context(0)
+    yield c
+    c.close()
+
+
+SCENES = ("spheres", "mirrors", "maze")
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp64_is_pixel_exact_against_oracle(pyipt, oracle, name):
+    W, H, spp, depth, seed = 256, 144, 8, 10, 2026
+    ref, cnt = oracle.render(oracle.Scene.load(name, W, H), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(oracle.scene_path(name), width=W, height=H)
+    img, st = pyipt.render(hs, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
+    assert frac_within(img, ref, 1e-9) >= 0.9999
+    assert abs(img.mean() - ref.mean()) <= 1e-6 * ref.mean()
+    assert st["samples"] == W * H * spp == cnt["samples"]
+    # the casts traced are exactly the casts that can contribute, up to flipped paths
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-4 * cnt["casts_needed"]
+    assert st["kernel_launches"] == depth + 1
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp32_matches_oracle_per_pixel(pyipt, oracle, name):
+    W, H, spp, depth, seed = 256, 144, 8, 10, 77
+    ref, cnt = oracle.render(oracle.Scene.load(name, W, H), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(oracle.scene_path(name), width=W, height=H)
+    img, st = pyipt.render(hs, spp, depth, seed=seed)
+    assert frac_within(img, ref, 1e-3) >= 0.99
+    assert np.all(np.abs(img.mean(axis=(0, 1)) - ref.mean(axis=(0, 1))) <= 1e-3 * ref.mean(axis=(0, 1)))
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 2e-3 * cnt["casts_needed"]
+
+
+@pytest.mark.parametrize("depth,spp,W,H", [(1, 4, 64, 36), (2, 4, 64, 36), (3, 4, 67, 41), (4, 5, 133, 75), (32, 2, 96, 54),
+                                            (129, 1, 48, 28), (10, 1, 23, 9), (10, 3, 9, 23), (7, 2, 320, 180)])
+def test_depth_and_frame_edge_cases(pyipt, oracle, depth, spp, W, H):
+    """maxDepth 1..129, 1 spp, odd / non-tile-multiple / narrow frames (the camera formula differs for odd widths,
+    Renderer.cu:118-125); mirrors.json has every material and both depth<2 splits."""
+    seed = depth * 1000 + W
+    ref, cnt = oracle.render(oracle.Scene.load("mirrors", W, H), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(oracle.scene_path("mirrors"), width=W, height=H)
+    img, st = pyipt.render(hs, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
+    assert frac_within(img, ref, 1e-9) >= 0.999
+    img32, _ = pyipt.render(hs, spp, depth, seed=seed)
+    assert frac_within(img32, ref, 1e-3) >= 0.97
+
+
+def test_tiny_frames_are_black_like_the_reference(pyipt, oracle, golden_dir):
+    """Renderer.cu:36-39: W <= 22 and H <= 22 -> nothing is rendered."""
+    g = np.load(os.path.join(golden_dir, "ref_images_small.npz"))
+    for W, H in ((22, 22), (21, 22), (8, 4)):
+        hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=W, height=H)
+        img, st = pyipt.render(hs, 4, 10)
+        assert img.shape == (H, W, 3) and not img.any()
+    assert np.array_equal(img.shape, (4, 8, 3)) and not g["spheres_d10_s4_22x22"].any()
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=23, height=22)
+    img, _ = pyipt.render(hs, 4, 10)
+    assert img.any()
+
+
+def test_image_is_independent_of_schedule(pyipt, oracle, ctx):
+    """Bit-identical frames for any batch size, tile size, rank count: counter-based RNG + integer accumulation."""
+    W, H, spp, depth = 200, 120, 6, 8
+    hs = pyipt.HostScene.load(oracle.scene_path("mirrors"), width=W, height=H)
+    ctx.set_scene(hs)
+    st0 = ctx.render(spp, depth, seed=5)
+    base = ctx.download(want64=False)
+    base64 = ctx.download(want64=True)
+    assert np.array_equal(base, base64.astype(np.float32))
+    for batch, tile in ((32 * 7, (8, 4)), (4096, (64, 32)), (0, (128, 64)), (1 << 16, (16, 8))):
+        st = ctx.render(spp, depth, seed=5, batch=batch, tile=tile)
+        assert np.array_equal(ctx.download(want64=False), base), (batch, tile)
+        assert st["traced_bounces"] == st0["traced_bounces"] and st["samples"] == st0["samples"]
+    for world in (2, 3, 8):
+        merged = np.zeros_like(base)
+        traced = samples = 0
+        tw, th = 32, 16
+        tiles_x = (W + tw - 1) // tw
+        own = np.array([[pyipt.lib().ipt_tile_owner(x // tw, z // th, tiles_x, world) for x in range(W)] for z in range(H)])
+        for rank in range(world):
+            st = ctx.render(spp, depth, seed=5, tile=(tw, th), rank=rank, world=world)
+            part = ctx.download(want64=False)
+            merged[own == rank] = part[own == rank]
+            traced += st["traced_bounces"]; samples += st["samples"]
+        assert np.array_equal(merged, base), world
+        assert traced == st0["traced_bounces"] and samples == st0["samples"]
+    st = ctx.render(spp, depth, seed=6)
+    assert not np.array_equal(ctx.download(want64=False), base)
+
+
+def test_nearest_hit_parity_brute_and_bvh(pyipt, oracle, tmp_path):
+    """Renderer.cu:227-243 vs the device nearest-hit (both scene modes, both precisions) on random rays."""
+    scene = synthetic_scene(400, 11)
+    path = write_scene(tmp_path / "syn.json", scene)
+    sc = oracle.Scene.load(path)
+    rng = np.random.default_rng(3)
+    n = 6000
+    o = rng.uniform([0, -500, 0], [1280, 700, 720], size=(n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[::9] *= rng.uniform(0.34, 1.0, (len(d[::9]), 1))          # non-unit directions (refracted rays)
+    d[::50, 0] = 0.0                                            # axis-parallel components (slab test with 0 * inf)
+    rays = np.concatenate([o, d], axis=1)
+    oi, ot = oracle.nearest_hit(sc, rays)
+    assert 0.5 < np.mean(oi >= 0)
+    for brute_max in (100000, 64):
+        hs = pyipt.HostScene.load(path, brute_max=brute_max, leaf_size=4)
+        assert (hs.view.contents.n_bvh_nodes > 0) == (brute_max == 64)
+        c = pyipt.Context(0); c.set_scene(hs)
+        gi, gt = c.trace(rays, pyipt.FLAG_FP64)
+        assert np.array_equal(gi, oi)
+        assert np.allclose(gt[oi >= 0], ot[oi >= 0], rtol=1e-10, atol=0)
+        gi, gt = c.trace(rays, 0)
+        same = gi == oi
+        assert same.mean() >= 0.998
+        hit = same & (oi >= 0)
+        assert np.median(np.abs(gt[hit] - ot[hit]) / ot[hit]) < 1e-5
+        c.close()
+
+
+@pytest.mark.parametrize("n_small,leaf", [(300, 4), (1500, 2), (1500, 8)])
+def test_bvh_render_matches_oracle(pyipt, oracle, tmp_path, n_small, leaf):
+    """A many-primitive scene (BASELINE config 5 in miniature) rendered through the BVH kernels vs the oracle's scan."""
+    scene = synthetic_scene(n_small, 100 + n_small, width=96, height=54)
+    path = write_scene(tmp_path / "syn.json", scene)
+    spp, depth, seed = 4, 8, 9
+    ref, cnt = oracle.render(oracle.Scene.load(path), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(path, leaf_size=leaf)
+    assert hs.view.contents.n_bvh_nodes > 0
+    img, st = pyipt.render(hs, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
+    assert frac_within(img, ref, 1e-9) >= 0.999
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-3 * cnt["casts_needed"]
+    img32, _ = pyipt.render(hs, spp, depth, seed=seed)
+    assert frac_within(img32, ref, 1e-3) >= 0.97
+    if n_small <= 300:   # same scene, brute force from shared memory (fp64 slots: 128 B per primitive)
+        hs2 = pyipt.HostScene.load(path, brute_max=100000)
+        img_b, _ = pyipt.render(hs2, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
+        assert frac_within(img_b, img, 1e-12) >= 0.9999
+
+
+def test_dropin_entry_takes_reference_buffers(pyipt, oracle):
+    """ipt_render_objects: the reference's ObjectData[] + Camera in, W*H Vec3 (fp64) out."""
+    W, H, spp, depth = 128, 72, 4, 6
+    sc = oracle.Scene.load("spheres", W, H)
+    cs = sc.c_scene()
+    out = np.zeros((H, W, 3))
+    rc = pyipt.lib().ipt_render_objects(ctypes.cast(cs.objects, ctypes.c_void_p), cs.n_objects, W, H,
+                                        ctypes.cast(cs.camera, ctypes.c_void_p), spp, depth, 1, out.ctypes.data)
+    assert rc == 0
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=W, height=H)
+    img, _ = pyipt.render(hs, spp, depth, seed=123456)
+    assert np.array_equal(out, img)
+    ref, _ = oracle.render(sc, spp, depth, rng=oracle.RNG_COUNTER, seed=123456)
+    assert frac_within(out, ref, 1e-3) >= 0.99
+
+
+def test_bad_arguments_are_rejected(pyipt, oracle):
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=64, height=36)
+    for kw in (dict(samples=0, depth=5), dict(samples=70000, depth=5), dict(samples=4, depth=0), dict(samples=4, depth=256)):
+        with pytest.raises(pyipt.IptError):
+            pyipt.render(hs, kw["samples"], kw["depth"])
+    with pytest.raises(pyipt.IptError):
+        pyipt.render(hs, 4, 5, tile=(10, 4))
+    with pytest.raises(pyipt.IptError):
+        pyipt.render(hs, 4, 5, n_gpus=64)
+
+
+@pytest.mark.parametrize("name,spp", [("spheres", 40), ("mirrors", 16), ("maze", 16)])
+def test_statistical_parity_with_reference_stream(pyipt, oracle, golden_dir, ctx, name, spp):
+    """Full 1280x720 frame, depth 10: the image mean of the reference's own run (golden, its XORWOW streams) lies
+    within 3 sigma of the GPU estimator's mean; sigma measured from 8 independent seeds."""
+    gold = json.load(open(os.path.join(golden_dir, "ref_meta.json")))["full_frame_means"][f"{name}_d10_s{spp}"]
+    hs = pyipt.HostScene.load(oracle.scene_path(name))
+    ctx.set_scene(hs)
+    means = []
+    for seed in range(8):
+        ctx.render(spp, 10, seed=1000 + seed)
+        means.append(ctx.download().mean(axis=(0, 1)))
+    means = np.array(means)
+    mu, sigma = means.mean(axis=0), means.std(axis=0, ddof=1)
+    # reference mean is one draw (sigma), ours is the mean of 8 (sigma/sqrt 8)
+    z = np.abs(np.array(gold["mean_rgb"]) - mu) / (sigma * np.sqrt(1 + 1 / 8))
+    assert np.all(z < 3.0), (z, mu, gold["mean_rgb"])
+    assert np.all(sigma / mu < 5e-3)
+
+
+def test_rmse_against_converged_reference_falls_as_inverse_sqrt_spp(pyipt, oracle, golden_dir, ctx):
+    """RMSE(spp) against the reference's 65535-spp image ~ spp^-1/2 (log-log slope -0.5 +- 0.06)."""
+    g = np.load(os.path.join(golden_dir, "ref_converged.npz"))
+    for key in g.files:
+        name, _, _, wh = key.split("_")
+        W, H = map(int, wh.split("x"))
+        hs = pyipt.HostScene.load(oracle.scene_path(name), width=W, height=H)
+        ctx.set_scene(hs)
+        spps = [4, 16, 64, 256, 1024]
+        rmse = []
+        for spp in spps:
+            e = []
+            for seed in range(4):
+                ctx.render(spp, 10, seed=seed)
+                e.append(np.mean((ctx.download() - g[key]) ** 2))
+            rmse.append(np.sqrt(np.mean(e)))
+        slope = np.polyfit(np.log(spps), np.log(rmse), 1)[0]
+        assert -0.56 < slope < -0.44, (key, slope, rmse)
+        ctx.render(16384, 10, seed=99)
+        conv = ctx.download()
+        rel = abs(conv.mean() - g[key].mean()) / g[key].mean()
+        assert rel < 2e-3, (key, rel)
+
+
+def test_russian_roulette_extension_is_unbiased(pyipt, oracle, ctx):
+    """Extension (not in the reference, off by default): the mean must not move."""
+    hs = pyipt.HostScene.load(oracle.scene_path("maze"), width=320, height=180)
+    ctx.set_scene(hs)
+    a, b = [], []
+    for seed in range(6):
+        s0 = ctx.render(64, 24, seed=seed); a.append(ctx.download().mean())
+        s1 = ctx.render(64, 24, seed=seed, flags=pyipt.FLAG_RUSSIAN_ROULETTE); b.append(ctx.download().mean())
+    assert s1["traced_bounces"] < 0.8 * s0["traced_bounces"]
+    sig = np.sqrt(np.var(a, ddof=1) / 6 + np.var(b, ddof=1) / 6)
+    assert abs(np.mean(a) - np.mean(b)) < 3.5 * sig
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_full_size_properties(pyipt, oracle, ctx, name):
+    """BASELINE configs 1-3 at full size (1280x720, d=10, s=40): fp32 vs fp64 on the same stream agree per pixel on
+    >= 95 % of pixels and in the mean to 1e-3; counts are consistent; frames are finite and non-negative."""
+    hs = pyipt.HostScene.load(oracle.scene_path(name))
+    ctx.set_scene(hs)
+    s32 = ctx.render(40, 10, seed=1)
+    a = ctx.download()
+    s64 = ctx.render(40, 10, seed=1, flags=pyipt.FLAG_FP64)
+    b = ctx.download()
+    assert np.isfinite(a).all() and a.min() >= 0
+    assert frac_within(a, b, 1e-3) >= 0.95
+    assert np.all(np.abs(a.mean(axis=(0, 1)) - b.mean(axis=(0, 1))) <= 1e-3 * b.mean(axis=(0, 1)))
+    assert s32["samples"] == s64["samples"] == 1280 * 720 * 40
+    assert abs(s32["traced_bounces"] - s64["traced_bounces"]) <= 2e-3 * s64["traced_bounces"]
+
+
+def test_4k_frame_properties(pyipt, oracle, ctx):
+    """BASELINE config 4's frame (spheres.json at 3840x2160, d=32) at reduced spp: literal reading leaves ~85 % of the
+    pixels black; two-rank split == one-rank frame bit for bit."""
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=3840, height=2160)
+    ctx.set_scene(hs)
+    st = ctx.render(4, 32, seed=3)
+    full = ctx.download(want64=False)
+    black = np.mean(np.all(full == 0, axis=2))
+    assert 0.80 < black < 0.90
+    assert st["samples"] == 3840 * 2160 * 4
+    merged = np.zeros_like(full)
+    tiles_x = (3840 + 63) // 64
+    ty, tx = np.meshgrid(np.arange(2160) // 32, np.arange(3840) // 64, indexing="ij")
+    own = (tx + ty) % 2
+    assert own[0, 64] == pyipt.lib().ipt_tile_owner(1, 0, tiles_x, 2)
+    for rank in range(2):
+        ctx.render(4, 32, seed=3, rank=rank, world=2)
+        part = ctx.download(want64=False)
+        merged[own == rank] = part[own == rank]
+    assert np.array_equal(merged, full)
+
+
+def test_tracer_program_surface(pyipt, oracle, tmp_path):
+    """`tracer -d=5 -s=4 scene.json`: stdout lines in the reference's order, <scene>D<d>S<s>.png = toRgb(frame),
+    benchmark.txt record `<id>;HH:MM:SS.ms;` without newline."""
+    from PIL import Image
+    exe = os.path.join(ROOT, "improved-path-tracer_b200", "tracer")
+    scene = tmp_path / "spheres.json"
+    j = json.load(open(oracle.scene_path("spheres")))
+    j["width"], j["height"] = 160, 90
+    scene.write_text(json.dumps(j))
+    r = subprocess.run([exe, "-d=5", "--samples=4", str(scene)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    order = ["Using GPU device: ", "Loading Scene Data...", "Data loaded successfully", "Begining render...", "Rendering", " - Done", "Render took: ", "Saving Image..."]
+    pos = [out.find(s) for s in order]
+    assert all(p >= 0 for p in pos) and pos == sorted(pos), out
+    bench = (tmp_path / "benchmark.txt").read_text()
+    assert re.fullmatch(r"spheresD5S4;\d\d:\d\d:\d\d\.\d{1,3};", bench), bench
+    png = np.asarray(Image.open(tmp_path / "spheresD5S4.png"))
+    hs = pyipt.HostScene.load(str(scene))
+    img, _ = pyipt.render(hs, 4, 5, seed=123456, want64=False)
+    want = np.clip((img.astype(np.float64) * 255).astype(np.int64), 0, 255).astype(np.uint8)
+    assert np.array_equal(png, want)
+    # invalid input: message + exit code 0 (main.cu:30-33)
+    r = subprocess.run([exe, "-s=3", str(scene)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "Number of samples out of range!" in r.stdout
