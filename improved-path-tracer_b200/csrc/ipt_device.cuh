@@ -353,4 +353,134 @@ __device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int ref
     return s;
 }
 
+
+// ============================================================================================== fp32 fast path
+// Brute-force scenes in fp32 (the product path for the three shipped scenes and BASELINE config 4): the scene is
+// re-laid out by ipt_ctx_set_scene into typed lists so that each list's test is a short branch-free sequence:
+//   spheres                  float4 {c.xyz, r}
+//   axis-aligned rectangles  per axis K (normal = +-e_K): float4 {p_K, lo_I, hi_I, lo_J}, float4 {hi_J, obj bits, 0, 0}
+//                            with I, J the two other axes in increasing order — t = (p_K - o_K) / d_K, inside iff
+//                            lo <= P <= hi on both axes.  Same test as Plane.cu:47-100 for n = +-e_K (all rectangles
+//                            of spheres/mirrors/maze.json are of this kind).
+//   general rectangles       the 4 x float4 slot of the generic path
+// Blob layout in 16-byte words: {n_sph, n_x, n_y, n_z} {n_gen, n_objects, 0, 0} sph[] sph_obj[] x[] y[] z[] gen[] gen_obj[] mat[]
+struct FastScene {
+    const float4* sph; const uint32_t* sph_obj; uint32_t n_sph;
+    const float4* ax[3]; uint32_t n_ax[3];
+    const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
+    const float4* mat;
+};
+__host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
+{
+    return 2 + n_sph + (n_sph + 3) / 4 + 2 * (nx + ny + nz) + 4 * n_gen + (n_gen + 3) / 4 + 2 * n_obj;
+}
+__device__ __forceinline__ FastScene fast_view(const uint4* blob)
+{
+    FastScene f;
+    const uint4 h0 = blob[0], h1 = blob[1];
+    const uint4* p = blob + 2;
+    f.n_sph = h0.x; f.n_ax[0] = h0.y; f.n_ax[1] = h0.z; f.n_ax[2] = h0.w; f.n_gen = h1.x;
+    f.sph = reinterpret_cast<const float4*>(p); p += f.n_sph;
+    f.sph_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_sph + 3) / 4;
+    for (int k = 0; k < 3; k++) { f.ax[k] = reinterpret_cast<const float4*>(p); p += 2 * f.n_ax[k]; }
+    f.gen = reinterpret_cast<const R4<float>*>(p); p += 4 * f.n_gen;
+    f.gen_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_gen + 3) / 4;
+    f.mat = reinterpret_cast<const float4*>(p);
+    return f;
+}
+
+// hit code: kind[28:32) (0 sphere, 1..3 axis-aligned rectangle with normal e_(kind-1), 4 general rectangle) | list index
+struct FastHit { float t; uint32_t obj; uint32_t code; };
+
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <int K> __device__ __forceinline__ float comp(const V3<float>& v) { return K == 0 ? v.x : (K == 1 ? v.y : v.z); }
+
+template <int K>
+__device__ __forceinline__ void fast_axis_list(const float4* list, uint32_t n, const V3<float>& o, const V3<float>& d, float inv_dk,
+                                               uint32_t self, FastHit& best)
+{
+    constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
+    const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
+#pragma unroll 4
+    for (uint32_t s = 0; s < n; s++) {
+        const float4 a = list[2 * s], b = list[2 * s + 1];
+        const uint32_t obj = __float_as_uint(b.y);
+        const float t = (a.x - ok) * inv_dk;                     // d_K == 0: +-inf or NaN, both rejected below (Plane.cu:55)
+        const float pi = fmaf(di, t, oi), pj = fmaf(dj, t, oj);
+        const bool closer = t < best.t || (t == best.t && obj < best.obj);
+        const bool ok_hit = t > (float)IPT_MARGIN && closer && pi >= a.y && pi <= a.z && pj >= a.w && pj <= b.x && obj != self;
+        if (ok_hit) { best.t = t; best.obj = obj; best.code = ((uint32_t)(K + 1) << 28) | s; }
+    }
+}
+
+// Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.
+__device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<float>& o, const V3<float>& d, uint32_t self, bool onSurf)
+{
+    FastHit best;
+    best.t = (float)IPT_INF; best.obj = NO_OBJECT; best.code = NO_OBJECT;
+#pragma unroll 3
+    for (uint32_t s = 0; s < f.n_sph; s++) {
+        const float4 sp = f.sph[s];
+        const uint32_t obj = f.sph_obj[s];
+        const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);
+        const float b = dot(op, d);
+        const float delta = fmaf(b, b, fmaf(sp.w, sp.w, -dot(op, op)));       // b*b - op.op + r*r   (Sphere.cu:31)
+        const float sq = sqrt_fast(fmaxf(delta, 0.f));
+        const float t1 = -b - sq, t2 = sq - b;
+        float t = t1 > (float)IPT_MARGIN ? t1 : t2;
+        bool ok_hit = delta >= 0.f;
+        if (obj == self && onSurf) { t = -2.f * b; ok_hit = true; }            // start point lies ON this sphere: exact second root
+        ok_hit = ok_hit && t > (float)IPT_MARGIN && (t < best.t || (t == best.t && obj < best.obj));
+        if (ok_hit) { best.t = t; best.obj = obj; best.code = s; }
+    }
+    fast_axis_list<0>(f.ax[0], f.n_ax[0], o, d, rcp_fast(d.x), self, best);
+    fast_axis_list<1>(f.ax[1], f.n_ax[1], o, d, rcp_fast(d.y), self, best);
+    fast_axis_list<2>(f.ax[2], f.n_ax[2], o, d, rcp_fast(d.z), self, best);
+    for (uint32_t s = 0; s < f.n_gen; s++) {
+        Hit<float> h;
+        h.t = best.t; h.obj = best.obj; h.slot = NO_OBJECT;
+        test_rect<float>(f.gen + 4 * s, s, f.gen_obj[s], o, d, self, h);
+        if (h.slot != NO_OBJECT) { best.t = h.t; best.obj = h.obj; best.code = (4u << 28) | s; }
+    }
+    return best;
+}
+
+// Branch-free variant of scatter<float>: all candidate directions are computed, the material selects.
+__device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_t code, int reflection, V3<float> P, V3<float> in,
+                                                     uint32_t depth, uint4 rnd)
+{
+    const uint32_t kind = code >> 28, idx = code & 0x0FFFFFFFu;
+    V3<float> raw, n;
+    if (kind == 0) {
+        const float4 sp = f.sph[idx];
+        raw = normalize(mk<float>(P.x - sp.x, P.y - sp.y, P.z - sp.z));       // Sphere.cu:44
+        n = dot(in, raw) < 0.f ? -raw : raw;                                  // Sphere.cu:45
+    } else {
+        V3<float> pn;
+        if (kind == 4) pn = xyz(f.gen[4 * idx]);
+        else pn = mk<float>(kind == 1 ? 1.f : 0.f, kind == 2 ? 1.f : 0.f, kind == 3 ? 1.f : 0.f);
+        n = dot(in, pn) < 0.f ? pn : -pn;                                     // Plane.cu:73
+        raw = n;                                                              // Plane.cu:79
+    }
+    const V3<float> diff = diffuse_dir(n, rnd);                               // AObject.hpp:35-45
+    const V3<float> spec = reflect_dir(in, n);                                // AObject.hpp:30-33
+    V3<float> refr;
+    const bool refr_ok = refract_dir(in, raw, refr);                          // AObject.hpp:47-60
+    const float u = u23<float>(rnd.w);
+    Spawn<float> s;
+    s.has0 = reflection >= 0 && reflection <= 2; s.has1 = false; s.w0 = 1.f; s.w1 = 0.f;
+    s.d0 = diff; s.d1 = diff;
+    if (reflection == 1) {                                                    // AObject.hpp:83-102
+        if (depth < 2) { s.d0 = spec; s.w0 = 0.92f; s.w1 = 0.08f; s.has1 = true; }
+        else if (!(u > 0.9f)) s.d0 = spec;
+    } else if (reflection == 2) {                                             // AObject.hpp:110-135
+        if (!refr_ok) s.d0 = spec;
+        else if (depth < 2) { s.d0 = refr; s.w0 = 0.95f; s.d1 = spec; s.w1 = 0.05f; s.has1 = true; }
+        else s.d0 = (u > 0.95f) ? spec : refr;
+    }
+    return s;
+}
+
 }  // namespace ipt

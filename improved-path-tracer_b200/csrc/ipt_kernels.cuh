@@ -45,6 +45,8 @@ template <typename R> struct KParams {
     unsigned long long* traced; // total nearest-hit queries (stats)
     unsigned long long* frame;  // 3 x 64-bit accumulators per pixel (fixed point, or fp64 bits with IPT_FLAG_FLOAT_ACCUM)
     double fixed_scale;
+    const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
+    uint32_t fast_words;
 };
 
 // Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
@@ -205,6 +207,106 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                 }
             }
             // ---- compaction: one atomic per warp
+            const uint32_t m_live = __ballot_sync(0xffffffffu, live);
+            const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
+            my_traced += __popc(m_live);
+            const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
+            if (tot) {
+                uint32_t ob = 0;
+                if (lane == 0) ob = atomicAdd(out_count, tot);
+                ob = __shfl_sync(0xffffffffu, ob, 0);
+                if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
+                if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
+            }
+        }
+    }
+    if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
+}
+
+// fp32 contributions are exact in fixed point without going through fp64: v * 2^k is exact in fp32.
+__device__ __forceinline__ void accumulate_fast(const KParams<float>& p, uint32_t pixel, V3<float> v)
+{
+    unsigned long long* f = p.frame + 3ull * pixel;
+    if (p.flags & 0x4u) {
+        atomicAdd(reinterpret_cast<double*>(f), (double)v.x);
+        atomicAdd(reinterpret_cast<double*>(f) + 1, (double)v.y);
+        atomicAdd(reinterpret_cast<double*>(f) + 2, (double)v.z);
+    } else {
+        const float sc = (float)p.fixed_scale;
+        atomicAdd(f, (unsigned long long)__float2ll_rn(v.x * sc));
+        atomicAdd(f + 1, (unsigned long long)__float2ll_rn(v.y * sc));
+        atomicAdd(f + 2, (unsigned long long)__float2ll_rn(v.z * sc));
+    }
+}
+
+// The product kernel for brute-force scenes: same wavefront step as k_bounce<float, MODE_BRUTE, FIRST>, on the typed
+// fp32 scene lists (FastScene) with branch-free intersection and scatter.
+template <bool FIRST>
+__global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_constant__ KParams<float> p)
+{
+    extern __shared__ uint4 smem[];
+    stage(smem, p.fast_blob, p.fast_words);
+    __syncthreads();
+    const FastScene sc = fast_view(smem);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.depth];
+    const uint32_t depth = p.depth;
+    uint32_t* work = p.counters + WORK + depth;
+    uint32_t* out_count = p.counters + CNT + depth + 1;
+    const bool may_continue = depth + 1 < p.maxDepth;
+    unsigned long long my_traced = 0;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, (uint32_t)GRAB);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_in) break;
+#pragma unroll 1
+        for (uint32_t k = 0; k < GRAB; k += 32) {
+            const uint32_t i = base + k + lane;
+            bool live = i < n_in;
+            Ray<float> r;
+            if (FIRST) {
+                uint32_t px = 0, pz = 0, sample = 0;
+                live = live && decode_sample(p, i, px, pz, sample);
+                if (live) camera_ray(p, px, pz, sample, r);
+            } else if (live) {
+                q_load(p.qin, i, r);
+            }
+            bool has0 = false, has1 = false;
+            Ray<float> o0, o1;
+            if (live) {
+                const FastHit h = nearest_fast(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
+                if (h.code != NO_OBJECT) {
+                    const uint32_t obj = h.obj & ~RECT_BIT;
+                    const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
+                    if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
+                    V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
+                    const bool go = may_continue && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
+                    if (go) {
+                        const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
+                        const V3<float> P = r.o + r.d * h.t;
+                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.key0, p.key1);
+                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
+                        bool alive = sp.has0;
+                        if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
+                            const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
+                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.key0, p.key1);
+                            if (u23<float>(rr.x) >= q) alive = false;
+                            else nthr = nthr * (1.f / q);
+                        }
+                        const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
+                        has0 = alive;
+                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.obj;
+                        o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
+                        has1 = sp.has1;
+                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.obj;
+                        o1.meta = make_meta(depth + 1, depth == 0 ? 2u : 1u, depth == 0, onS, sample);
+                    }
+                }
+            }
             const uint32_t m_live = __ballot_sync(0xffffffffu, live);
             const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
             my_traced += __popc(m_live);

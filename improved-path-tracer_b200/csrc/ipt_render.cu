@@ -74,6 +74,8 @@ struct ipt_ctx {
     void *geom32 = nullptr, *geom64 = nullptr, *mat32 = nullptr, *mat64 = nullptr;
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
+    uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
+    uint32_t fast_words = 0;
     // render state
     uint4* q[2] = {nullptr, nullptr};
     size_t q_bytes = 0;
@@ -127,8 +129,8 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
 
 static void free_scene(ipt_ctx* c)
 {
-    cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes);
-    c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr;
+    cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob);
+    c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr; c->fast_blob = nullptr; c->fast_words = 0;
     c->have_scene = false;
 }
 
@@ -146,6 +148,66 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
+}
+
+// fp32 brute-force layout (see FastScene in ipt_device.cuh): spheres, axis-aligned rectangles per normal axis,
+// general rectangles, materials.  Built in fp64 from the flattened scene, rounded once to fp32.
+static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
+{
+    struct AxRect { float pk, loI, hiI, loJ, hiJ; uint32_t obj; };
+    std::vector<AxRect> ax[3];
+    std::vector<uint32_t> gen;
+    auto axis_of = [](const double* v, int& k, double& sign) {
+        k = -1;
+        for (int i = 0; i < 3; i++) {
+            if (std::fabs(std::fabs(v[i]) - 1.0) <= 1e-12) { if (k >= 0) return false; k = i; sign = v[i]; }
+            else if (std::fabs(v[i]) > 1e-12) return false;
+        }
+        return k >= 0;
+    };
+    for (uint32_t j = 0; j < s->n_rects; j++) {
+        const double *pl = s->rect_plane + 4 * (size_t)j, *u = s->rect_u + 4 * (size_t)j, *v = s->rect_v + 4 * (size_t)j, *b = s->rect_bounds + 4 * (size_t)j;
+        int K, iu, iv; double sk, su, sv;
+        const bool aa = axis_of(pl, K, sk) && axis_of(u, iu, su) && axis_of(v, iv, sv) && b[0] == 0.0 && b[2] == 0.0 && iu != iv && iu != K && iv != K;
+        if (!aa) { gen.push_back(j); continue; }
+        const int I = K == 0 ? 1 : 0;
+        const double cu = u[3] / su, cv = v[3] / sv;   // centre coordinates along the two in-plane axes
+        AxRect r;
+        r.pk = (float)(pl[3] / sk);
+        const double loU = cu - b[1], hiU = cu + b[1], loV = cv - b[3], hiV = cv + b[3];
+        if (iu == I) { r.loI = (float)loU; r.hiI = (float)hiU; r.loJ = (float)loV; r.hiJ = (float)hiV; }
+        else { r.loI = (float)loV; r.hiI = (float)hiV; r.loJ = (float)loU; r.hiJ = (float)hiU; }
+        r.obj = s->rect_object[j] | RECT_BIT;
+        ax[K].push_back(r);
+    }
+    const uint32_t ns = s->n_spheres, ng = (uint32_t)gen.size(), no = s->n_objects;
+    const uint32_t words = fast_blob_words(ns, (uint32_t)ax[0].size(), (uint32_t)ax[1].size(), (uint32_t)ax[2].size(), ng, no);
+    std::vector<uint32_t> blob((size_t)words * 4, 0u);
+    auto F = [](double x) { float f = (float)x; uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    auto Ff = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    uint32_t* p = blob.data();
+    p[0] = ns; p[1] = (uint32_t)ax[0].size(); p[2] = (uint32_t)ax[1].size(); p[3] = (uint32_t)ax[2].size(); p[4] = ng; p[5] = no;
+    p += 8;
+    for (uint32_t i = 0; i < ns; i++) for (int k = 0; k < 4; k++) *p++ = F(s->sphere_cxyzr[4 * (size_t)i + k]);
+    for (uint32_t i = 0; i < (ns + 3) / 4 * 4; i++) *p++ = i < ns ? s->sphere_object[i] : NO_OBJECT;
+    for (int k = 0; k < 3; k++)
+        for (const AxRect& r : ax[k]) { *p++ = Ff(r.pk); *p++ = Ff(r.loI); *p++ = Ff(r.hiI); *p++ = Ff(r.loJ); *p++ = Ff(r.hiJ); *p++ = r.obj; *p++ = 0; *p++ = 0; }
+    for (uint32_t j : gen) {
+        for (int k = 0; k < 4; k++) *p++ = F(s->rect_plane[4 * (size_t)j + k]);
+        for (int k = 0; k < 4; k++) *p++ = F(s->rect_u[4 * (size_t)j + k]);
+        for (int k = 0; k < 4; k++) *p++ = F(s->rect_v[4 * (size_t)j + k]);
+        for (int k = 0; k < 4; k++) *p++ = F(s->rect_bounds[4 * (size_t)j + k]);
+    }
+    for (uint32_t i = 0; i < (ng + 3) / 4 * 4; i++) *p++ = i < ng ? (s->rect_object[gen[i]] | RECT_BIT) : NO_OBJECT;
+    for (uint32_t k = 0; k < no; k++) {
+        bool anyE = false;
+        for (int j = 0; j < 3; j++) anyE = anyE || s->mat_emission[3 * (size_t)k + j] != 0.0;
+        for (int j = 0; j < 3; j++) *p++ = F(s->mat_color[3 * (size_t)k + j]);
+        *p++ = F((double)s->mat_reflection[k]);
+        for (int j = 0; j < 3; j++) *p++ = F(s->mat_emission[3 * (size_t)k + j]);
+        *p++ = F(anyE ? 1.0 : 0.0);
+    }
+    return blob;
 }
 
 // Host -> device copy of the scene.  Builds the slot arrays (BVH leaf order, or spheres then rectangles), the
@@ -247,12 +309,21 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> blob;
+    if (!bvh) {
+        blob = build_fast_blob(s);
+        if (blob.size() * 4 <= 200 * 1024) {
+            CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
+            CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            c->fast_words = (uint32_t)(blob.size() / 4);
+        }
+    }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total;
+    c->last.h2d_bytes = total + blob.size() * 4;
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -272,6 +343,22 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 }
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
+
+template <bool FIRST>
+static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
+{
+    auto kern = k_bounce_fast<FIRST>;
+    const size_t smem = (size_t)kp.fast_words * 16;
+    if (*grid_cache == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, smem));
+        if (per_sm < 1) { set_err("fast kernel does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
+        *grid_cache = per_sm * c->sm_count;
+    }
+    kern<<<*grid_cache, BLOCK_THREADS, smem, c->stream>>>(kp);
+    return IPT_OK;
+}
 
 template <typename R, int MODE, bool FIRST>
 static int launch_bounce(ipt_ctx* c, const KParams<R>& kp, size_t smem, int* grid_cache)
@@ -367,6 +454,9 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
                             : ((size_t)c->n_slots * 4 + (size_t)c->n_objects * 2) * sizeof(R4<R>) + ((size_t)c->n_slots + 3) / 4 * 16;
     if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
 
+    // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
+    const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && !std::getenv("IPT_GENERIC_KERNEL");
+    kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -386,7 +476,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             kp.qin = Queue{c->q[(d + 1) & 1], cap};
             kp.qout = Queue{c->q[d & 1], cap};
             int rc;
-            if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
+            if (use_fast) rc = d == 0 ? launch_bounce_fast<true>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false>(c, (const KParams<float>&)kp, &grid_next);
+            else if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
             else rc = bvh ? launch_bounce<R, MODE_BVH, false>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false>(c, kp, smem, &grid_next);
             if (rc) return rc;
             launches++;
