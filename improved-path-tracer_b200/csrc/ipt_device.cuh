@@ -57,10 +57,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        // one 32x32->64 multiply each (IMAD.WIDE); the round keys k + r*W are uniform across the grid
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t kr0 = k0 + (uint32_t)r * 0x9E3779B9u, kr1 = k1 + (uint32_t)r * 0xBB67AE85u;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ kr0; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ kr1; c3 = (uint32_t)p0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -358,15 +358,21 @@ __device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int ref
 // Brute-force scenes in fp32 (the product path for the three shipped scenes and BASELINE config 4): the scene is
 // re-laid out by ipt_ctx_set_scene into typed lists so that each list's test is a short branch-free sequence:
 //   spheres                  float4 {c.xyz, r}
-//   axis-aligned rectangles  per axis K (normal = +-e_K): float4 {p_K, lo_I, hi_I, lo_J}, float4 {hi_J, obj bits, 0, 0}
+//   axis-aligned rectangles  per axis K (normal = +-e_K): float4 {p_K, c_I, c_J, h_I}, float4 {h_J, obj bits, 0, 0}
 //                            with I, J the two other axes in increasing order — t = (p_K - o_K) / d_K, inside iff
-//                            lo <= P <= hi on both axes.  Same test as Plane.cu:47-100 for n = +-e_K (all rectangles
-//                            of spheres/mirrors/maze.json are of this kind).
+//                            |P_I - c_I| <= h_I and |P_J - c_J| <= h_J.  Same test as Plane.cu:47-100 for n = +-e_K
+//                            (all rectangles of spheres/mirrors/maze.json are of this kind).
 //   general rectangles       the 4 x float4 slot of the generic path
+// Every list is kept in object (JSON) order and updated with a strict '<', so among primitives of one list the lowest
+// object index wins exact ties in t, as in Renderer.cu:235 (coplanar overlapping rectangles share a list; ties across
+// lists need a ray through a geometric edge).  A hit on an axis-aligned rectangle sets the hit point's K coordinate to
+// p_K exactly, so the next ray's test against that plane (and any coplanar one) gives t = 0 and fails `t > 1e-4`
+// exactly like the reference's fp64 arithmetic does — no per-primitive self comparison is needed in these lists.
 // Blob layout in 16-byte words: {n_sph, n_x, n_y, n_z} {n_gen, n_objects, 0, 0} sph[] sph_obj[] x[] y[] z[] gen[] gen_obj[] mat[]
 struct FastScene {
     const float4* sph; const uint32_t* sph_obj; uint32_t n_sph;
-    const float4* ax[3]; uint32_t n_ax[3];
+    const float4* axs;                       // the three axis lists back to back; list K starts at record ax0[K]
+    uint32_t ax0_x, ax0_y, ax0_z, n_x, n_y, n_z;
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
 };
@@ -374,23 +380,26 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 {
     return 2 + n_sph + (n_sph + 3) / 4 + 2 * (nx + ny + nz) + 4 * n_gen + (n_gen + 3) / 4 + 2 * n_obj;
 }
-__device__ __forceinline__ FastScene fast_view(const uint4* blob)
+// The list sizes come in as kernel parameters (uniform registers / constant bank), not from the blob in shared memory.
+struct FastHeader { uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj; };
+__device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    const uint4 h0 = blob[0], h1 = blob[1];
     const uint4* p = blob + 2;
-    f.n_sph = h0.x; f.n_ax[0] = h0.y; f.n_ax[1] = h0.z; f.n_ax[2] = h0.w; f.n_gen = h1.x;
+    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen;
     f.sph = reinterpret_cast<const float4*>(p); p += f.n_sph;
     f.sph_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_sph + 3) / 4;
-    for (int k = 0; k < 3; k++) { f.ax[k] = reinterpret_cast<const float4*>(p); p += 2 * f.n_ax[k]; }
+    f.axs = reinterpret_cast<const float4*>(p); p += 2 * (f.n_x + f.n_y + f.n_z);
+    f.ax0_x = 0; f.ax0_y = f.n_x; f.ax0_z = f.n_x + f.n_y;
     f.gen = reinterpret_cast<const R4<float>*>(p); p += 4 * f.n_gen;
     f.gen_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_gen + 3) / 4;
     f.mat = reinterpret_cast<const float4*>(p);
     return f;
 }
 
-// hit code: kind[28:32) (0 sphere, 1..3 axis-aligned rectangle with normal e_(kind-1), 4 general rectangle) | list index
-struct FastHit { float t; uint32_t obj; uint32_t code; };
+// hit code: kind[28:32) (0 sphere, 1..3 axis-aligned rectangle with normal e_(kind-1), 4 general rectangle) | index in
+// the sphere list / the concatenated axis lists / the general list
+struct FastHit { float t; uint32_t code; };
 
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -398,20 +407,20 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ft
 template <int K> __device__ __forceinline__ float comp(const V3<float>& v) { return K == 0 ? v.x : (K == 1 ? v.y : v.z); }
 
 template <int K>
-__device__ __forceinline__ void fast_axis_list(const float4* list, uint32_t n, const V3<float>& o, const V3<float>& d, float inv_dk,
-                                               uint32_t self, FastHit& best)
+__device__ __forceinline__ void fast_axis_list(const float4* __restrict__ axs, uint32_t first, uint32_t n, const V3<float>& o,
+                                               const V3<float>& d, float inv_dk, FastHit& best)
 {
     constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
     const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
 #pragma unroll 4
-    for (uint32_t s = 0; s < n; s++) {
-        const float4 a = list[2 * s], b = list[2 * s + 1];
-        const uint32_t obj = __float_as_uint(b.y);
+    for (uint32_t s = first; s < first + n; s++) {
+        const float4 a = axs[2 * s];
+        const float hj = axs[2 * s + 1].x;
         const float t = (a.x - ok) * inv_dk;                     // d_K == 0: +-inf or NaN, both rejected below (Plane.cu:55)
-        const float pi = fmaf(di, t, oi), pj = fmaf(dj, t, oj);
-        const bool closer = t < best.t || (t == best.t && obj < best.obj);
-        const bool ok_hit = t > (float)IPT_MARGIN && closer && pi >= a.y && pi <= a.z && pj >= a.w && pj <= b.x && obj != self;
-        if (ok_hit) { best.t = t; best.obj = obj; best.code = ((uint32_t)(K + 1) << 28) | s; }
+        const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
+        const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
+        best.t = hit ? t : best.t;
+        best.code = hit ? (((uint32_t)(K + 1) << 28) | s) : best.code;
     }
 }
 
@@ -419,32 +428,51 @@ __device__ __forceinline__ void fast_axis_list(const float4* list, uint32_t n, c
 __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<float>& o, const V3<float>& d, uint32_t self, bool onSurf)
 {
     FastHit best;
-    best.t = (float)IPT_INF; best.obj = NO_OBJECT; best.code = NO_OBJECT;
+    best.t = (float)IPT_INF; best.code = NO_OBJECT;
 #pragma unroll 3
     for (uint32_t s = 0; s < f.n_sph; s++) {
         const float4 sp = f.sph[s];
-        const uint32_t obj = f.sph_obj[s];
+        const bool selfS = onSurf && f.sph_obj[s] == self;       // start point lies ON this sphere: exact second root -2b
         const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);
         const float b = dot(op, d);
         const float delta = fmaf(b, b, fmaf(sp.w, sp.w, -dot(op, op)));       // b*b - op.op + r*r   (Sphere.cu:31)
         const float sq = sqrt_fast(fmaxf(delta, 0.f));
         const float t1 = -b - sq, t2 = sq - b;
         float t = t1 > (float)IPT_MARGIN ? t1 : t2;
-        bool ok_hit = delta >= 0.f;
-        if (obj == self && onSurf) { t = -2.f * b; ok_hit = true; }            // start point lies ON this sphere: exact second root
-        ok_hit = ok_hit && t > (float)IPT_MARGIN && (t < best.t || (t == best.t && obj < best.obj));
-        if (ok_hit) { best.t = t; best.obj = obj; best.code = s; }
+        t = selfS ? -2.f * b : t;
+        const bool hit = (delta >= 0.f || selfS) && t > (float)IPT_MARGIN && t < best.t;
+        best.t = hit ? t : best.t;
+        best.code = hit ? s : best.code;
     }
-    fast_axis_list<0>(f.ax[0], f.n_ax[0], o, d, rcp_fast(d.x), self, best);
-    fast_axis_list<1>(f.ax[1], f.n_ax[1], o, d, rcp_fast(d.y), self, best);
-    fast_axis_list<2>(f.ax[2], f.n_ax[2], o, d, rcp_fast(d.z), self, best);
+    fast_axis_list<0>(f.axs, f.ax0_x, f.n_x, o, d, rcp_fast(d.x), best);
+    fast_axis_list<1>(f.axs, f.ax0_y, f.n_y, o, d, rcp_fast(d.y), best);
+    fast_axis_list<2>(f.axs, f.ax0_z, f.n_z, o, d, rcp_fast(d.z), best);
     for (uint32_t s = 0; s < f.n_gen; s++) {
         Hit<float> h;
-        h.t = best.t; h.obj = best.obj; h.slot = NO_OBJECT;
+        h.t = best.t; h.obj = NO_OBJECT; h.slot = NO_OBJECT;     // obj = max: strict '<' within this (ordered) list
         test_rect<float>(f.gen + 4 * s, s, f.gen_obj[s], o, d, self, h);
-        if (h.slot != NO_OBJECT) { best.t = h.t; best.obj = h.obj; best.code = (4u << 28) | s; }
+        if (h.slot != NO_OBJECT) { best.t = h.t; best.code = (4u << 28) | s; }
     }
     return best;
+}
+
+// Object id (with RECT_BIT) of a hit code, and the hit point with the axis-aligned snap described above.
+__device__ __forceinline__ uint32_t fast_hit_object(const FastScene& f, uint32_t code)
+{
+    const uint32_t kind = code >> 28, idx = code & 0x0FFFFFFFu;
+    if (kind == 0) return f.sph_obj[idx];
+    if (kind == 4) return f.gen_obj[idx];
+    return __float_as_uint(f.axs[2 * idx + 1].y);
+}
+__device__ __forceinline__ V3<float> fast_hit_point(const FastScene& f, uint32_t code, const V3<float>& o, const V3<float>& d, float t)
+{
+    V3<float> P = mk<float>(fmaf(d.x, t, o.x), fmaf(d.y, t, o.y), fmaf(d.z, t, o.z));
+    const uint32_t kind = code >> 28;
+    if (kind >= 1 && kind <= 3) {
+        const float pk = f.axs[2 * (code & 0x0FFFFFFFu)].x;
+        P.x = kind == 1 ? pk : P.x; P.y = kind == 2 ? pk : P.y; P.z = kind == 3 ? pk : P.z;
+    }
+    return P;
 }
 
 // Branch-free variant of scatter<float>: all candidate directions are computed, the material selects.
@@ -466,20 +494,24 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
     }
     const V3<float> diff = diffuse_dir(n, rnd);                               // AObject.hpp:35-45
     const V3<float> spec = reflect_dir(in, n);                                // AObject.hpp:30-33
-    V3<float> refr;
+    V3<float> refr = spec;
     const bool refr_ok = refract_dir(in, raw, refr);                          // AObject.hpp:47-60
     const float u = u23<float>(rnd.w);
+    const bool early = depth < 2;
+    const bool isSpec = reflection == 1, isRefr = reflection == 2;
+    // main ray: diffuse -> diff; specular -> spec (depth<2, or u <= 0.9), else diff; refractive -> spec on TIR or
+    // (depth>=2 and u > 0.95), else refr
+    const bool pickSpec = (isSpec && (early || !(u > 0.9f))) || (isRefr && (!refr_ok || (!early && u > 0.95f)));
+    const bool pickRefr = isRefr && !pickSpec;
     Spawn<float> s;
-    s.has0 = reflection >= 0 && reflection <= 2; s.has1 = false; s.w0 = 1.f; s.w1 = 0.f;
-    s.d0 = diff; s.d1 = diff;
-    if (reflection == 1) {                                                    // AObject.hpp:83-102
-        if (depth < 2) { s.d0 = spec; s.w0 = 0.92f; s.w1 = 0.08f; s.has1 = true; }
-        else if (!(u > 0.9f)) s.d0 = spec;
-    } else if (reflection == 2) {                                             // AObject.hpp:110-135
-        if (!refr_ok) s.d0 = spec;
-        else if (depth < 2) { s.d0 = refr; s.w0 = 0.95f; s.d1 = spec; s.w1 = 0.05f; s.has1 = true; }
-        else s.d0 = (u > 0.95f) ? spec : refr;
-    }
+    s.d0.x = pickSpec ? spec.x : (pickRefr ? refr.x : diff.x);
+    s.d0.y = pickSpec ? spec.y : (pickRefr ? refr.y : diff.y);
+    s.d0.z = pickSpec ? spec.z : (pickRefr ? refr.z : diff.z);
+    s.has0 = reflection >= 0 && reflection <= 2;
+    s.has1 = early && (isSpec || (isRefr && refr_ok));                        // AObject.hpp:91-94, :122-125
+    s.w0 = s.has1 ? (isSpec ? 0.92f : 0.95f) : 1.f;
+    s.w1 = isSpec ? 0.08f : 0.05f;
+    s.d1.x = isSpec ? diff.x : spec.x; s.d1.y = isSpec ? diff.y : spec.y; s.d1.z = isSpec ? diff.z : spec.z;
     return s;
 }
 

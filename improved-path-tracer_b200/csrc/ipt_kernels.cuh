@@ -47,6 +47,7 @@ template <typename R> struct KParams {
     double fixed_scale;
     const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
     uint32_t fast_words;
+    FastHeader fast_hd;
 };
 
 // Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
@@ -241,15 +242,25 @@ __device__ __forceinline__ void accumulate_fast(const KParams<float>& p, uint32_
 
 // The product kernel for brute-force scenes: same wavefront step as k_bounce<float, MODE_BRUTE, FIRST>, on the typed
 // fp32 scene lists (FastScene) with branch-free intersection and scatter.
+//
+// Work distribution and compaction are per CTA here: a CTA claims CTA_GRAB rays with one atomic, and the continuation
+// rays of each 256-ray slice are compacted warp ballot -> per-warp counts in shared memory -> ONE global atomic per
+// slice.  (One atomic per warp, as in k_bounce, serialises on the queue counter at ~0.9 G atomics/s on B200, which
+// capped these scenes at ~29 Grays/s: profiles/r01_*.)
+static constexpr int CTA_SLICES = 4;
+static constexpr int CTA_GRAB = BLOCK_THREADS * CTA_SLICES;
+static constexpr int WARPS = BLOCK_THREADS / 32;
+
 template <bool FIRST>
-__global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_constant__ KParams<float> p)
+__global__ void __launch_bounds__(BLOCK_THREADS, 4) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
     extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_base, s_tot[WARPS], s_off[WARPS];
     stage(smem, p.fast_blob, p.fast_words);
     __syncthreads();
-    const FastScene sc = fast_view(smem);
+    const FastScene sc = fast_view(smem, p.fast_hd);
 
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.depth];
     const uint32_t depth = p.depth;
@@ -259,13 +270,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_c
     unsigned long long my_traced = 0;
 
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, (uint32_t)GRAB);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (threadIdx.x == 0) s_base = atomicAdd(work, (uint32_t)CTA_GRAB);
+        __syncthreads();
+        const uint32_t base = s_base;
         if (base >= n_in) break;
 #pragma unroll 1
-        for (uint32_t k = 0; k < GRAB; k += 32) {
-            const uint32_t i = base + k + lane;
+        for (uint32_t k = 0; k < CTA_GRAB; k += BLOCK_THREADS) {
+            const uint32_t i = base + k + threadIdx.x;
             bool live = i < n_in;
             Ray<float> r;
             if (FIRST) {
@@ -280,14 +291,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_c
             if (live) {
                 const FastHit h = nearest_fast(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
                 if (h.code != NO_OBJECT) {
-                    const uint32_t obj = h.obj & ~RECT_BIT;
+                    const uint32_t hobj = fast_hit_object(sc, h.code);
+                    const uint32_t obj = hobj & ~RECT_BIT;
                     const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
                     if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
                     V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
                     const bool go = may_continue && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
                     if (go) {
                         const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
-                        const V3<float> P = r.o + r.d * h.t;
+                        const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
                         const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.key0, p.key1);
                         const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
                         bool alive = sp.has0;
@@ -299,26 +311,41 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_c
                         }
                         const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
                         has0 = alive;
-                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.obj;
+                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = hobj;
                         o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
                         has1 = sp.has1;
-                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.obj;
+                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = hobj;
                         o1.meta = make_meta(depth + 1, depth == 0 ? 2u : 1u, depth == 0, onS, sample);
                     }
                 }
             }
+            // ---- compaction: ballot + popc per warp, shared-memory prefix per CTA, one global atomic per slice
             const uint32_t m_live = __ballot_sync(0xffffffffu, live);
             const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
             my_traced += __popc(m_live);
             const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
-            if (tot) {
-                uint32_t ob = 0;
-                if (lane == 0) ob = atomicAdd(out_count, tot);
-                ob = __shfl_sync(0xffffffffu, ob, 0);
-                if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
-                if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
+            if (lane == 0) s_tot[warp] = tot;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t v = lane < WARPS ? s_tot[lane] : 0u;
+                uint32_t incl = v;
+#pragma unroll
+                for (int dlt = 1; dlt < WARPS; dlt <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, dlt);
+                    if (lane >= (uint32_t)dlt) incl += n;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, WARPS - 1);
+                uint32_t gb = 0;
+                if (lane == 0 && total) gb = atomicAdd(out_count, total);
+                gb = __shfl_sync(0xffffffffu, gb, 0);
+                if (lane < WARPS) s_off[lane] = gb + incl - v;
             }
+            __syncthreads();
+            const uint32_t ob = s_off[warp];
+            if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
+            if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
         }
+        __syncthreads();   // s_base is rewritten by the next claim
     }
     if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
 }

@@ -76,6 +76,7 @@ struct ipt_ctx {
     float4* nodes = nullptr;
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
+    FastHeader fast_hd = {};
     // render state
     uint4* q[2] = {nullptr, nullptr};
     size_t q_bytes = 0;
@@ -154,7 +155,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
 // general rectangles, materials.  Built in fp64 from the flattened scene, rounded once to fp32.
 static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
 {
-    struct AxRect { float pk, loI, hiI, loJ, hiJ; uint32_t obj; };
+    struct AxRect { float pk, cI, cJ, hI, hJ; uint32_t obj; };
     std::vector<AxRect> ax[3];
     std::vector<uint32_t> gen;
     auto axis_of = [](const double* v, int& k, double& sign) {
@@ -174,9 +175,8 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         const double cu = u[3] / su, cv = v[3] / sv;   // centre coordinates along the two in-plane axes
         AxRect r;
         r.pk = (float)(pl[3] / sk);
-        const double loU = cu - b[1], hiU = cu + b[1], loV = cv - b[3], hiV = cv + b[3];
-        if (iu == I) { r.loI = (float)loU; r.hiI = (float)hiU; r.loJ = (float)loV; r.hiJ = (float)hiV; }
-        else { r.loI = (float)loV; r.hiI = (float)hiV; r.loJ = (float)loU; r.hiJ = (float)hiU; }
+        if (iu == I) { r.cI = (float)cu; r.hI = (float)b[1]; r.cJ = (float)cv; r.hJ = (float)b[3]; }
+        else { r.cI = (float)cv; r.hI = (float)b[3]; r.cJ = (float)cu; r.hJ = (float)b[1]; }
         r.obj = s->rect_object[j] | RECT_BIT;
         ax[K].push_back(r);
     }
@@ -191,7 +191,7 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
     for (uint32_t i = 0; i < ns; i++) for (int k = 0; k < 4; k++) *p++ = F(s->sphere_cxyzr[4 * (size_t)i + k]);
     for (uint32_t i = 0; i < (ns + 3) / 4 * 4; i++) *p++ = i < ns ? s->sphere_object[i] : NO_OBJECT;
     for (int k = 0; k < 3; k++)
-        for (const AxRect& r : ax[k]) { *p++ = Ff(r.pk); *p++ = Ff(r.loI); *p++ = Ff(r.hiI); *p++ = Ff(r.loJ); *p++ = Ff(r.hiJ); *p++ = r.obj; *p++ = 0; *p++ = 0; }
+        for (const AxRect& r : ax[k]) { *p++ = Ff(r.pk); *p++ = Ff(r.cI); *p++ = Ff(r.cJ); *p++ = Ff(r.hI); *p++ = Ff(r.hJ); *p++ = r.obj; *p++ = 0; *p++ = 0; }
     for (uint32_t j : gen) {
         for (int k = 0; k < 4; k++) *p++ = F(s->rect_plane[4 * (size_t)j + k]);
         for (int k = 0; k < 4; k++) *p++ = F(s->rect_u[4 * (size_t)j + k]);
@@ -316,6 +316,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
             CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
             CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
             c->fast_words = (uint32_t)(blob.size() / 4);
+            c->fast_hd = FastHeader{blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]};
         }
     }
     CK(cudaEventRecord(e1, c->stream));
@@ -456,7 +457,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
 
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && !std::getenv("IPT_GENERIC_KERNEL");
-    kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words;
+    kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
