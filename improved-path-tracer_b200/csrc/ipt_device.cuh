@@ -44,6 +44,8 @@ template <typename R> __device__ __forceinline__ V3<R> xyz(const R4<R>& q) { ret
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }  // Vec3.hpp:48-51: v * (1/sqrt(v.v))
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
 template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * rsqrt_(dot(a, a)); }
 
@@ -53,14 +55,21 @@ template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { retu
 // depend on how rays are scheduled, batched, tiled or split over GPUs.  The reference seeds one XORWOW stream per
 // CUDA thread (Renderer.cu:95-97) and walks it through ~1900 pixels, which no parallel schedule can reproduce;
 // parity with it is therefore statistical, and exact against the oracle run on this same counter stream.
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+// The ten round keys k + r*W are the same for every thread of a render: the host expands them once into the kernel
+// parameters (constant bank), so a round is two IMAD.WIDE and two LOP3 with a constant operand.
+struct PhiloxKeys { uint32_t k[20]; };
+__host__ __device__ inline PhiloxKeys philox_expand(uint32_t k0, uint32_t k1)
+{
+    PhiloxKeys ks;
+    for (int r = 0; r < 10; r++) { ks.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; ks.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    return ks;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        // one 32x32->64 multiply each (IMAD.WIDE); the round keys k + r*W are uniform across the grid
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
-        const uint32_t kr0 = k0 + (uint32_t)r * 0x9E3779B9u, kr1 = k1 + (uint32_t)r * 0xBB67AE85u;
-        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ kr0; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ kr1; c3 = (uint32_t)p0;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks.k[2 * r]; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks.k[2 * r + 1]; c3 = (uint32_t)p0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -305,7 +314,7 @@ template <typename R> __device__ __forceinline__ bool refract_dir(V3<R> in, V3<R
     const R cosI = fabs(dot(n, in));
     const R sin2 = (index * index) * ((R)1 - cosI * cosI);
     if (sin2 > (R)1) return false;
-    const R cosT = sqrt((R)1 - sin2);
+    const R cosT = sqrt_((R)1 - sin2);
     out = in * index + n * (index * cosI - cosT);
     return !(out.x == (R)0 && out.y == (R)0 && out.z == (R)0);   // AObject.hpp:117 compares the result with Vec3()
 }
@@ -412,8 +421,8 @@ __device__ __forceinline__ void fast_axis_list(const float4* __restrict__ axs, u
 {
     constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
     const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
-#pragma unroll 4
-    for (uint32_t s = first; s < first + n; s++) {
+#pragma unroll 2
+    for (uint32_t s = first; s < first + n; s++) {   // n is even: lists are padded with a never-hit record
         const float4 a = axs[2 * s];
         const float hj = axs[2 * s + 1].x;
         const float t = (a.x - ok) * inv_dk;                     // d_K == 0: +-inf or NaN, both rejected below (Plane.cu:55)
@@ -429,8 +438,8 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
 {
     FastHit best;
     best.t = (float)IPT_INF; best.code = NO_OBJECT;
-#pragma unroll 3
-    for (uint32_t s = 0; s < f.n_sph; s++) {
+#pragma unroll 2
+    for (uint32_t s = 0; s < f.n_sph; s++) {         // n_sph is even (padded with a never-hit sphere)
         const float4 sp = f.sph[s];
         const bool selfS = onSurf && f.sph_obj[s] == self;       // start point lies ON this sphere: exact second root -2b
         const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);

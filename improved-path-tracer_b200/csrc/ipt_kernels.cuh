@@ -33,7 +33,7 @@ template <typename R> struct KParams {
     uint32_t W, H, spp, maxDepth;
     uint32_t depth;             // depth of every ray in this pass
     uint32_t flags;
-    uint32_t key0, key1;
+    PhiloxKeys keys;
     // tile schedule of this rank: local tile lt -> global tile id tile_ids[lt]
     const uint32_t* tile_ids;
     uint32_t n_tiles_local, tiles_x, tile_w, tile_h;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void camera_ray(const KParams<R>& p, uint32_t px, uin
     const R stepZ = (pz < p.H / 2) ? (R)(p.H / 2 - pz) - corr : ((R)p.H / (R)2 - (R)pz - (R)1) + ((corr == (R)0) ? (R)1 : corr);
     r.d = normalize(p.camD + p.camX * stepX * p.fov + p.camZ * stepZ * p.fov);                       // :127
     const uint32_t pixel = pz * p.W + px;
-    const uint4 rnd = philox4x32_10(pixel, sample, NODE_CAMERA, CTR_TAG, p.key0, p.key1);
+    const uint4 rnd = philox4x32_10(pixel, sample, NODE_CAMERA, CTR_TAG, p.keys);
     const R jx = s24<R>(rnd.x), jz = s24<R>(rnd.y);                                                   // :133-134
     const V3<R> tent = p.camX * jx + p.camZ * jz;                                                     // :135
     const V3<R> origin = p.camO + p.camX * stepX + p.camZ * stepZ + tent;                             // :138
@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                         if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0) {
                             const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
                             const V3<R> P = r.o + r.d * h.t;                                       // :156,:179,:207
-                            const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.key0, p.key1);
+                            const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
                             const Spawn<R> sp = scatter<R>(isRect, sc.geom[4 * (size_t)h.slot], (int)m0.w, P, r.d, depth, rnd);
                             bool alive = sp.has0;
                             if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension, off by default)
                                 const R q = fmin((R)1, fmax((R)0.05, fmax(nthr.x, fmax(nthr.y, nthr.z))));
-                                const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.key0, p.key1);
+                                const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
                                 if (u23<R>(rr.x) >= q) alive = false;
                                 else nthr = nthr * ((R)1 / q);
                             }
@@ -251,8 +251,8 @@ static constexpr int CTA_SLICES = 4;
 static constexpr int CTA_GRAB = BLOCK_THREADS * CTA_SLICES;
 static constexpr int WARPS = BLOCK_THREADS / 32;
 
-template <bool FIRST>
-__global__ void __launch_bounds__(BLOCK_THREADS, 4) k_bounce_fast(const __grid_constant__ KParams<float> p)
+template <bool FIRST, int MINB>
+__global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_base, s_tot[WARPS], s_off[WARPS];
@@ -300,22 +300,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) k_bounce_fast(const __grid_c
                     if (go) {
                         const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
-                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.key0, p.key1);
+                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
                         const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
                         bool alive = sp.has0;
                         if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
-                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.key0, p.key1);
+                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
                             if (u23<float>(rr.x) >= q) alive = false;
                             else nthr = nthr * (1.f / q);
                         }
                         const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
                         has0 = alive;
                         o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = hobj;
-                        o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
+                        const uint32_t mcommon = (r.meta & 0xFFFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
+                        o0.meta = mcommon | (r.meta & 0x300u);
                         has1 = sp.has1;
                         o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = hobj;
-                        o1.meta = make_meta(depth + 1, depth == 0 ? 2u : 1u, depth == 0, onS, sample);
+                        o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
                     }
                 }
             }

@@ -180,7 +180,10 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         r.obj = s->rect_object[j] | RECT_BIT;
         ax[K].push_back(r);
     }
-    const uint32_t ns = s->n_spheres, ng = (uint32_t)gen.size(), no = s->n_objects;
+    // every list is padded to an even length with a record that can never be hit (the device loops are unrolled by 2)
+    for (int k = 0; k < 3; k++)
+        if (ax[k].size() & 1) ax[k].push_back(AxRect{3.0e38f, 0.f, 0.f, -1.f, -1.f, NO_OBJECT});
+    const uint32_t ns_real = s->n_spheres, ns = (ns_real + 1) & ~1u, ng = (uint32_t)gen.size(), no = s->n_objects;
     const uint32_t words = fast_blob_words(ns, (uint32_t)ax[0].size(), (uint32_t)ax[1].size(), (uint32_t)ax[2].size(), ng, no);
     std::vector<uint32_t> blob((size_t)words * 4, 0u);
     auto F = [](double x) { float f = (float)x; uint32_t u; std::memcpy(&u, &f, 4); return u; };
@@ -188,8 +191,9 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
     uint32_t* p = blob.data();
     p[0] = ns; p[1] = (uint32_t)ax[0].size(); p[2] = (uint32_t)ax[1].size(); p[3] = (uint32_t)ax[2].size(); p[4] = ng; p[5] = no;
     p += 8;
-    for (uint32_t i = 0; i < ns; i++) for (int k = 0; k < 4; k++) *p++ = F(s->sphere_cxyzr[4 * (size_t)i + k]);
-    for (uint32_t i = 0; i < (ns + 3) / 4 * 4; i++) *p++ = i < ns ? s->sphere_object[i] : NO_OBJECT;
+    for (uint32_t i = 0; i < ns; i++)
+        for (int k = 0; k < 4; k++) *p++ = i < ns_real ? F(s->sphere_cxyzr[4 * (size_t)i + k]) : F(k < 3 ? (double)NAN : 0.0);   // pad: NaN centre -> delta is NaN -> never a hit
+    for (uint32_t i = 0; i < (ns + 3) / 4 * 4; i++) *p++ = i < ns_real ? s->sphere_object[i] : (NO_OBJECT - 1u);
     for (int k = 0; k < 3; k++)
         for (const AxRect& r : ax[k]) { *p++ = Ff(r.pk); *p++ = Ff(r.cI); *p++ = Ff(r.cJ); *p++ = Ff(r.hI); *p++ = Ff(r.hJ); *p++ = r.obj; *p++ = 0; *p++ = 0; }
     for (uint32_t j : gen) {
@@ -345,10 +349,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
 
-template <bool FIRST>
+template <bool FIRST, int MINB>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
-    auto kern = k_bounce_fast<FIRST>;
+    auto kern = k_bounce_fast<FIRST, MINB>;
     const size_t smem = (size_t)kp.fast_words * 16;
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -419,7 +423,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.fov = (R)0.0009f;
     kp.W = c->W; kp.H = c->H; kp.spp = prm.samples; kp.maxDepth = prm.max_depth;
     kp.flags = prm.flags;
-    kp.key0 = (uint32_t)prm.seed; kp.key1 = (uint32_t)(prm.seed >> 32);
+    kp.keys = philox_expand((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
     kp.tile_ids = c->tile_ids; kp.n_tiles_local = (uint32_t)c->tile_host.size(); kp.tiles_x = tiles_x;
     kp.tile_w = tile_w; kp.tile_h = tile_h; kp.mt_x = tile_w / 8; kp.mt_per_tile = (tile_w / 8) * (tile_h / 4);
     kp.counters = c->counters; kp.traced = c->traced; kp.frame = c->frame;
@@ -457,6 +461,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
 
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && !std::getenv("IPT_GENERIC_KERNEL");
+    const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 4;   // A/B knob: CTAs per SM the fast kernel is compiled for
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
@@ -477,7 +482,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             kp.qin = Queue{c->q[(d + 1) & 1], cap};
             kp.qout = Queue{c->q[d & 1], cap};
             int rc;
-            if (use_fast) rc = d == 0 ? launch_bounce_fast<true>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false>(c, (const KParams<float>&)kp, &grid_next);
+            if (use_fast && fast_minb == 3) rc = d == 0 ? launch_bounce_fast<true, 3>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 3>(c, (const KParams<float>&)kp, &grid_next);
+            else if (use_fast) rc = d == 0 ? launch_bounce_fast<true, 4>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 4>(c, (const KParams<float>&)kp, &grid_next);
             else if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
             else rc = bvh ? launch_bounce<R, MODE_BVH, false>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false>(c, kp, smem, &grid_next);
             if (rc) return rc;
