@@ -77,6 +77,7 @@ struct ipt_ctx {
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
     FastHeader fast_hd = {};
+    size_t scene_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // sizes of the scene allocations (reused when unchanged)
     // render state
     uint4* q[2] = {nullptr, nullptr};
     size_t q_bytes = 0;
@@ -132,6 +133,7 @@ static void free_scene(ipt_ctx* c)
 {
     cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob);
     c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr; c->fast_blob = nullptr; c->fast_words = 0;
+    std::memset(c->scene_bytes, 0, sizeof(c->scene_bytes));
     c->have_scene = false;
 }
 
@@ -302,26 +304,30 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         std::memcpy(o + 12, ch, 8);
         o[14] = 0; o[15] = 0;
     }
-    free_scene(c);
-    CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
-    CK(cudaMalloc(&c->mat64, b_mat64)); CK(cudaMalloc(&c->mat32, b_mat32));
-    CK(cudaMalloc(&c->slot_obj, b_slot));
-    if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
+    std::vector<uint32_t> blob;
+    if (!bvh) { blob = build_fast_blob(s); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
+    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4};
+    if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom64) {
+        free_scene(c);
+        CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
+        CK(cudaMalloc(&c->mat64, b_mat64)); CK(cudaMalloc(&c->mat32, b_mat32));
+        CK(cudaMalloc(&c->slot_obj, b_slot));
+        if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
+        if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
+        std::memcpy(c->scene_bytes, want, sizeof(want));
+    }
+    c->have_scene = false;
     CK(cudaMemcpyAsync(c->geom64, g64, b_geom64, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->geom32, g32, b_geom32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->mat64, m64, b_mat64, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
-    std::vector<uint32_t> blob;
-    if (!bvh) {
-        blob = build_fast_blob(s);
-        if (blob.size() * 4 <= 200 * 1024) {
-            CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
-            CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
-            c->fast_words = (uint32_t)(blob.size() / 4);
-            c->fast_hd = FastHeader{blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]};
-        }
+    c->fast_words = 0;
+    if (!blob.empty()) {
+        CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        c->fast_words = (uint32_t)(blob.size() / 4);
+        c->fast_hd = FastHeader{blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]};
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -460,7 +466,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
 
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
-    const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && !std::getenv("IPT_GENERIC_KERNEL");
+    const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 4;   // A/B knob: CTAs per SM the fast kernel is compiled for
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));

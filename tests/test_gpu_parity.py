@@ -318,3 +318,16 @@ def test_tracer_program_surface(pyipt, oracle, tmp_path):
     # invalid input: message + exit code 0 (main.cu:30-33)
     r = subprocess.run([exe, "-s=3", str(scene)], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0 and "Number of samples out of range!" in r.stdout
+
+
+def test_single_process_multi_gpu_gather(pyipt, oracle):
+    """ipt_render(n_gpus=2): tiles interleaved over two devices of this process, rank 1's tiles stored straight into
+    device 0's frame over NVLink peer access; the frame equals the one-GPU frame bit for bit."""
+    if pyipt.lib().ipt_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    hs = pyipt.HostScene.load(oracle.scene_path("mirrors"), width=640, height=360)
+    one, s1 = pyipt.render(hs, 8, 10, seed=4, want64=False)
+    two, s2 = pyipt.render(hs, 8, 10, seed=4, n_gpus=2, want64=False)
+    assert np.array_equal(one, two)
+    assert s2["traced_bounces"] == s1["traced_bounces"] and s2["samples"] == s1["samples"]
+    assert s2["per_gpu_bounces"][0] > 0 and s2["per_gpu_bounces"][1] > 0
