@@ -3,6 +3,17 @@
 // (Renderer.cu:227-243).  The BVH must return the same nearest hit as that scan, so boxes are conservative:
 // padded for the +-5e-5 edge tolerance of Plane.cu:87-100, for the MARGIN = 1e-4 near-surface roots of
 // Sphere.cu:36-37 and for fp32 rounding of the bounds themselves.
+//
+// Non-unit directions.  Rays leaving a refractive sphere are not normalised (AObject.hpp:59) and Sphere::intersect is
+// used unchanged on them, so its "hit" is not the geometric one.  Culling by geometric boxes is still exact:
+//  * lengths never exceed 1: |T|^2 = 1 - eta^2 (1 - l^2) on entry and <= that on exit for an incoming length l <= 1;
+//    reflection keeps the length, the diffuse rule resets it to 1;
+//  * for |d| = l <= 1, with x = -(op.d^) > 0 and c = op.op - r^2 > 0 the reference's root is f(l x) and the geometric
+//    entry (in units of d) is f(x)/l with f(y) = y - sqrt(y^2 - c) = c / (y + sqrt(y^2 - c)); then
+//    l f(l x) = c / (x + sqrt(x^2 - c/l^2)) >= c / (x + sqrt(x^2 - c)) = f(x): the reported t is never in front of the
+//    sphere's (hence the box's) entry point, and delta_ref >= 0 implies the line does meet the sphere;
+//  * c <= 0 means the origin is inside the sphere, hence inside (or within the padding of) its box.
+// So a box that the reported hit needs is never culled by `entry <= best t`.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
