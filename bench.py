@@ -94,6 +94,13 @@ def physical_gpu_index(local):
     return local
 
 
+def spread_cells(n_cells, m):
+    """m distinct cells of the reference's 22x22 thread grid spread over the whole frame (multiplicative stride coprime
+    with the grid, so no row/column aliasing)."""
+    step = 197 if n_cells % 197 else 199
+    return sorted({(i * step + 5) % n_cells for i in range(m)})
+
+
 def run_reference(args, wl, rank):
     """The reference's own per-pixel routine on the host cores: a bounded sample of the workload per step."""
     if rank != 0:
@@ -109,30 +116,19 @@ def run_reference(args, wl, rank):
     # bounded sample: every `stride`-th reference cell (a cell = one reference CUDA thread's pixel rectangle,
     # Renderer.cu:33-53), reduced spp; throughput in samples/s does not depend on spp
     stride, spp = args.ref_stride, args.ref_spp
-    cells = list(range(0, n_cells, stride))
+    cells = spread_cells(n_cells, max(1, n_cells // stride))
     px_per_cell = (W * H) / n_cells
 
-    import numpy as np
-    path = O.scene_path(wl["scene"]).encode()
-    out = np.zeros((H, W, 3))
+    def one_step():
+        return O.ref_time_cells(wl["scene"], spp, wl["depth"], wl["width"], wl["height"], cells, cores)
 
-    # run the sampled cells in parallel: one thread per cell through a pool of `cores` workers
-    from concurrent.futures import ThreadPoolExecutor
-
-    def one_step_parallel():
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            list(ex.map(lambda c: O.ref().ref_render_cells(path, spp, wl["depth"], W if wl["width"] else 0, H if wl["height"] else 0,
-                                                          c, c + 1, 1, out.ctypes.data), cells))
-        return time.perf_counter() - t0
-
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        one_step_parallel()
-    times = [one_step_parallel() for _ in range(args.steps)]
+    for _ in range(min(args.warmup, 1)):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
     samples = len(cells) * px_per_cell * spp
     ms = 1e3 * sum(times) / len(times)
     value = samples / (ms * 1e-3) / 1e6
-    sample_desc = f"every {stride}th of the reference's {n_cells} thread cells ({len(cells)} cells, {int(samples)} samples) at {spp} spp, depth {wl['depth']}"
+    sample_desc = f"{len(cells)} of the reference's {n_cells} thread cells, spread over the frame ({int(samples)} samples) at {spp} spp, depth {wl['depth']}"
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": wl["desc"], "sample": sample_desc},
@@ -148,34 +144,18 @@ def cpu_baseline(wl, seconds_budget=20.0):
         import oracle as O
         if not O.ref_available():
             raise RuntimeError("oracle/_ref not built")
-        import numpy as np
-        from concurrent.futures import ThreadPoolExecutor
         cores = os.cpu_count() or 1
         W, H = wl["width"] or 1280, wl["height"] or 720
         n_cells = O.ref().ref_num_cells(W, H)
-        path = O.scene_path(wl["scene"]).encode()
-        out = np.zeros((H, W, 3))
+        cells = spread_cells(n_cells, min(n_cells, 4 * cores))
         spp = 4
-        cells = list(range(0, n_cells, max(1, n_cells // (4 * cores))))
-
-        def run(c):
-            O.ref().ref_render_cells(path, spp, wl["depth"], W if wl["width"] else 0, H if wl["height"] else 0, c, c + 1, 1, out.ctypes.data)
-
-        t0 = time.perf_counter()
-        done = 0
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            for _ in ex.map(run, cells):
-                done += 1
-        dt = time.perf_counter() - t0
+        dt = O.ref_time_cells(wl["scene"], spp, wl["depth"], wl["width"], wl["height"], cells, cores)
         # scale spp so that the sample takes ~seconds_budget, then time that
         spp = int(max(4, min(256, spp * seconds_budget / max(dt, 1e-3))))
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            list(ex.map(run, cells))
-        dt = time.perf_counter() - t0
+        dt = O.ref_time_cells(wl["scene"], spp, wl["depth"], wl["width"], wl["height"], cells, cores)
         samples = len(cells) * (W * H / n_cells) * spp
         return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                "sample": f"{len(cells)} of the reference's {n_cells} thread cells (evenly strided over the frame) at {spp} spp, depth {wl['depth']}: {int(samples)} samples in {dt:.1f} s, fp64"}
+                "sample": f"{len(cells)} of the reference's {n_cells} thread cells (spread over the frame) at {spp} spp, depth {wl['depth']}: {int(samples)} samples in {dt:.1f} s, fp64"}
     except Exception as e:   # the baseline is reported, never required for the GPU number
         return {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -192,6 +172,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--fp64", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
     ap.add_argument("--ref-stride", type=int, default=11)
     ap.add_argument("--ref-spp", type=int, default=8)
     args = ap.parse_args()
@@ -213,6 +194,10 @@ def main():
 
     import numpy as np
     import pyipt
+
+    if args.dry_run:
+        dry_run(args, wl, rank, world, pyipt)
+        return
 
     dist = None
     if world > 1:
@@ -348,6 +333,41 @@ def main():
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def shard(pyipt, W, H, tile_w, tile_h, rank, world):
+    """Tiles (and pixels) of `rank` under the library's static interleaved schedule (ipt_tile_owner)."""
+    tiles_x, tiles_y = (W + tile_w - 1) // tile_w, (H + tile_h - 1) // tile_h
+    L = pyipt.lib()
+    tiles = [(tx, ty) for ty in range(tiles_y) for tx in range(tiles_x) if L.ipt_tile_owner(tx, ty, tiles_x, world) == rank]
+    pixels = sum((min(W, (tx + 1) * tile_w) - tx * tile_w) * (min(H, (ty + 1) * tile_h) - ty * tile_h) for tx, ty in tiles)
+    return tiles, pixels
+
+
+def dry_run(args, wl, rank, world, pyipt):
+    """The N > 1 host logic on CPU (gloo): every rank computes its shard, the 64-byte frame handle goes round, sums and
+    maxima are reduced, rank 0 prints one line.  No rendering, no GPU: used by tests/test_distributed_cpu.py."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("gloo")
+    W, H = wl["width"] or 1280, wl["height"] or 720
+    tiles, pixels = shard(pyipt, W, H, 64, 32, rank, world)
+    handle = [bytes(range(64)) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(handle, src=0)
+    assert handle[0] == bytes(range(64))
+    tot = torch.tensor([float(pixels) * wl["spp"], float(len(tiles))], dtype=torch.float64)
+    mx = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"dry_run": True, "n_gpus": world, "samples_per_step": int(tot[0].item()), "tiles": int(tot[1].item()),
+                          "max_rank_plus_1": int(mx.item()), "my_tiles": len(tiles), "frame": [W, H], "scaling": "strong"}))
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

@@ -139,6 +139,8 @@ def ref():
         L = ctypes.CDLL(os.path.join(REF_DIR, "libref_host.so"))
         L.ref_render_cells.argtypes = [ctypes.c_char_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p]
         L.ref_render_cells.restype = ctypes.c_int
+        L.ref_render_cell_list.argtypes = [ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.ref_render_cell_list.restype = ctypes.c_int
         L.ref_scene_dims.argtypes = [ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3
         L.ref_num_cells.argtypes = [ctypes.c_int, ctypes.c_int]
         dp = ctypes.POINTER(ctypes.c_double)
@@ -190,6 +192,18 @@ def ref_render(path, samples, depth, width=0, height=0, cell_begin=0, cell_end=-
     if rc != 0:
         raise RuntimeError("ref_render_cells failed")
     return out
+
+
+def ref_time_cells(path, samples, depth, width, height, cells, nthreads=None):
+    """Wall time of the reference routine over the given thread cells (no image returned): bench.py's CPU baseline."""
+    import time
+    arr = (ctypes.c_int * len(cells))(*cells)
+    t0 = time.perf_counter()
+    rc = ref().ref_render_cell_list(scene_path(path).encode(), samples, depth, width or 0, height or 0, arr, len(cells),
+                                    nthreads or os.cpu_count() or 1, None)
+    if rc != 0:
+        raise RuntimeError("ref_render_cell_list failed")
+    return time.perf_counter() - t0
 
 
 def philox(counter, key):

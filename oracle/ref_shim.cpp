@@ -34,6 +34,7 @@ void operator delete[](void* p, std::size_t) noexcept { std::free(p); }
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -83,7 +84,10 @@ struct Loaded {
 Loaded load(const char* path, int W_override, int H_override)
 {
     Loaded l;
-    // SceneData prints "Loading Scene Data..." etc. on std::cout: silence it.
+    // SceneData prints "Loading Scene Data..." etc. on std::cout: silence it.  Swapping cout's buffer is not thread
+    // safe and callers may render cells from several threads: one load at a time.
+    static std::mutex load_mutex;
+    std::lock_guard<std::mutex> lock(load_mutex);
     std::streambuf* old = std::cout.rdbuf();
     std::ostringstream sink;
     std::cout.rdbuf(sink.rdbuf());
@@ -163,6 +167,33 @@ int ref_render_cells(const char* path, int samples, int depth, int W_override, i
         out_rgb[3 * i + 1] = img[i].yy_;
         out_rgb[3 * i + 2] = img[i].zz_;
     }
+    return 0;
+}
+
+// The same for an explicit list of cells (bench.py's bounded sample: cells strided over the frame), one call,
+// `nthreads` host threads.  out_rgb may be NULL (timing only).
+int ref_render_cell_list(const char* path, int samples, int depth, int W_override, int H_override,
+                         const int* cells, int n_cells, int nthreads, double* out_rgb)
+{
+    Loaded l = load(path, W_override, H_override);
+    if (!l.ok) return -1;
+    Vec3 vecZ = (l.cam.direction_ % l.cam.orientation_).norm();
+    const uint32_t nT = l.W <= 22 ? l.W : 22, nB = l.H <= 22 ? l.H : 22;
+    std::vector<Vec3> img((size_t)l.W * l.H);
+    std::atomic<int> next{0};
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n_cells) break;
+                if (cells[i] >= 0 && (uint32_t)cells[i] < nT * nB) run_cell(l, (uint32_t)cells[i], nT, (uint32_t)samples, (uint8_t)depth, img.data(), vecZ);
+            }
+        });
+    for (auto& th : pool) th.join();
+    if (out_rgb)
+        for (size_t i = 0; i < img.size(); i++) { out_rgb[3 * i] = img[i].xx_; out_rgb[3 * i + 1] = img[i].yy_; out_rgb[3 * i + 2] = img[i].zz_; }
     return 0;
 }
 
