@@ -321,7 +321,7 @@ def main():
             "config": {"workload": wl["desc"], "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],
                        "samples_per_step": int(tot_samples), "traced_bounces_per_step": int(tot_bounces),
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
-                       "l2": "inputs larger than L2: each wavefront batch streams 2 x 403 MB ray queues", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
+                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray)", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": tot_launches,
