@@ -161,6 +161,7 @@ template <typename R> struct SceneView {
     uint32_t n_objects;
     const float4* nodes;           // BVH: 4 x float4 per node (see unpack in traverse), may be null
     uint32_t n_nodes;
+    const float4* bslot;           // fp32 BVH leaf records, 2 x float4 per slot (see nearest_bvh_f32), may be null
 };
 
 template <typename R> struct Hit {
@@ -294,6 +295,102 @@ __device__ __forceinline__ Hit<R> nearest_bvh(const SceneView<R>& sc, const floa
         }
     }
     return best;
+}
+
+// fp32 BVH traversal (BASELINE config 5).  Differences from the generic nearest_bvh<R>:
+//  * while-while: every lane first descends inner nodes until it holds a leaf, then the warp tests leaf primitives
+//    together — inner-node and leaf code no longer serialise against each other inside one loop iteration;
+//  * slab tests in FMA form, t = lo * (1/d) - o * (1/d);
+//  * compact typed leaf records (32 B instead of the 64-B generic slot), two independent 128-bit loads per primitive:
+//      sphere                   a = {c.xyz, r}           b = {kind 0, obj, -, -}
+//      axis-aligned rectangle   a = {p_K, c_I, c_J, h_I} b = {kind 1+K, obj|RECT, h_J, -}     (as in FastScene)
+//      general rectangle        a = {-, -, -, -}         b = {kind 4, obj|RECT, -, -}          -> generic 64-B slot
+//  Ties in t across primitives are resolved by object index explicitly (traversal order is arbitrary).
+__device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t slot, const V3<float>& o, const V3<float>& d,
+                                           const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best)
+{
+    const float4 a = __ldg(sc.bslot + 2 * (size_t)slot), b = __ldg(sc.bslot + 2 * (size_t)slot + 1);
+    const uint32_t kind = __float_as_uint(b.x), obj = __float_as_uint(b.y);
+    float t;
+    bool hit;
+    if (kind == 0) {
+        const bool selfS = onSurf && obj == self;
+        const V3<float> op = mk<float>(o.x - a.x, o.y - a.y, o.z - a.z);
+        const float bb = dot(op, d);
+        const float delta = fmaf(bb, bb, fmaf(a.w, a.w, -dot(op, op)));
+        const float sq = sqrt_(fmaxf(delta, 0.f));
+        const float t1 = -bb - sq, t2 = sq - bb;
+        t = t1 > (float)IPT_MARGIN ? t1 : t2;
+        t = selfS ? -2.f * bb : t;
+        hit = (delta >= 0.f || selfS) && t > (float)IPT_MARGIN;
+    } else if (kind <= 3) {
+        const bool kx = kind == 1, kz = kind == 3;
+        const float ok = kx ? o.x : (kz ? o.z : o.y), ik = kx ? inv.x : (kz ? inv.z : inv.y);
+        const float oi = kx ? o.y : o.x, di = kx ? d.y : d.x, oj = kz ? o.y : o.z, dj = kz ? d.y : d.z;
+        t = (a.x - ok) * ik;
+        const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
+        hit = t > (float)IPT_MARGIN && ei <= a.w && ej <= b.z && obj != self;
+    } else {
+        test_rect<float>(sc.geom + 4 * (size_t)slot, slot, obj, o, d, self, best);
+        return;
+    }
+    hit = hit && (t < best.t || (t == best.t && obj < best.obj));
+    best.t = hit ? t : best.t;
+    best.slot = hit ? slot : best.slot;
+    best.obj = hit ? obj : best.obj;
+}
+
+__device__ __forceinline__ Hit<float> nearest_bvh_f32(const SceneView<float>& sc, const float4* top, uint32_t n_top, const V3<float> o,
+                                                      const V3<float> d, uint32_t self, bool onSurf)
+{
+    Hit<float> best;
+    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+    const V3<float> inv = mk<float>(1.f / d.x, 1.f / d.y, 1.f / d.z);        // primitive tests: +-inf for zero components (Plane.cu:55)
+    // box tests use t = lo * (1/d) - o * (1/d); an infinite 1/d would turn that into inf - inf, so components below
+    // 1e-18 are replaced by +-1e-18 there (the boxes are padded by 2e-3, far more than the error this introduces)
+    const float tiny = 1e-18f;
+    const V3<float> bi = mk<float>(1.f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), 1.f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                                   1.f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+    const V3<float> oi = mk<float>(o.x * bi.x, o.y * bi.y, o.z * bi.z);
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    const float slack = 1.0000004f;
+    for (;;) {
+        while (node >= 0) {
+            float4 a, b, c, e;
+            if ((uint32_t)node < n_top) { const float4* p = top + 4 * node; a = p[0]; b = p[1]; c = p[2]; e = p[3]; }
+            else { const float4* p = sc.nodes + 4 * (size_t)node; a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); e = __ldg(p + 3); }
+            float t0x = fmaf(a.x, bi.x, -oi.x), t1x = fmaf(a.w, bi.x, -oi.x);
+            float t0y = fmaf(a.y, bi.y, -oi.y), t1y = fmaf(b.x, bi.y, -oi.y);
+            float t0z = fmaf(a.z, bi.z, -oi.z), t1z = fmaf(b.y, bi.z, -oi.z);
+            const float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+            const float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t)) * slack;
+            t0x = fmaf(b.z, bi.x, -oi.x); t1x = fmaf(c.y, bi.x, -oi.x);
+            t0y = fmaf(b.w, bi.y, -oi.y); t1y = fmaf(c.z, bi.y, -oi.y);
+            t0z = fmaf(c.x, bi.z, -oi.z); t1z = fmaf(c.w, bi.z, -oi.z);
+            const float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+            const float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t)) * slack;
+            const bool h0 = n0 <= f0, h1 = n1 <= f1;
+            const int c0 = __float_as_int(e.x), c1 = __float_as_int(e.y);
+            if (h0 && h1) {
+                const bool swap = n1 < n0;
+                stack[sp++] = swap ? c0 : c1;
+                node = swap ? c1 : c0;
+            } else if (h0 || h1) {
+                node = h0 ? c0 : c1;
+            } else {
+                if (sp == 0) return best;
+                node = stack[--sp];
+            }
+        }
+        // leaf: ~node = first_slot * 16 + (count - 1)
+        const uint32_t code = (uint32_t)(~node);
+        const uint32_t first = code >> 4, cnt = (code & 15u) + 1u;
+        for (uint32_t s = first; s < first + cnt; s++) test_bslot(sc, s, o, d, inv, self, onSurf, best);
+        if (sp == 0) return best;
+        node = stack[--sp];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- scatter

@@ -111,6 +111,22 @@ __device__ __forceinline__ void stage(uint4* dst, const uint4* src, uint32_t n16
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
+// Nearest hit for the generic kernels: brute-force slots, or the BVH (fp32: typed leaf records when present).
+template <typename R, int MODE>
+__device__ __forceinline__ Hit<R> nearest_any(const SceneView<R>& sc, const float4* top, uint32_t n_top, const V3<R> o, const V3<R> d,
+                                              uint32_t self, bool onSurf)
+{
+    if (MODE == MODE_BRUTE) return nearest_brute<R>(sc, o, d, self, onSurf);
+    return nearest_bvh<R>(sc, top, n_top, o, d, self, onSurf);
+}
+template <>
+__device__ __forceinline__ Hit<float> nearest_any<float, MODE_BVH>(const SceneView<float>& sc, const float4* top, uint32_t n_top,
+                                                                   const V3<float> o, const V3<float> d, uint32_t self, bool onSurf)
+{
+    if (sc.bslot) return nearest_bvh_f32(sc, top, n_top, o, d, self, onSurf);
+    return nearest_bvh<float>(sc, top, n_top, o, d, self, onSurf);
+}
+
 // One bounce of one batch.  FIRST: rays are generated from sample ids instead of read from qin.
 template <typename R, int MODE, bool FIRST>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant__ KParams<R> p)
@@ -165,8 +181,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
             Ray<R> o0, o1;
             if (live) {
                 const bool onSurf = (r.meta & META_ONSURF) != 0;
-                const Hit<R> h = (MODE == MODE_BRUTE) ? nearest_brute<R>(sc, r.o, r.d, r.self, onSurf)
-                                                      : nearest_bvh<R>(sc, top, n_top, r.o, r.d, r.self, onSurf);
+                const Hit<R> h = nearest_any<R, MODE>(sc, top, n_top, r.o, r.d, r.self, onSurf);
                 if (h.slot != NO_OBJECT) {
                     const bool isRect = (h.obj & RECT_BIT) != 0;
                     const uint32_t obj = h.obj & ~RECT_BIT;
@@ -407,8 +422,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_trace(SceneView<R> scv, const
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const V3<R> o = mk<R>((R)rays[6 * i], (R)rays[6 * i + 1], (R)rays[6 * i + 2]);
         const V3<R> d = mk<R>((R)rays[6 * i + 3], (R)rays[6 * i + 4], (R)rays[6 * i + 5]);
-        const Hit<R> h = (MODE == MODE_BRUTE) ? nearest_brute<R>(sc, o, d, NO_OBJECT, false)
-                                              : nearest_bvh<R>(sc, top, n_top, o, d, NO_OBJECT, false);
+        const Hit<R> h = nearest_any<R, MODE>(sc, top, n_top, o, d, NO_OBJECT, false);
         out_obj[i] = h.slot == NO_OBJECT ? -1 : (int32_t)(h.obj & ~RECT_BIT);
         out_t[i] = (double)h.t;
     }

@@ -74,6 +74,7 @@ struct ipt_ctx {
     void *geom32 = nullptr, *geom64 = nullptr, *mat32 = nullptr, *mat64 = nullptr;
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
+    float4* bslot = nullptr;         // fp32 BVH leaf records (2 x float4 per slot), built when the scene has a BVH
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
     FastHeader fast_hd = {};
@@ -131,7 +132,8 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
 
 static void free_scene(ipt_ctx* c)
 {
-    cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob);
+    cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob); cudaFree(c->bslot);
+    c->bslot = nullptr;
     c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr; c->fast_blob = nullptr; c->fast_words = 0;
     std::memset(c->scene_bytes, 0, sizeof(c->scene_bytes));
     c->have_scene = false;
@@ -306,7 +308,42 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     }
     std::vector<uint32_t> blob;
     if (!bvh) { blob = build_fast_blob(s); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
-    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4};
+    // fp32 BVH leaf records: typed 32-byte entries in leaf (slot) order
+    std::vector<float> bs;
+    if (bvh) {
+        bs.assign((size_t)n * 8, 0.f);
+        auto axis_of = [](const double* v, int& k, double& sign) {
+            k = -1;
+            for (int i = 0; i < 3; i++) {
+                if (std::fabs(std::fabs(v[i]) - 1.0) <= 1e-12) { if (k >= 0) return false; k = i; sign = v[i]; }
+                else if (std::fabs(v[i]) > 1e-12) return false;
+            }
+            return k >= 0;
+        };
+        for (uint32_t slot = 0; slot < n; slot++) {
+            const uint32_t prim = s->bvh_slot_prim[slot], idx = prim & ~RECT_BIT;
+            float* o8 = &bs[(size_t)slot * 8];
+            uint32_t kind, obj;
+            if (!(prim & RECT_BIT)) {
+                for (int k = 0; k < 4; k++) o8[k] = (float)s->sphere_cxyzr[4 * (size_t)idx + k];
+                kind = 0; obj = s->sphere_object[idx];
+            } else {
+                const double *pl = s->rect_plane + 4 * (size_t)idx, *u = s->rect_u + 4 * (size_t)idx, *v = s->rect_v + 4 * (size_t)idx, *b = s->rect_bounds + 4 * (size_t)idx;
+                int K, iu, iv; double sk, su, sv;
+                obj = s->rect_object[idx] | RECT_BIT;
+                if (axis_of(pl, K, sk) && axis_of(u, iu, su) && axis_of(v, iv, sv) && b[0] == 0.0 && b[2] == 0.0 && iu != iv && iu != K && iv != K) {
+                    const int I = K == 0 ? 1 : 0;
+                    const double cu = u[3] / su, cv = v[3] / sv;
+                    o8[0] = (float)(pl[3] / sk);
+                    if (iu == I) { o8[1] = (float)cu; o8[2] = (float)cv; o8[3] = (float)b[1]; o8[6] = (float)b[3]; }
+                    else { o8[1] = (float)cv; o8[2] = (float)cu; o8[3] = (float)b[3]; o8[6] = (float)b[1]; }
+                    kind = 1u + (uint32_t)K;
+                } else kind = 4;
+            }
+            std::memcpy(o8 + 4, &kind, 4); std::memcpy(o8 + 5, &obj, 4);
+        }
+    }
+    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4};
     if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom64) {
         free_scene(c);
         CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
@@ -314,6 +351,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         CK(cudaMalloc(&c->slot_obj, b_slot));
         if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
         if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
+        if (!bs.empty()) CK(cudaMalloc(&c->bslot, bs.size() * 4));
         std::memcpy(c->scene_bytes, want, sizeof(want));
     }
     c->have_scene = false;
@@ -323,6 +361,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
+    if (!bs.empty()) CK(cudaMemcpyAsync(c->bslot, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, c->stream));
     c->fast_words = 0;
     if (!blob.empty()) {
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -334,7 +373,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total + blob.size() * 4;
+    c->last.h2d_bytes = total + blob.size() * 4 + bs.size() * 4;
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -419,7 +458,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.sc.mat = (const R4<R>*)(sizeof(R) == 4 ? c->mat32 : c->mat64);
     kp.sc.slot_obj = c->slot_obj;
     kp.sc.n_slots = c->n_slots; kp.sc.n_spheres = c->n_spheres; kp.sc.n_objects = c->n_objects;
-    kp.sc.nodes = c->nodes; kp.sc.n_nodes = c->n_nodes;
+    kp.sc.nodes = c->nodes; kp.sc.n_nodes = c->n_nodes; kp.sc.bslot = std::getenv("IPT_GENERIC_KERNEL") ? nullptr : c->bslot;
     // camera: vecZ = normalize(direction x orientation) in fp64 on the host (RenderController.cu:39)
     const double* D = c->cam + 3; const double* X = c->cam + 6;
     double Z[3] = {D[1] * X[2] - D[2] * X[1], D[2] * X[0] - D[0] * X[2], D[0] * X[1] - D[1] * X[0]};
@@ -699,7 +738,7 @@ extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_
         using R = decltype(tag);
         sv.geom = (const R4<R>*)(f64 ? c->geom64 : c->geom32); sv.mat = (const R4<R>*)(f64 ? c->mat64 : c->mat32);
         sv.slot_obj = c->slot_obj; sv.n_slots = c->n_slots; sv.n_spheres = c->n_spheres; sv.n_objects = c->n_objects;
-        sv.nodes = c->nodes; sv.n_nodes = c->n_nodes;
+        sv.nodes = c->nodes; sv.n_nodes = c->n_nodes; sv.bslot = c->bslot;
     };
     if (f64) {
         SceneView<double> sv; fill(sv, double());
