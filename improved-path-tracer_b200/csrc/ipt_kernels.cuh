@@ -14,7 +14,7 @@
 
 namespace ipt {
 
-enum { MODE_BRUTE = 0, MODE_BVH = 1 };
+enum { MODE_BRUTE = 0, MODE_BVH = 1, MODE_SHADE = 2 };   // MODE_SHADE: hits were found by k_extend_bvh, k_bounce only shades
 
 static constexpr int BLOCK_THREADS = 256;
 static constexpr int GRAB = 128;          // rays a warp claims per atomic on the work counter (4 iterations of 32)
@@ -22,8 +22,8 @@ static constexpr int BVH_TOP_NODES = 512; // top of the BVH staged in shared mem
 
 // counters[] layout (uint32): [CNT + p] rays queued for pass p, [WORK + p] work-claim counter of pass p
 static constexpr int MAX_PASSES = 256;
-static constexpr int CNT = 0, WORK = MAX_PASSES;
-static constexpr int N_COUNTERS = 2 * MAX_PASSES;
+static constexpr int CNT = 0, WORK = MAX_PASSES, WORK_EXTEND = 2 * MAX_PASSES;   // WORK_EXTEND: claim counter of k_extend_bvh
+static constexpr int N_COUNTERS = 3 * MAX_PASSES;
 
 template <typename R> struct KParams {
     SceneView<R> sc;
@@ -45,6 +45,7 @@ template <typename R> struct KParams {
     unsigned long long* traced; // total nearest-hit queries (stats)
     unsigned long long* frame;  // 3 x 64-bit accumulators per pixel (fixed point, or fp64 bits with IPT_FLAG_FLOAT_ACCUM)
     double fixed_scale;
+    uint2* hits;                // split pipeline: {t bits, slot} per ray of the current pass (k_extend_bvh -> k_bounce<MODE_SHADE>)
     const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
     uint32_t fast_words;
     FastHeader fast_hd;
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
     SceneView<R> sc = p.sc;
     const float4* top = nullptr;
     uint32_t n_top = 0;
-    if (MODE == MODE_BRUTE) {
+    if (MODE == MODE_SHADE) {
+        // nothing to stage: geometry and materials of the hit slot are read from global memory
+    } else if (MODE == MODE_BRUTE) {
         // whole scene -> shared memory: geometry slots, slot->object ids, materials
         constexpr uint32_t W16 = sizeof(R4<R>) / 16;
         const uint32_t ng = sc.n_slots * 4 * W16, nm = sc.n_objects * 2 * W16, ni = (sc.n_slots + 3) / 4;
@@ -181,7 +184,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
             Ray<R> o0, o1;
             if (live) {
                 const bool onSurf = (r.meta & META_ONSURF) != 0;
-                const Hit<R> h = nearest_any<R, MODE>(sc, top, n_top, r.o, r.d, r.self, onSurf);
+                Hit<R> h;
+                if (MODE == MODE_SHADE) {
+                    const uint2 hv = p.hits[i];
+                    h.t = (R)__uint_as_float(hv.x); h.slot = hv.y;
+                    h.obj = hv.y == NO_OBJECT ? NO_OBJECT : __ldg(sc.slot_obj + hv.y);
+                } else {
+                    h = nearest_any<R, MODE>(sc, top, n_top, r.o, r.d, r.self, onSurf);
+                }
                 if (h.slot != NO_OBJECT) {
                     const bool isRect = (h.obj & RECT_BIT) != 0;
                     const uint32_t obj = h.obj & ~RECT_BIT;
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
             // ---- compaction: one atomic per warp
             const uint32_t m_live = __ballot_sync(0xffffffffu, live);
             const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
-            my_traced += __popc(m_live);
+            if (MODE != MODE_SHADE) my_traced += __popc(m_live);   // the split pipeline counts casts in k_extend_bvh
             const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
             if (tot) {
                 uint32_t ob = 0;
@@ -237,6 +247,130 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
         }
     }
     if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
+}
+
+// ---------------------------------------------------------------------------------------------- split pipeline (BVH, fp32)
+// Stage 1 of the split wavefront step used for BVH scenes: camera rays -> queue (compacted, one atomic per warp).
+template <typename R>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(const __grid_constant__ KParams<R> p)
+{
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    uint32_t* out_count = p.counters + CNT;   // rays queued for pass 0
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < p.n_first; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        uint32_t px = 0, pz = 0, sample = 0;
+        const bool live = i < p.n_first && decode_sample(p, i, px, pz, sample);
+        Ray<R> r;
+        if (live) camera_ray(p, px, pz, sample, r);
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        if (m) {
+            uint32_t ob = 0;
+            if (lane == 0) ob = atomicAdd(out_count, (uint32_t)__popc(m));
+            ob = __shfl_sync(0xffffffffu, ob, 0);
+            if (live) q_store(p.qout, ob + __popc(m & lt_mask), r);
+        }
+    }
+}
+
+// Stage 2: nearest hit through the BVH with persistent threads and LANE-level refill.  Traversal lengths differ by an
+// order of magnitude between rays of one warp (the fused kernel ran at 5.5 of 32 lanes active on the 1M-primitive
+// scene, profiles/r01_ncu_bvh_v1.txt); here a lane that has finished its ray writes the hit and, as soon as
+// REFILL_MIN lanes of the warp are idle, the idle lanes claim new rays with one warp-aggregated atomic.
+static constexpr int REFILL_MIN = 8;
+
+__global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_constant__ KParams<float> p)
+{
+    extern __shared__ uint4 smem[];
+    const SceneView<float> sc = p.sc;
+    const uint32_t n_top = sc.n_nodes < (uint32_t)BVH_TOP_NODES ? sc.n_nodes : (uint32_t)BVH_TOP_NODES;
+    stage(smem, reinterpret_cast<const uint4*>(sc.nodes), n_top * 4);
+    const float4* top = reinterpret_cast<const float4*>(smem);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const uint32_t n_in = p.counters[CNT + p.depth];
+    uint32_t* work = p.counters + WORK_EXTEND + p.depth;
+    unsigned long long my_traced = 0;
+
+    int stack[64];
+    int sp = 0, node = 0;
+    bool has = false, exhausted = false;
+    uint32_t idx = 0, self = NO_OBJECT;
+    bool onSurf = false;
+    V3<float> o = mk<float>(0, 0, 0), d = o, inv = o, bi = o, oi = o;
+    Hit<float> best;
+    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+    const float slack = 1.0000004f, tiny = 1e-18f;
+
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !has);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= REFILL_MIN)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (uint32_t)__popc(idle) >= n_in;
+            if (!has) {
+                idx = base + __popc(idle & lt_mask);
+                if (idx < n_in) {
+                    const uint4 a = p.qin.base[idx], b = p.qin.base[p.qin.capacity + idx], c = p.qin.base[2u * p.qin.capacity + idx];
+                    o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+                    d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+                    onSurf = (c.z & META_ONSURF) != 0; self = c.w;
+                    inv = mk<float>(1.f / d.x, 1.f / d.y, 1.f / d.z);
+                    bi = mk<float>(1.f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), 1.f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                                   1.f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+                    oi = mk<float>(o.x * bi.x, o.y * bi.y, o.z * bi.z);
+                    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+                    sp = 0; node = 0; has = true;
+                    my_traced++;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, has) == 0) break;
+        if (has) {
+            bool done = false;
+            // descend inner nodes until this lane holds a leaf (or runs out of nodes)
+            while (node >= 0) {
+                float4 a, b, c, e;
+                if ((uint32_t)node < n_top) { const float4* q = top + 4 * node; a = q[0]; b = q[1]; c = q[2]; e = q[3]; }
+                else { const float4* q = sc.nodes + 4 * (size_t)node; a = __ldg(q); b = __ldg(q + 1); c = __ldg(q + 2); e = __ldg(q + 3); }
+                float t0x = fmaf(a.x, bi.x, -oi.x), t1x = fmaf(a.w, bi.x, -oi.x);
+                float t0y = fmaf(a.y, bi.y, -oi.y), t1y = fmaf(b.x, bi.y, -oi.y);
+                float t0z = fmaf(a.z, bi.z, -oi.z), t1z = fmaf(b.y, bi.z, -oi.z);
+                const float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+                const float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t)) * slack;
+                t0x = fmaf(b.z, bi.x, -oi.x); t1x = fmaf(c.y, bi.x, -oi.x);
+                t0y = fmaf(b.w, bi.y, -oi.y); t1y = fmaf(c.z, bi.y, -oi.y);
+                t0z = fmaf(c.x, bi.z, -oi.z); t1z = fmaf(c.w, bi.z, -oi.z);
+                const float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+                const float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t)) * slack;
+                const bool h0 = n0 <= f0, h1 = n1 <= f1;
+                const int c0 = __float_as_int(e.x), c1 = __float_as_int(e.y);
+                if (h0 && h1) {
+                    const bool swap = n1 < n0;
+                    stack[sp++] = swap ? c0 : c1;
+                    node = swap ? c1 : c0;
+                } else if (h0 || h1) {
+                    node = h0 ? c0 : c1;
+                } else {
+                    if (sp == 0) { done = true; break; }
+                    node = stack[--sp];
+                }
+            }
+            if (!done) {
+                const uint32_t code = (uint32_t)(~node);
+                const uint32_t first = code >> 4, cnt = (code & 15u) + 1u;
+                for (uint32_t s = first; s < first + cnt; s++) test_bslot(sc, s, o, d, inv, self, onSurf, best);
+                if (sp == 0) done = true;
+                else node = stack[--sp];
+            }
+            if (done) {
+                p.hits[idx] = make_uint2(__float_as_uint(best.t), best.slot);
+                has = false;
+            }
+        }
+    }
+    if (my_traced) atomicAdd(p.traced, my_traced);
 }
 
 // fp32 contributions are exact in fixed point without going through fp64: v * 2^k is exact in fp32.

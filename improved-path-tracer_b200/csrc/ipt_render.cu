@@ -82,6 +82,8 @@ struct ipt_ctx {
     // render state
     uint4* q[2] = {nullptr, nullptr};
     size_t q_bytes = 0;
+    uint2* hits = nullptr;           // split pipeline: one {t, slot} per queued ray
+    size_t hits_bytes = 0;
     uint32_t* counters = nullptr;
     unsigned long long* traced = nullptr;
     unsigned long long* frame = nullptr;
@@ -145,7 +147,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
-    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
+    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
     cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->tile_ids);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -410,6 +412,34 @@ static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_ca
     return IPT_OK;
 }
 
+// One batch of the split pipeline (fp32, BVH): raygen, then per bounce k_extend_bvh and k_bounce<MODE_SHADE>.
+static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth, uint32_t cap, size_t smem_top, int* grids, uint64_t* launches)
+{
+    auto shade = k_bounce<float, MODE_SHADE, false>;
+    if (grids[0] == 0) {
+        CK(cudaFuncSetAttribute(k_extend_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_top));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_bvh, BLOCK_THREADS, smem_top));
+        if (per_sm < 1) { set_err("k_extend_bvh does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
+        grids[0] = per_sm * c->sm_count;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade, BLOCK_THREADS, 0));
+        grids[1] = std::max(per_sm, 1) * c->sm_count;
+    }
+    kp.depth = 0;
+    kp.qout = Queue{c->q[0], cap};
+    k_raygen<float><<<c->sm_count * 8, BLOCK_THREADS, 0, c->stream>>>(kp);
+    (*launches)++;
+    for (uint32_t d = 0; d < max_depth; d++) {
+        kp.depth = d;
+        kp.qin = Queue{c->q[d & 1], cap};
+        kp.qout = Queue{c->q[(d + 1) & 1], cap};
+        k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
+        shade<<<grids[1], BLOCK_THREADS, 0, c->stream>>>(kp);
+        *launches += 2;
+    }
+    return IPT_OK;
+}
+
 template <typename R, int MODE, bool FIRST>
 static int launch_bounce(ipt_ctx* c, const KParams<R>& kp, size_t smem, int* grid_cache)
 {
@@ -506,6 +536,14 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
                             : ((size_t)c->n_slots * 4 + (size_t)c->n_objects * 2) * sizeof(R4<R>) + ((size_t)c->n_slots + 3) / 4 * 16;
     if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
 
+    // fp32 + BVH: split pipeline (raygen -> [extend with lane refill -> shade + compact] per bounce)
+    const bool use_split = sizeof(R) == 4 && bvh && kp.sc.bslot != nullptr && !std::getenv("IPT_FUSED_BVH");
+    if (use_split && (size_t)cap * 8 > c->hits_bytes) {
+        cudaFree(c->hits); c->hits = nullptr; c->hits_bytes = 0;
+        CK(cudaMalloc(&c->hits, (size_t)cap * 8));
+        c->hits_bytes = (size_t)cap * 8;
+    }
+    kp.hits = c->hits;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 4;   // A/B knob: CTAs per SM the fast kernel is compiled for
@@ -513,7 +551,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
-    int grid_first = 0, grid_next = 0;
+    int grid_first = 0, grid_next = 0, split_grids[2] = {0, 0};
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
     // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
@@ -524,6 +562,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         kp.base_sample = (uint32_t)(g0 % prm.samples);
         kp.n_first = (uint32_t)(std::min<uint64_t>(groups_per_batch, total_groups - g0) * 32);
         CK(cudaMemsetAsync(c->counters, 0, N_COUNTERS * sizeof(uint32_t), c->stream));
+        if (use_split) {
+            int rc = launch_split_batch(c, (KParams<float>&)kp, prm.max_depth, cap, smem, split_grids, &launches);
+            if (rc) return rc;
+            batches++;
+            continue;
+        }
         for (uint32_t d = 0; d < prm.max_depth; d++) {
             kp.depth = d;
             kp.qin = Queue{c->q[(d + 1) & 1], cap};
