@@ -45,6 +45,7 @@ template <typename R> struct KParams {
     unsigned long long* traced; // total nearest-hit queries (stats)
     unsigned long long* frame;  // 3 x 64-bit accumulators per pixel (fixed point, or fp64 bits with IPT_FLAG_FLOAT_ACCUM)
     double fixed_scale;
+    uint32_t refill_min;        // k_extend_bvh: idle lanes per warp that trigger a refill
     uint2* hits;                // split pipeline: {t bits, slot} per ray of the current pass (k_extend_bvh -> k_bounce<MODE_SHADE>)
     const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
     uint32_t fast_words;
@@ -275,8 +276,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(const __grid_constant_
 // Stage 2: nearest hit through the BVH with persistent threads and LANE-level refill.  Traversal lengths differ by an
 // order of magnitude between rays of one warp (the fused kernel ran at 5.5 of 32 lanes active on the 1M-primitive
 // scene, profiles/r01_ncu_bvh_v1.txt); here a lane that has finished its ray writes the hit and, as soon as
-// REFILL_MIN lanes of the warp are idle, the idle lanes claim new rays with one warp-aggregated atomic.
-static constexpr int REFILL_MIN = 8;
+// `refill_min` lanes of the warp are idle, the idle lanes claim new rays with one warp-aggregated atomic.
 
 __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_constant__ KParams<float> p)
 {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
 
     for (;;) {
         const uint32_t idle = __ballot_sync(0xffffffffu, !has);
-        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= REFILL_MIN)) {
+        if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= p.refill_min)) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(work, (uint32_t)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -327,10 +327,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
             }
         }
         if (__ballot_sync(0xffffffffu, has) == 0) break;
-        if (has) {
-            bool done = false;
-            // descend inner nodes until this lane holds a leaf (or runs out of nodes)
-            while (node >= 0) {
+        // Both phases are warp-synchronous loops driven by __any_sync: the warp reconverges before the leaf phase
+        // (left to the compiler, lanes that found their leaf early ran the primitive tests one or two at a time).
+        bool done = false;
+        // ---- phase 1: every lane with a ray descends inner nodes until it holds a leaf or runs out of nodes
+        while (__any_sync(0xffffffffu, has && !done && node >= 0)) {
+            if (has && !done && node >= 0) {
                 float4 a, b, c, e;
                 if ((uint32_t)node < n_top) { const float4* q = top + 4 * node; a = q[0]; b = q[1]; c = q[2]; e = q[3]; }
                 else { const float4* q = sc.nodes + 4 * (size_t)node; a = __ldg(q); b = __ldg(q + 1); c = __ldg(q + 2); e = __ldg(q + 3); }
@@ -352,22 +354,29 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
                     node = swap ? c1 : c0;
                 } else if (h0 || h1) {
                     node = h0 ? c0 : c1;
+                } else if (sp == 0) {
+                    done = true;
                 } else {
-                    if (sp == 0) { done = true; break; }
                     node = stack[--sp];
                 }
             }
-            if (!done) {
-                const uint32_t code = (uint32_t)(~node);
-                const uint32_t first = code >> 4, cnt = (code & 15u) + 1u;
-                for (uint32_t s = first; s < first + cnt; s++) test_bslot(sc, s, o, d, inv, self, onSurf, best);
-                if (sp == 0) done = true;
-                else node = stack[--sp];
-            }
-            if (done) {
-                p.hits[idx] = make_uint2(__float_as_uint(best.t), best.slot);
-                has = false;
-            }
+        }
+        // ---- phase 2: the lanes holding a leaf test its primitives, one primitive per lane per iteration
+        uint32_t s_cur = 0, s_end = 0;
+        if (has && !done) {
+            const uint32_t code = (uint32_t)(~node);
+            s_cur = code >> 4; s_end = s_cur + (code & 15u) + 1u;
+        }
+        while (__any_sync(0xffffffffu, s_cur < s_end)) {
+            if (s_cur < s_end) { test_bslot(sc, s_cur, o, d, inv, self, onSurf, best); s_cur++; }
+        }
+        if (has && !done) {
+            if (sp == 0) done = true;
+            else node = stack[--sp];
+        }
+        if (has && done) {
+            p.hits[idx] = make_uint2(__float_as_uint(best.t), best.slot);
+            has = false;
         }
     }
     if (my_traced) atomicAdd(p.traced, my_traced);
