@@ -89,8 +89,8 @@ template <typename R> struct Ray {
 // Queue = structure of arrays of 16-byte planes: a warp reads/writes 512 contiguous bytes per plane (128-bit,
 // fully coalesced).  fp32: 3 planes (48 B/ray); fp64: 6 planes (96 B/ray).
 template <typename R> struct QPlanes;
-template <> struct QPlanes<float> { static constexpr int N = 3; };
-template <> struct QPlanes<double> { static constexpr int N = 6; };
+template <> struct QPlanes<float> { static constexpr int N = 3, ACC = 1; };
+template <> struct QPlanes<double> { static constexpr int N = 6, ACC = 2; };
 
 struct Queue {
     uint4* base;        // plane p of ray i at base[p * capacity + i]
@@ -145,6 +145,30 @@ __device__ __forceinline__ void q_load(const Queue& q, uint32_t i, Ray<double>& 
     unpack2(e, r.thr.z, dummy);
     r.pixel = e.z; r.meta = e.w;
     r.self = q.base[5 * c + i].x;
+}
+
+// Deferred radiance of a deep path (only when maxDepth >= 130, see k_bounce): extra planes after the regular ones.
+__device__ __forceinline__ void q_store_acc(const Queue& q, uint32_t i, const V3<float>& a)
+{
+    q.base[3u * q.capacity + i] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), 0u);
+}
+__device__ __forceinline__ void q_load_acc(const Queue& q, uint32_t i, V3<float>& a)
+{
+    const uint4 v = q.base[3u * q.capacity + i];
+    a = mk<float>(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z));
+}
+__device__ __forceinline__ void q_store_acc(const Queue& q, uint32_t i, const V3<double>& a)
+{
+    const size_t c = q.capacity;
+    q.base[6 * c + i] = pack2(a.x, a.y);
+    q.base[7 * c + i] = pack2(a.z, 0.0);
+}
+__device__ __forceinline__ void q_load_acc(const Queue& q, uint32_t i, V3<double>& a)
+{
+    const size_t c = q.capacity;
+    double dummy;
+    unpack2(q.base[6 * c + i], a.x, a.y);
+    unpack2(q.base[7 * c + i], a.z, dummy);
 }
 
 // ---------------------------------------------------------------------------------------------- scene view

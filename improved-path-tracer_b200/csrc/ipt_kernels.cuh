@@ -130,7 +130,14 @@ __device__ __forceinline__ Hit<float> nearest_any<float, MODE_BVH>(const SceneVi
 }
 
 // One bounce of one batch.  FIRST: rays are generated from sample ids instead of read from qin.
-template <typename R, int MODE, bool FIRST>
+//
+// DEFER (maxDepth >= 130 only): the reference folds a deep path's radiance with an int8_t index starting at
+// depth_end - 2 (Renderer.cu:216), so a deepLayers() call that ends at depth_end >= 130 — by reaching maxDepth, or by
+// missing the scene at depth >= 130 — returns 0 as a whole, emission of its earlier hits included.  To reproduce that,
+// the emission a path collects from depth 2 on travels with the ray (extra queue planes) and reaches the frame only
+// when the path misses the scene at depth <= 129; a path with deferred radiance is traced to its end even when its
+// throughput has dropped to zero.
+template <typename R, int MODE, bool FIRST, bool DEFER>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant__ KParams<R> p)
 {
     extern __shared__ uint4 smem[];
@@ -183,8 +190,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
             }
             bool has0 = false, has1 = false;
             Ray<R> o0, o1;
+            V3<R> acc = mk<R>(0, 0, 0);
+            if (DEFER && !FIRST && live) q_load_acc(p.qin, i, acc);
             if (live) {
                 const bool onSurf = (r.meta & META_ONSURF) != 0;
+                const bool deep = DEFER && depth >= 2 && !(r.meta & META_PROBE);
                 Hit<R> h;
                 if (MODE == MODE_SHADE) {
                     const uint2 hv = p.hits[i];
@@ -197,14 +207,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                     const bool isRect = (h.obj & RECT_BIT) != 0;
                     const uint32_t obj = h.obj & ~RECT_BIT;
                     const R4<R> m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
-                    if (m1.w != (R)0) accumulate(p, r.pixel, mul(r.thr, xyz(m1)));   // E of every hit counts (Renderer.cu:170,193,211)
+                    if (m1.w != (R)0) {   // E of every hit counts (Renderer.cu:170,193,211)
+                        if (deep) acc = acc + mul(r.thr, xyz(m1));
+                        else accumulate(p, r.pixel, mul(r.thr, xyz(m1)));
+                    }
                     const bool probe = (r.meta & META_PROBE) != 0;
                     // Continuation exists iff another hit would still be evaluated: depth+1 < maxDepth (:161,:184,:201).
                     // Paths whose throughput is exactly 0 and the second branch of a depth-0 split after its first hit
                     // contribute exactly 0 and are not traced.
                     if (!probe && depth + 1 < p.maxDepth) {
                         V3<R> nthr = mul(r.thr, xyz(m0));
-                        if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0) {
+                        const bool pending = deep && (acc.x != (R)0 || acc.y != (R)0 || acc.z != (R)0);
+                        if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0 || pending) {
                             const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
                             const V3<R> P = r.o + r.d * h.t;                                       // :156,:179,:207
                             const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
@@ -231,6 +245,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                             }
                         }
                     }
+                } else if (deep && depth <= 129) {
+                    // the path leaves the scene at depth <= 129: its fold index fits an int8_t, its radiance counts
+                    if (acc.x != (R)0 || acc.y != (R)0 || acc.z != (R)0) accumulate(p, r.pixel, acc);
                 }
             }
             // ---- compaction: one atomic per warp
@@ -244,6 +261,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                 ob = __shfl_sync(0xffffffffu, ob, 0);
                 if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
                 if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
+                if (DEFER) {
+                    // the main continuation inherits the deferred radiance; a ray spawned by a split starts with none
+                    if (has0) q_store_acc(p.qout, ob + __popc(m0b & lt_mask), acc);   // non-zero only on deep paths
+                    if (has1) q_store_acc(p.qout, ob + c0 + __popc(m1b & lt_mask), mk<R>(0, 0, 0));
+                }
             }
         }
     }

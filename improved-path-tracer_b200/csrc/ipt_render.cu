@@ -415,7 +415,7 @@ static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_ca
 // One batch of the split pipeline (fp32, BVH): raygen, then per bounce k_extend_bvh and k_bounce<MODE_SHADE>.
 static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth, uint32_t cap, size_t smem_top, int* grids, uint64_t* launches)
 {
-    auto shade = k_bounce<float, MODE_SHADE, false>;
+    auto shade = k_bounce<float, MODE_SHADE, false, false>;
     if (grids[0] == 0) {
         CK(cudaFuncSetAttribute(k_extend_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_top));
         int per_sm = 0;
@@ -440,10 +440,10 @@ static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth
     return IPT_OK;
 }
 
-template <typename R, int MODE, bool FIRST>
+template <typename R, int MODE, bool FIRST, bool DEFER = false>
 static int launch_bounce(ipt_ctx* c, const KParams<R>& kp, size_t smem, int* grid_cache)
 {
-    auto kern = k_bounce<R, MODE, FIRST>;
+    auto kern = k_bounce<R, MODE, FIRST, DEFER>;
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -526,7 +526,9 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
     const uint32_t cap = (uint32_t)(2 * B);
-    const size_t q_bytes = (size_t)cap * 16 * QPlanes<R>::N;
+    // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
+    const bool defer = prm.max_depth >= 130;
+    const size_t q_bytes = (size_t)cap * 16 * (QPlanes<R>::N + (defer ? QPlanes<R>::ACC : 0));
     if (q_bytes > c->q_bytes) {
         cudaFree(c->q[0]); cudaFree(c->q[1]); c->q[0] = c->q[1] = nullptr; c->q_bytes = 0;
         CK(cudaMalloc(&c->q[0], q_bytes)); CK(cudaMalloc(&c->q[1], q_bytes));
@@ -537,7 +539,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
 
     // fp32 + BVH: split pipeline (raygen -> [extend with lane refill -> shade + compact] per bounce)
-    const bool use_split = sizeof(R) == 4 && bvh && kp.sc.bslot != nullptr && !std::getenv("IPT_FUSED_BVH");
+    const bool use_split = sizeof(R) == 4 && bvh && kp.sc.bslot != nullptr && !defer && !std::getenv("IPT_FUSED_BVH");
     if (use_split && (size_t)cap * 8 > c->hits_bytes) {
         cudaFree(c->hits); c->hits = nullptr; c->hits_bytes = 0;
         CK(cudaMalloc(&c->hits, (size_t)cap * 8));
@@ -546,7 +548,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.hits = c->hits;
     kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
-    const bool use_fast = sizeof(R) == 4 && !bvh && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
+    const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 4;   // A/B knob: CTAs per SM the fast kernel is compiled for
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
@@ -576,6 +578,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             int rc;
             if (use_fast && fast_minb == 3) rc = d == 0 ? launch_bounce_fast<true, 3>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 3>(c, (const KParams<float>&)kp, &grid_next);
             else if (use_fast) rc = d == 0 ? launch_bounce_fast<true, 4>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 4>(c, (const KParams<float>&)kp, &grid_next);
+            else if (defer && d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true, true>(c, kp, smem, &grid_first);
+            else if (defer) rc = bvh ? launch_bounce<R, MODE_BVH, false, true>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false, true>(c, kp, smem, &grid_next);
             else if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
             else rc = bvh ? launch_bounce<R, MODE_BVH, false>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false>(c, kp, smem, &grid_next);
             if (rc) return rc;

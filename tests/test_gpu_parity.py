@@ -331,3 +331,31 @@ def test_single_process_multi_gpu_gather(pyipt, oracle):
     assert np.array_equal(one, two)
     assert s2["traced_bounces"] == s1["traced_bounces"] and s2["samples"] == s1["samples"]
     assert s2["per_gpu_bounces"][0] > 0 and s2["per_gpu_bounces"][1] > 0
+
+
+@pytest.mark.parametrize("depth", [130, 131, 200, 255])
+def test_int8_fold_quirk_from_depth_130(pyipt, oracle, tmp_path, depth):
+    """Renderer.cu:216: the fold index is an int8_t, so from maxDepth 130 on a deep path counts only if it LEAVES the
+    scene before depth 130.  Closed scene (spheres.json): all deep radiance vanishes; leaky scene (one wall shrunk):
+    escaping paths keep theirs.  fp64 kernels vs the oracle's literal restatement, same counter stream."""
+    import json as js
+    W, H, spp = 64, 36, 2
+    j = js.load(open(oracle.scene_path("spheres")))
+    j["width"], j["height"] = W, H
+    open_scene = js.loads(js.dumps(j))
+    for k in ("xx", "yy", "zz"):
+        open_scene["objects"][1]["north"][k] *= 0.9   # shrink one wall: some paths escape early, others never do
+    closed_path, open_path = tmp_path / "closed.json", tmp_path / "open.json"
+    closed_path.write_text(js.dumps(j)); open_path.write_text(js.dumps(open_scene))
+    for path in (closed_path, open_path):
+        ref, cnt = oracle.render(oracle.Scene.load(str(path)), spp, depth, rng=oracle.RNG_COUNTER, seed=depth)
+        ref129, _ = oracle.render(oracle.Scene.load(str(path)), spp, 129, rng=oracle.RNG_COUNTER, seed=depth)
+        assert not np.allclose(ref, ref129)                      # the quirk changes the image
+        hs = pyipt.HostScene.load(str(path))
+        img, st = pyipt.render(hs, spp, depth, seed=depth, flags=pyipt.FLAG_FP64)
+        assert frac_within(img, ref, 1e-9) >= 0.995, path
+        img32, _ = pyipt.render(hs, spp, depth, seed=depth)
+        assert frac_within(img32, ref, 1e-3) >= 0.95, path
+        hs_bvh = pyipt.HostScene.load(str(path), brute_max=4)
+        img_b, _ = pyipt.render(hs_bvh, spp, depth, seed=depth, flags=pyipt.FLAG_FP64)
+        assert frac_within(img_b, ref, 1e-9) >= 0.995, path
