@@ -23,6 +23,7 @@ static constexpr uint32_t RECT_BIT = 0x80000000u;
 // ray meta word: depth[0:8) lane[8:10) probe[10] onSurf[11] sample[12:28)
 static constexpr uint32_t META_PROBE = 1u << 10;
 static constexpr uint32_t META_ONSURF = 1u << 11;
+static constexpr uint32_t META_DEAD = 1u << 31;   // padding slot at the end of a warp's output block (k_bounce_fast): not a ray
 __host__ __device__ inline uint32_t make_meta(uint32_t depth, uint32_t lane, bool probe, bool onSurf, uint32_t sample)
 {
     return depth | (lane << 8) | (probe ? META_PROBE : 0u) | (onSurf ? META_ONSURF : 0u) | (sample << 12);

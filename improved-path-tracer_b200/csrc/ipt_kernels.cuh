@@ -421,113 +421,133 @@ __device__ __forceinline__ void accumulate_fast(const KParams<float>& p, uint32_
 }
 
 // The product kernel for brute-force scenes: same wavefront step as k_bounce<float, MODE_BRUTE, FIRST>, on the typed
-// fp32 scene lists (FastScene) with branch-free intersection and scatter.
-//
-// Work distribution and compaction are per CTA here: a CTA claims CTA_GRAB rays with one atomic, and the continuation
-// rays of each 256-ray slice are compacted warp ballot -> per-warp counts in shared memory -> ONE global atomic per
-// slice.  (One atomic per warp, as in k_bounce, serialises on the queue counter at ~0.9 G atomics/s on B200, which
-// capped these scenes at ~29 Grays/s: profiles/r01_*.)
-static constexpr int CTA_SLICES = 4;
-static constexpr int CTA_GRAB = BLOCK_THREADS * CTA_SLICES;
-static constexpr int WARPS = BLOCK_THREADS / 32;
+// fp32 scene lists (FastScene) with branch-free intersection and scatter.  What the ncu captures led to
+// (profiles/README.md):
+//  * slices of 32 rays are assigned to warps statically (slice = warp + k * warps): every ray costs the same here, so
+//    no work-claim atomic is needed and the next slice is known — its three 16-byte record planes are prefetched with
+//    cp.async into a per-thread shared-memory slot while the current slice is computed (double buffered, no barrier:
+//    a thread only ever reads what it fetched itself);
+//  * compaction is warp ballot + popc into a WARP-PRIVATE block of OUT_BLOCK queue slots, reserved with one atomic per
+//    block.  One atomic per warp iteration serialises on the queue counter at ~0.9 G atomics/s on B200 (which capped
+//    these scenes at ~29 Grays/s); per-CTA aggregation fixed that but cost two barriers per slice.  The unused tail of
+//    a warp's last block is filled with META_DEAD records, which the next pass skips.
+static constexpr uint32_t OUT_BLOCK = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <bool FIRST, int MINB>
 __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
     extern __shared__ uint4 smem[];
-    __shared__ uint32_t s_base, s_tot[WARPS], s_off[WARPS];
+    uint4* stagebuf = smem + p.fast_words;              // [2 buffers][3 planes][BLOCK_THREADS]
     stage(smem, p.fast_blob, p.fast_words);
     __syncthreads();
     const FastScene sc = fast_view(smem, p.fast_hd);
 
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.depth];
     const uint32_t depth = p.depth;
-    uint32_t* work = p.counters + WORK + depth;
     uint32_t* out_count = p.counters + CNT + depth + 1;
     const bool may_continue = depth + 1 < p.maxDepth;
+    const uint32_t warp_global = blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t stride = gridDim.x * BLOCK_THREADS;   // rays per sweep of the whole grid
     unsigned long long my_traced = 0;
+    uint32_t blk_base = 0, blk_used = OUT_BLOCK;         // no block reserved yet
 
-    for (;;) {
-        if (threadIdx.x == 0) s_base = atomicAdd(work, (uint32_t)CTA_GRAB);
-        __syncthreads();
-        const uint32_t base = s_base;
-        if (base >= n_in) break;
-#pragma unroll 1
-        for (uint32_t k = 0; k < CTA_GRAB; k += BLOCK_THREADS) {
-            const uint32_t i = base + k + threadIdx.x;
-            bool live = i < n_in;
-            Ray<float> r;
-            if (FIRST) {
-                uint32_t px = 0, pz = 0, sample = 0;
-                live = live && decode_sample(p, i, px, pz, sample);
-                if (live) camera_ray(p, px, pz, sample, r);
-            } else if (live) {
-                q_load(p.qin, i, r);
-            }
-            bool has0 = false, has1 = false;
-            Ray<float> o0, o1;
-            if (live) {
-                const FastHit h = nearest_fast(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
-                if (h.code != NO_OBJECT) {
-                    const uint32_t hobj = fast_hit_object(sc, h.code);
-                    const uint32_t obj = hobj & ~RECT_BIT;
-                    const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
-                    if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
-                    V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
-                    const bool go = may_continue && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
-                    if (go) {
-                        const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
-                        const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
-                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
-                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
-                        bool alive = sp.has0;
-                        if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
-                            const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
-                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
-                            if (u23<float>(rr.x) >= q) alive = false;
-                            else nthr = nthr * (1.f / q);
-                        }
-                        const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
-                        has0 = alive;
-                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = hobj;
-                        const uint32_t mcommon = (r.meta & 0xFFFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
-                        o0.meta = mcommon | (r.meta & 0x300u);
-                        has1 = sp.has1;
-                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = hobj;
-                        o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
-                    }
-                }
-            }
-            // ---- compaction: ballot + popc per warp, shared-memory prefix per CTA, one global atomic per slice
-            const uint32_t m_live = __ballot_sync(0xffffffffu, live);
-            const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
-            my_traced += __popc(m_live);
-            const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
-            if (lane == 0) s_tot[warp] = tot;
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t v = lane < WARPS ? s_tot[lane] : 0u;
-                uint32_t incl = v;
-#pragma unroll
-                for (int dlt = 1; dlt < WARPS; dlt <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, dlt);
-                    if (lane >= (uint32_t)dlt) incl += n;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, WARPS - 1);
-                uint32_t gb = 0;
-                if (lane == 0 && total) gb = atomicAdd(out_count, total);
-                gb = __shfl_sync(0xffffffffu, gb, 0);
-                if (lane < WARPS) s_off[lane] = gb + incl - v;
-            }
-            __syncthreads();
-            const uint32_t ob = s_off[warp];
-            if (has0) q_store(p.qout, ob + __popc(m0b & lt_mask), o0);
-            if (has1) q_store(p.qout, ob + c0 + __popc(m1b & lt_mask), o1);
-        }
-        __syncthreads();   // s_base is rewritten by the next claim
+    uint32_t i = warp_global * 32u + lane;
+    int buf = 0;
+    if (!FIRST && i < n_in) {
+        for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + (buf * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + i);
     }
+    cp_async_commit();
+
+    for (; (i & ~31u) < n_in; i += stride) {
+        bool live = i < n_in;
+        Ray<float> r;
+        if (FIRST) {
+            uint32_t px = 0, pz = 0, sample = 0;
+            live = live && decode_sample(p, i, px, pz, sample);
+            if (live) camera_ray(p, px, pz, sample, r);
+        } else {
+            cp_async_wait_all();
+            const uint32_t nxt = i + stride;
+            if (nxt < n_in)
+                for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + ((buf ^ 1) * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + nxt);
+            cp_async_commit();
+            if (live) {
+                const uint4 a = stagebuf[(buf * 3 + 0) * BLOCK_THREADS + threadIdx.x], b = stagebuf[(buf * 3 + 1) * BLOCK_THREADS + threadIdx.x],
+                            c = stagebuf[(buf * 3 + 2) * BLOCK_THREADS + threadIdx.x];
+                r.o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+                r.d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+                r.thr = mk<float>(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+                r.pixel = c.y; r.meta = c.z; r.self = c.w;
+                live = !(r.meta & META_DEAD);
+            }
+            buf ^= 1;
+        }
+        bool has0 = false, has1 = false;
+        Ray<float> o0, o1;
+        if (live) {
+            const FastHit h = nearest_fast(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
+            if (h.code != NO_OBJECT) {
+                const uint32_t hobj = fast_hit_object(sc, h.code);
+                const uint32_t obj = hobj & ~RECT_BIT;
+                const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
+                if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
+                V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
+                const bool go = may_continue && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
+                if (go) {
+                    const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
+                    const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
+                    const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
+                    const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
+                    bool alive = sp.has0;
+                    if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
+                        const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
+                        const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
+                        if (u23<float>(rr.x) >= q) alive = false;
+                        else nthr = nthr * (1.f / q);
+                    }
+                    const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
+                    has0 = alive;
+                    o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = hobj;
+                    const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
+                    o0.meta = mcommon | (r.meta & 0x300u);
+                    has1 = sp.has1;
+                    o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = hobj;
+                    o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
+                }
+            }
+        }
+        // ---- compaction into the warp's private output block
+        const uint32_t m_live = __ballot_sync(0xffffffffu, live);
+        const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
+        my_traced += __popc(m_live);
+        const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
+        if (tot) {
+            // outputs fill the rest of the current block and spill into a freshly reserved one: no holes inside blocks
+            const uint32_t room = OUT_BLOCK - blk_used;
+            uint32_t nb = blk_base;
+            if (tot > room) {
+                if (lane == 0) nb = atomicAdd(out_count, OUT_BLOCK);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+            }
+            const uint32_t j0 = __popc(m0b & lt_mask), j1 = c0 + __popc(m1b & lt_mask);
+            if (has0) q_store(p.qout, j0 < room ? blk_base + blk_used + j0 : nb + (j0 - room), o0);
+            if (has1) q_store(p.qout, j1 < room ? blk_base + blk_used + j1 : nb + (j1 - room), o1);
+            if (tot > room) { blk_base = nb; blk_used = tot - room; }
+            else blk_used += tot;
+        }
+    }
+    // the unused tail of the last block: dead records (skipped by the next pass)
+    for (uint32_t s = blk_used + lane; s < OUT_BLOCK; s += 32) p.qout.base[2u * p.qout.capacity + blk_base + s] = make_uint4(0u, 0u, META_DEAD, NO_OBJECT);
     if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
 }
 

@@ -400,7 +400,7 @@ template <bool FIRST, int MINB>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
     auto kern = k_bounce_fast<FIRST, MINB>;
-    const size_t smem = (size_t)kp.fast_words * 16;
+    const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * BLOCK_THREADS * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -525,7 +525,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     uint64_t B = prm.batch_samples ? prm.batch_samples : (1u << 26);
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
-    const uint32_t cap = (uint32_t)(2 * B);
+    // a sample has at most two live rays; + room for the dead tails of the fast kernel's per-warp output blocks
+    const uint32_t cap = (uint32_t)(2 * B) + (1u << 20);
     // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
     const bool defer = prm.max_depth >= 130;
     const size_t q_bytes = (size_t)cap * 16 * (QPlanes<R>::N + (defer ? QPlanes<R>::ACC : 0));
