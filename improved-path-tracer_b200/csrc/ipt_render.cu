@@ -550,7 +550,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
-    const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 4;   // A/B knob: CTAs per SM the fast kernel is compiled for
+    const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 3;   // A/B knob: CTAs per SM the fast kernel is compiled for (3: 78 regs, no spill; 4: 64 regs, spills)
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
