@@ -583,6 +583,18 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Resolve
     }
 }
 
+// Image.cpp:19-22 on the device: byte = clamp(int(x * 255), 0, 255), computed in fp64 from the fp32 frame exactly as
+// ipt_host_to_rgb does on the host (NaN -> 0, saturation instead of the reference's undefined int overflow).
+__global__ void __launch_bounds__(256) k_to_rgb8(const float* __restrict__ frame, uint8_t* __restrict__ out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = (double)frame[i] * 255.0;
+        int b = 0;
+        if (v == v) b = v >= 2147483647.0 ? 255 : (v <= -2147483648.0 ? 0 : min(max((int)v, 0), 255));
+        out[i] = (uint8_t)b;
+    }
+}
+
 // Function-level access for parity tests: nearest hit of explicit rays through the same device functions.
 template <typename R, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_trace(SceneView<R> scv, const double* rays, uint32_t n, int32_t* out_obj, double* out_t)

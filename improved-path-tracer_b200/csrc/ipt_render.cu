@@ -90,6 +90,8 @@ struct ipt_ctx {
     size_t frame_pixels = 0;
     float* out32 = nullptr;
     double* out64 = nullptr;
+    uint8_t* out8 = nullptr;         // toRgb bytes of the whole frame (ipt_ctx_download_rgb8)
+    size_t out8_bytes = 0;
     float* gather32 = nullptr;   // where resolve writes (own frame unless a gather target is set)
     double* gather64 = nullptr;
     void* ipc_mapped = nullptr;
@@ -148,7 +150,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
-    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->tile_ids);
+    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -525,11 +527,19 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     uint64_t B = prm.batch_samples ? prm.batch_samples : (1u << 26);
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
-    // a sample has at most two live rays; + room for the dead tails of the fast kernel's per-warp output blocks
-    const uint32_t cap = (uint32_t)(2 * B) + (1u << 20);
     // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
     const bool defer = prm.max_depth >= 130;
-    const size_t q_bytes = (size_t)cap * 16 * (QPlanes<R>::N + (defer ? QPlanes<R>::ACC : 0));
+    const size_t ray_bytes = (size_t)16 * (QPlanes<R>::N + (defer ? QPlanes<R>::ACC : 0));
+    // a sample has at most two live rays; + room for the dead tails of the fast kernel's per-warp output blocks
+    auto cap_of = [](uint64_t b) { return (uint32_t)(2 * b) + (1u << 20); };
+    {   // the default batch shrinks on devices (or in processes) where two queues of that size do not fit comfortably
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t)0; }
+        const size_t avail = free_b / 2 + 2 * c->q_bytes;
+        while (!prm.batch_samples && B > (1u << 20) && 2 * (size_t)cap_of(B) * ray_bytes > avail) B = B / 2 / 32 * 32;
+    }
+    const uint32_t cap = cap_of(B);
+    const size_t q_bytes = (size_t)cap * ray_bytes;
     if (q_bytes > c->q_bytes) {
         cudaFree(c->q[0]); cudaFree(c->q[1]); c->q[0] = c->q[1] = nullptr; c->q_bytes = 0;
         CK(cudaMalloc(&c->q[0], q_bytes)); CK(cudaMalloc(&c->q[1], q_bytes));
@@ -653,6 +663,29 @@ extern "C" int ipt_ctx_download(ipt_ctx* c, float* out32, double* out64)
     return IPT_OK;
 }
 
+extern "C" int ipt_ctx_download_rgb8(ipt_ctx* c, uint8_t* out8)
+{
+    if (!c || !c->have_scene || !out8) { set_err("ipt_ctx_download_rgb8: no frame"); return IPT_ERR_BAD_ARGUMENT; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->frame_pixels * 3;
+    if (c->out8_bytes < n) {
+        cudaFree(c->out8); c->out8 = nullptr; c->out8_bytes = 0;
+        CK(cudaMalloc(&c->out8, n));
+        c->out8_bytes = n;
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_to_rgb8<<<c->sm_count * 8, 256, 0, c->stream>>>(c->out32, c->out8, n);
+    CK(cudaMemcpyAsync(out8, c->out8, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last.download_ms = ms;
+    c->last.d2h_bytes = n;
+    c->last.kernel_launches += 1;
+    return IPT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ gather targets
 extern "C" int ipt_ctx_export_frame(ipt_ctx* c, void* handle64)
 {
@@ -696,7 +729,7 @@ extern "C" int ipt_ctx_set_gather_target(ipt_ctx* c, ipt_ctx* owner)
 }
 
 // ------------------------------------------------------------------------------------------------ one-shot render
-extern "C" int ipt_render(const ipt_scene* scene, const ipt_params* params, int n_gpus, float* out32, double* out64, ipt_stats* stats)
+static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_gpus, float* out32, double* out64, uint8_t* out8, ipt_stats* stats)
 {
     if (!scene || !params) { set_err("ipt_render: null argument"); return IPT_ERR_BAD_ARGUMENT; }
     const int ndev = ipt_device_count();
@@ -733,6 +766,10 @@ extern "C" int ipt_render(const ipt_scene* scene, const ipt_params* params, int 
         for (auto& t : th) t.join();
         for (int g = 0; g < n_gpus; g++) if (rcs[g]) rc = rcs[g];
     }
+    if (rc == IPT_OK && out8) {
+        if (host_merge && n_gpus > 1) { set_err("ipt_render_rgb8: needs peer access between the GPUs"); rc = IPT_ERR_CUDA; }
+        else rc = ipt_ctx_download_rgb8(ctx[0], out8);
+    }
     if (rc == IPT_OK && (out32 || out64)) {
         rc = ipt_ctx_download(ctx[0], out32, out64);
         if (rc == IPT_OK && host_merge && n_gpus > 1) {
@@ -766,6 +803,17 @@ extern "C" int ipt_render(const ipt_scene* scene, const ipt_params* params, int 
     }
     for (int g = 0; g < n_gpus; g++) ipt_ctx_destroy(ctx[g]);
     return rc;
+}
+
+extern "C" int ipt_render(const ipt_scene* scene, const ipt_params* params, int n_gpus, float* out32, double* out64, ipt_stats* stats)
+{
+    return render_impl(scene, params, n_gpus, out32, out64, nullptr, stats);
+}
+
+extern "C" int ipt_render_rgb8(const ipt_scene* scene, const ipt_params* params, int n_gpus, uint8_t* out8, ipt_stats* stats)
+{
+    if (!out8) { set_err("ipt_render_rgb8: null output"); return IPT_ERR_BAD_ARGUMENT; }
+    return render_impl(scene, params, n_gpus, nullptr, nullptr, out8, stats);
 }
 
 // ------------------------------------------------------------------------------------------------ trace (tests)

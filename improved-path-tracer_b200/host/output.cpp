@@ -36,15 +36,14 @@ void chunk(std::vector<unsigned char>& out, const char* type, const unsigned cha
 
 // Image.cpp:39-56: W x H, 8-bit RGB, row 0 = top.  (The reference keeps the bytes in a stack VLA, which overflows
 // at 3840x2160; a heap buffer is used here.)
-extern "C" int ipt_host_write_png(const char* path, const float* rgb, uint32_t W, uint32_t H)
+extern "C" int ipt_host_write_png_rgb8(const char* path, const uint8_t* rgb8, uint32_t W, uint32_t H)
 {
-    if (!path || !rgb || !W || !H) return -1;
+    if (!path || !rgb8 || !W || !H) return -1;
     std::vector<unsigned char> raw((size_t)H * (1 + (size_t)W * 3));
     for (uint32_t z = 0; z < H; z++) {
         unsigned char* row = &raw[(size_t)z * (1 + (size_t)W * 3)];
         row[0] = 0;   // filter: none
-        const float* src = rgb + (size_t)z * W * 3;
-        for (size_t i = 0; i < (size_t)W * 3; i++) row[1 + i] = (unsigned char)ipt_host_to_rgb((double)src[i]);
+        std::memcpy(row + 1, rgb8 + (size_t)z * W * 3, (size_t)W * 3);
     }
     uLongf zn = compressBound((uLong)raw.size());
     std::vector<unsigned char> z(zn);
@@ -61,6 +60,14 @@ extern "C" int ipt_host_write_png(const char* path, const float* rgb, uint32_t W
     const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
     std::fclose(f);
     return ok ? 0 : -1;
+}
+
+extern "C" int ipt_host_write_png(const char* path, const float* rgb, uint32_t W, uint32_t H)
+{
+    if (!path || !rgb || !W || !H) return -1;
+    std::vector<uint8_t> bytes((size_t)W * H * 3);
+    for (size_t i = 0; i < bytes.size(); i++) bytes[i] = (uint8_t)ipt_host_to_rgb((double)rgb[i]);
+    return ipt_host_write_png_rgb8(path, bytes.data(), W, H);
 }
 
 // Measurements.cpp:21-41: every unit is "00" when zero, zero-padded to two digits below 10; the milliseconds are

@@ -45,14 +45,14 @@ int main(int argc, char* argv[])
     int gpus = std::getenv("IPT_GPUS") ? std::atoi(std::getenv("IPT_GPUS")) : 1;
     if (gpus < 1) gpus = 1;
 
-    std::vector<float> image((size_t)view->width * view->height * 3);
+    std::vector<uint8_t> image((size_t)view->width * view->height * 3);   // toRgb runs on the device: bytes come back
     ipt_stats stats = {};
     // Measurements.cpp:58-70: the timed region is the whole render call (allocation, upload, kernels, copy back)
     std::cout << "Begining render..." << std::endl;
     std::printf("\rRendering %.2f%%", 0.0f);
     std::fflush(stdout);
     const auto t0 = std::chrono::high_resolution_clock::now();
-    const int rc = ipt_render(view, &params, gpus, image.data(), nullptr, &stats);
+    const int rc = ipt_render_rgb8(view, &params, gpus, image.data(), &stats);
     const auto t1 = std::chrono::high_resolution_clock::now();
     if (rc == IPT_OK) std::printf("\rRendering %.2f%%", 100.0f);
     else std::cout << "render error: " << ipt_last_error() << std::endl;    // RenderController.cu:20-27 prints and carries on
@@ -64,7 +64,7 @@ int main(int argc, char* argv[])
     if (rc != IPT_OK) { ipt_host_free_scene(scene); return 1; }             // main.cu:52-56
 
     std::cout << "Saving Image..." << std::endl;                            // Image.cpp:41
-    ipt_host_write_png((id + ".png").c_str(), image.data(), view->width, view->height);
+    ipt_host_write_png_rgb8((id + ".png").c_str(), image.data(), view->width, view->height);
     if (std::getenv("IPT_VERBOSE"))
         std::fprintf(stderr, "[ipt] %.3f Msamples/s  %.3f Gbounces/s  kernels %.1f ms  launches %llu\n",
                      stats.samples / stats.render_ms * 1e-3, stats.traced_bounces / stats.render_ms * 1e-6, stats.render_ms,

@@ -18,14 +18,14 @@ FLAG_FLOAT_ACCUM = 0x4
 FLAG_RUSSIAN_ROULETTE = 0x8
 
 ABI_SYMBOLS = [
-    "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_objects",
-    "ipt_ctx_create", "ipt_ctx_destroy", "ipt_ctx_set_scene", "ipt_ctx_render", "ipt_ctx_download",
+    "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_rgb8", "ipt_render_objects",
+    "ipt_ctx_create", "ipt_ctx_destroy", "ipt_ctx_set_scene", "ipt_ctx_render", "ipt_ctx_download", "ipt_ctx_download_rgb8",
     "ipt_ctx_export_frame", "ipt_ctx_set_gather_target_ipc", "ipt_ctx_set_gather_target", "ipt_tile_owner",
     "ipt_ctx_trace",
 ]
 HOST_SYMBOLS = [
     "ipt_host_load_scene", "ipt_host_from_objects", "ipt_host_free_scene", "ipt_host_scene_view", "ipt_host_set_size",
-    "ipt_host_build_bvh", "ipt_host_to_rgb", "ipt_host_write_png", "ipt_host_time_string", "ipt_host_append_benchmark",
+    "ipt_host_build_bvh", "ipt_host_to_rgb", "ipt_host_write_png", "ipt_host_write_png_rgb8", "ipt_host_time_string", "ipt_host_append_benchmark",
     "ipt_host_parse_cli",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.ipt_device_name.restype = ctypes.c_char_p
     L.ipt_last_error.restype = ctypes.c_char_p
     L.ipt_render.argtypes = [ctypes.POINTER(Scene), ctypes.POINTER(Params), i32, vp, vp, ctypes.POINTER(Stats)]
+    L.ipt_render_rgb8.argtypes = [ctypes.POINTER(Scene), ctypes.POINTER(Params), i32, vp, ctypes.POINTER(Stats)]
     L.ipt_render_objects.argtypes = [vp, u32, u32, u32, vp, u32, u32, i32, vp]
     L.ipt_ctx_create.argtypes = [i32]
     L.ipt_ctx_create.restype = vp
@@ -102,6 +103,7 @@ def lib():
     L.ipt_ctx_set_scene.argtypes = [vp, ctypes.POINTER(Scene)]
     L.ipt_ctx_render.argtypes = [vp, ctypes.POINTER(Params), ctypes.POINTER(Stats)]
     L.ipt_ctx_download.argtypes = [vp, vp, vp]
+    L.ipt_ctx_download_rgb8.argtypes = [vp, vp]
     L.ipt_ctx_export_frame.argtypes = [vp, vp]
     L.ipt_ctx_set_gather_target_ipc.argtypes = [vp, vp]
     L.ipt_ctx_set_gather_target.argtypes = [vp, vp]
@@ -121,6 +123,7 @@ def lib():
     L.ipt_host_build_bvh.argtypes = [vp, u32, u32]
     L.ipt_host_to_rgb.argtypes = [ctypes.c_double]
     L.ipt_host_write_png.argtypes = [ctypes.c_char_p, vp, u32, u32]
+    L.ipt_host_write_png_rgb8.argtypes = [ctypes.c_char_p, vp, u32, u32]
     L.ipt_host_time_string.argtypes = [ctypes.c_uint64, ctypes.c_char_p, ctypes.c_size_t]
     L.ipt_host_time_string.restype = None
     L.ipt_host_append_benchmark.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
@@ -236,6 +239,16 @@ def render(scene, samples, depth, n_gpus=1, seed=123456, flags=0, tile=(0, 0), b
     return (out64 if want64 else out32), st.as_dict()
 
 
+def render_rgb8(scene, samples, depth, n_gpus=1, seed=123456, flags=0):
+    """One-shot ipt_render_rgb8(): toRgb applied on the device, uint8 frame [H,W,3] back."""
+    v = scene.view.contents
+    out = np.zeros((v.height, v.width, 3), dtype=np.uint8)
+    p = make_params(samples, depth, seed, flags)
+    st = Stats()
+    _check(lib().ipt_render_rgb8(scene.view, ctypes.byref(p), n_gpus, out.ctypes.data, ctypes.byref(st)), "ipt_render_rgb8")
+    return out, st.as_dict()
+
+
 class Context:
     """Resident per-GPU context (ipt_ctx_*)."""
 
@@ -263,6 +276,12 @@ class Context:
             _check(lib().ipt_ctx_download(self.h, None, out.ctypes.data), "ipt_ctx_download")
         else:
             _check(lib().ipt_ctx_download(self.h, out.ctypes.data, None), "ipt_ctx_download")
+        return out
+
+    def download_rgb8(self):
+        v = self.scene.view.contents
+        out = np.zeros((v.height, v.width, 3), dtype=np.uint8)
+        _check(lib().ipt_ctx_download_rgb8(self.h, out.ctypes.data), "ipt_ctx_download_rgb8")
         return out
 
     def trace(self, rays, flags=0):

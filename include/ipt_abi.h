@@ -134,6 +134,10 @@ const char* ipt_last_error(void);
 int ipt_render(const ipt_scene* scene, const ipt_params* params, int n_gpus, float* out_rgb32, double* out_rgb64,
                ipt_stats* stats);
 
+/* The same with the output stage fused on the device: Image.cpp:19-22's toRgb (clamp(int(x*255),0,255), no gamma) is
+ * applied by a kernel and only width*height*3 BYTES cross PCIe. */
+int ipt_render_rgb8(const ipt_scene* scene, const ipt_params* params, int n_gpus, uint8_t* out_rgb8, ipt_stats* stats);
+
 /* The reference's own buffers: `objects` is n records of the 144-byte ObjectData layout (ObjectData.hpp:15-31:
  * type@0 radius@8 north@16 east@40 position@64 emission@88 color@112 reflection@136), `camera` the 72-byte
  * Camera (origin, direction, orientation as 9 doubles, Camera.hpp:8-16). */
@@ -147,6 +151,7 @@ void ipt_ctx_destroy(ipt_ctx* ctx);
 int ipt_ctx_set_scene(ipt_ctx* ctx, const ipt_scene* scene);                 /* host -> device copy of the scene     */
 int ipt_ctx_render(ipt_ctx* ctx, const ipt_params* params, ipt_stats* stats); /* kernels only; frame stays in HBM    */
 int ipt_ctx_download(ipt_ctx* ctx, float* out_rgb32, double* out_rgb64);     /* device -> host copy of the frame     */
+int ipt_ctx_download_rgb8(ipt_ctx* ctx, uint8_t* out_rgb8);                  /* toRgb on the device, bytes to host   */
 /* Tiles of other ranks: a context can write its finished tiles into another context's frame (same process: pass
  * the context; other process: pass the 64-byte CUDA IPC handle exported by the owner). */
 int ipt_ctx_export_frame(ipt_ctx* ctx, void* handle64);

@@ -38,6 +38,8 @@ int ipt_host_build_bvh(ipt_host_scene* scene, uint32_t leaf_size, uint32_t brute
 int ipt_host_to_rgb(double x);
 /* Image.cpp:39-56: 8-bit RGB PNG, row 0 on top, written to `path` (zlib deflate; Magick++ is not needed). */
 int ipt_host_write_png(const char* path, const float* rgb, uint32_t width, uint32_t height);
+/* The same from bytes already mapped by toRgb (ipt_render_rgb8 / ipt_ctx_download_rgb8). */
+int ipt_host_write_png_rgb8(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
 
 /* Measurements.cpp:26-41: "HH:MM:SS.ms" with the milliseconds NOT zero-padded. */
 void ipt_host_time_string(uint64_t milliseconds, char* out, size_t out_len);

@@ -359,3 +359,23 @@ def test_int8_fold_quirk_from_depth_130(pyipt, oracle, tmp_path, depth):
         hs_bvh = pyipt.HostScene.load(str(path), brute_max=4)
         img_b, _ = pyipt.render(hs_bvh, spp, depth, seed=depth, flags=pyipt.FLAG_FP64)
         assert frac_within(img_b, ref, 1e-9) >= 0.995, path
+
+
+def test_device_side_to_rgb_matches_host_mapping(pyipt, oracle, ctx, tmp_path):
+    """ipt_render_rgb8 / ipt_ctx_download_rgb8: Image.cpp:19-22 on the device == the host mapping of the same frame,
+    byte for byte; PNG written from those bytes decodes to them."""
+    from PIL import Image
+    hs = pyipt.HostScene.load(oracle.scene_path("maze"), width=333, height=187)   # maze: many channels above 1.0
+    ctx.set_scene(hs)
+    ctx.render(16, 8, seed=8)
+    f32 = ctx.download(want64=False)
+    rgb8 = ctx.download_rgb8()
+    want = np.array([[pyipt.lib().ipt_host_to_rgb(float(x)) for x in row.ravel()] for row in f32[:20]], dtype=np.uint8).reshape(20, 333, 3)
+    assert np.array_equal(rgb8[:20], want)
+    assert np.array_equal(rgb8, np.clip((f32.astype(np.float64) * 255).astype(np.int64), 0, 255).astype(np.uint8))
+    assert rgb8.max() == 255 and rgb8.min() == 0
+    one, _ = pyipt.render_rgb8(hs, 16, 8, seed=8)
+    assert np.array_equal(one, rgb8)
+    p = str(tmp_path / "m.png")
+    assert pyipt.lib().ipt_host_write_png_rgb8(p.encode(), rgb8.ctypes.data, 333, 187) == 0
+    assert np.array_equal(np.asarray(Image.open(p)), rgb8)
