@@ -17,25 +17,38 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
+#include <thread>
 
 #include "host_scene.hpp"
 
 namespace {
 
+// Builder boxes are fp32 (the build is memory-bound: 40-byte instead of 80-byte primitives); fp64 bounds are rounded
+// outwards when they enter a box, so boxes stay conservative.
 struct Box {
-    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-    void grow(const double* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    void grow(const double* p)
+    {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], std::nextafterf((float)p[k], -INFINITY));
+            hi[k] = std::max(hi[k], std::nextafterf((float)p[k], INFINITY));
+        }
+    }
+    void grow(const float* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
     void grow(const Box& b) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
     double area() const
     {
-        const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        const double x = (double)hi[0] - lo[0], y = (double)hi[1] - lo[1], z = (double)hi[2] - lo[2];
         return (x < 0 || y < 0 || z < 0) ? 0.0 : 2 * (x * y + y * z + z * x);
     }
 };
 
-struct Prim { Box box; double c[3]; uint32_t ref; };
+struct Prim { Box box; float c[3]; uint32_t ref; };
 
 struct BNode { Box box; int left = -1, right = -1; uint32_t first = 0, count = 0; };
 
@@ -43,28 +56,55 @@ struct Builder {
     std::vector<Prim>& prims;
     std::vector<BNode> nodes;
     uint32_t leaf_size;
+    int par_depth = 0;   // levels below this node that may still fork a thread
 
-    int build(uint32_t first, uint32_t count)
+    // Splits [first, first+count) in place; returns the split position, or first when the range becomes a leaf.
+    uint32_t split(uint32_t first, uint32_t count, Box& box)
     {
-        const int id = (int)nodes.size();
-        nodes.emplace_back();
-        Box box, cb;
+        Box cb;
         for (uint32_t i = first; i < first + count; i++) { box.grow(prims[i].box); cb.grow(prims[i].c); }
-        nodes[id].box = box;
-        if (count <= leaf_size) { nodes[id].first = first; nodes[id].count = count; return id; }
+        if (count <= leaf_size) return first;
         // binned SAH over the centroid bounds, 16 bins per axis
         constexpr int NB = 16;
         int bestAxis = -1, bestSplit = -1;
         double bestCost = DBL_MAX;
+        if (count <= 12) {
+            // tiny ranges (the bulk of the nodes): median split along the widest centroid axis — initialising 48 bins
+            // per node cost more than the whole SAH evaluation down here
+            int ax = 0;
+            for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+            const uint32_t mid = first + count / 2;
+            std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
+                             [ax](const Prim& a, const Prim& b) { return a.c[ax] < b.c[ax]; });
+            return mid;
+        }
+        // one pass over the primitives fills the bins of all three axes (chunks of a large range on several threads)
+        struct Bins { Box bb[3][NB]; uint32_t bc[3][NB]; Bins() { std::memset(bc, 0, sizeof(bc)); } };
+        double kk[3];
+        for (int ax = 0; ax < 3; ax++) { const double ext = (double)cb.hi[ax] - cb.lo[ax]; kk[ax] = ext > 0 ? NB * (1 - 1e-9) / ext : 0.0; }
+        auto fill = [&](Bins& B, uint32_t a, uint32_t e) {
+            for (uint32_t i = a; i < e; i++)
+                for (int ax = 0; ax < 3; ax++) {
+                    const int b = std::min(NB - 1, std::max(0, (int)(((double)prims[i].c[ax] - cb.lo[ax]) * kk[ax])));
+                    B.bb[ax][b].grow(prims[i].box); B.bc[ax][b]++;
+                }
+        };
+        Bins bins;
+        const int nthr = (par_depth > 0 && count > 262144) ? (1 << par_depth) : 1;
+        if (nthr == 1) fill(bins, first, first + count);
+        else {
+            std::vector<Bins> part(nthr);
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; t++)
+                th.emplace_back([&, t] { fill(part[t], first + (uint32_t)((uint64_t)count * t / nthr), first + (uint32_t)((uint64_t)count * (t + 1) / nthr)); });
+            for (auto& t : th) t.join();
+            for (const Bins& P : part)
+                for (int ax = 0; ax < 3; ax++)
+                    for (int b = 0; b < NB; b++) { if (P.bc[ax][b]) bins.bb[ax][b].grow(P.bb[ax][b]); bins.bc[ax][b] += P.bc[ax][b]; }
+        }
         for (int ax = 0; ax < 3; ax++) {
-            const double ext = cb.hi[ax] - cb.lo[ax];
-            if (!(ext > 0)) continue;
-            Box bb[NB]; uint32_t bc[NB] = {0};
-            const double k = NB * (1 - 1e-9) / ext;
-            for (uint32_t i = first; i < first + count; i++) {
-                const int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cb.lo[ax]) * k)));
-                bb[b].grow(prims[i].box); bc[b]++;
-            }
+            if (!(kk[ax] > 0)) continue;
+            const Box* bb = bins.bb[ax]; const uint32_t* bc = bins.bc[ax];
             double rightArea[NB]; uint32_t rightCnt[NB];
             Box acc; uint32_t cnt = 0;
             for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); cnt += bc[b]; rightArea[b] = acc.area(); rightCnt[b] = cnt; }
@@ -80,12 +120,39 @@ struct Builder {
         if (bestAxis < 0) {
             mid = first + count / 2;   // all centroids coincide: split by index
         } else {
-            const double ext = cb.hi[bestAxis] - cb.lo[bestAxis], k = NB * (1 - 1e-9) / ext, lo = cb.lo[bestAxis];
+            const double k = kk[bestAxis], lo = cb.lo[bestAxis];
             auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
-                return std::min(NB - 1, std::max(0, (int)((p.c[bestAxis] - lo) * k))) <= bestSplit;
+                return std::min(NB - 1, std::max(0, (int)(((double)p.c[bestAxis] - lo) * k))) <= bestSplit;
             });
             mid = (uint32_t)(it - prims.begin());
             if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        return mid;
+    }
+
+    int build(uint32_t first, uint32_t count)
+    {
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        Box box;
+        const uint32_t mid = split(first, count, box);
+        nodes[id].box = box;
+        if (mid == first) { nodes[id].first = first; nodes[id].count = count; return id; }
+        if (par_depth > 0 && count > 65536) {
+            // large subtree: the two halves are independent (disjoint primitive ranges) -> build them on two threads
+            // into private node arrays, then splice them in with an index offset
+            Builder lb{prims, {}, leaf_size, par_depth - 1}, rb{prims, {}, leaf_size, par_depth - 1};
+            std::thread t([&] { lb.build(first, mid - first); });
+            rb.build(mid, first + count - mid);
+            t.join();
+            auto splice = [&](const std::vector<BNode>& sub) {
+                const int off = (int)nodes.size();
+                for (BNode n : sub) { if (n.left >= 0) { n.left += off; n.right += off; } nodes.push_back(n); }
+                return off;
+            };
+            const int l = splice(lb.nodes), r = splice(rb.nodes);
+            nodes[id].left = l; nodes[id].right = r;
+            return id;
         }
         const int l = build(first, mid - first);
         const int r = build(mid, first + count - mid);
@@ -96,11 +163,12 @@ struct Builder {
 
 inline float down(double v, double pad) { return std::nextafterf((float)(v - pad), -INFINITY); }
 inline float up(double v, double pad) { return std::nextafterf((float)(v + pad), INFINITY); }
+inline double dabs(float v) { return std::fabs((double)v); }
 
 void put_box(const Box& b, float* lo, float* hi)
 {
     for (int k = 0; k < 3; k++) {
-        const double pad = 2e-3 + 2e-6 * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+        const double pad = 2e-3 + 2e-6 * std::max(dabs(b.lo[k]), dabs(b.hi[k]));
         lo[k] = down(b.lo[k], pad); hi[k] = up(b.hi[k], pad);
     }
 }
@@ -113,13 +181,17 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
     s->bvh_nodes.clear(); s->bvh_slot_prim.clear();
     const uint32_t ns = (uint32_t)s->sphere_object.size(), nr = (uint32_t)s->rect_object.size(), n = ns + nr;
     if (n <= brute_max) { s->refresh_view(); return 0; }
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (std::getenv("IPT_VERBOSE")) std::fprintf(stderr, "[bvh] %s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count()); };
     leaf_size = std::min(16u, std::max(1u, leaf_size));
     std::vector<Prim> prims(n);
     for (uint32_t i = 0; i < ns; i++) {
         const double* c = &s->sphere_cxyzr[4 * (size_t)i];
         const double r = std::fabs(c[3]);
         Prim& p = prims[i];
-        for (int k = 0; k < 3; k++) { p.box.lo[k] = c[k] - r; p.box.hi[k] = c[k] + r; p.c[k] = c[k]; }
+        const double lo[3] = {c[0] - r, c[1] - r, c[2] - r}, hi[3] = {c[0] + r, c[1] + r, c[2] + r};
+        p.box.grow(lo); p.box.grow(hi);
+        for (int k = 0; k < 3; k++) p.c[k] = (float)c[k];
         p.ref = i;
     }
     for (uint32_t j = 0; j < nr; j++) {
@@ -131,12 +203,18 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
                 for (int k = 0; k < 3; k++) q[k] = c[k] + sn * N[k] + se * E[k];
                 p.box.grow(q);
             }
-        for (int k = 0; k < 3; k++) p.c[k] = c[k];
+        for (int k = 0; k < 3; k++) p.c[k] = (float)c[k];
         p.ref = 0x80000000u | j;
     }
-    Builder b{prims, {}, leaf_size};
+    // fork threads on the top levels of large scenes (2^par_depth subtrees in flight)
+    int par_depth = 0;
+    for (unsigned hw = std::max(1u, std::thread::hardware_concurrency()); (1u << par_depth) < hw && par_depth < 5;) par_depth++;
+    if (const char* e = std::getenv("IPT_BVH_PAR_DEPTH")) par_depth = std::atoi(e);
+    lap("prims");
+    Builder b{prims, {}, leaf_size, par_depth};
     b.nodes.reserve(2 * (size_t)n / leaf_size + 16);
     const int root = b.build(0, n);
+    lap("tree");
     s->bvh_slot_prim.resize(n);
     for (uint32_t i = 0; i < n; i++) s->bvh_slot_prim[i] = prims[i].ref;
 
@@ -146,7 +224,7 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         ipt_bvh_node o;
         std::memset(&o, 0, sizeof(o));
         put_box(b.nodes[root].box, o.lo0, o.hi0);
-        for (int k = 0; k < 3; k++) { o.lo1[k] = FLT_MAX; o.hi1[k] = -FLT_MAX; }
+        for (int k = 0; k < 3; k++) { o.lo1[k] = FLT_MAX; o.hi1[k] = -FLT_MAX; }   // inverted: never hit
         o.child[0] = leaf_code(b.nodes[root]); o.count[0] = b.nodes[root].count;
         o.child[1] = ~0; o.count[1] = 1;
         s->bvh_nodes.push_back(o);
@@ -177,5 +255,6 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         if (r.left >= 0) o.child[1] = index[nd.right]; else { o.child[1] = leaf_code(r); o.count[1] = r.count; }
     }
     s->refresh_view();
+    lap("emit");
     return (int)s->bvh_nodes.size();
 }
