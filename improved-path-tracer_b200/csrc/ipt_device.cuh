@@ -512,19 +512,32 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
     return 2 + n_sph + (n_sph + 3) / 4 + 2 * (nx + ny + nz) + 4 * n_gen + (n_gen + 3) / 4 + 2 * n_obj;
 }
 // The list sizes come in as kernel parameters (uniform registers / constant bank), not from the blob in shared memory.
-struct FastHeader { uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj; };
+struct FastHeader {
+    uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
+    uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
+};
+__host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
+{
+    FastHeader h;
+    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj;
+    h.off_sphobj = 2 + n_sph;
+    h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
+    h.off_gen = h.off_axs + 2 * (nx + ny + nz);
+    h.off_genobj = h.off_gen + 4 * n_gen;
+    h.off_mat = h.off_genobj + (n_gen + 3) / 4;
+    return h;
+}
 __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    const uint4* p = blob + 2;
     f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen;
-    f.sph = reinterpret_cast<const float4*>(p); p += f.n_sph;
-    f.sph_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_sph + 3) / 4;
-    f.axs = reinterpret_cast<const float4*>(p); p += 2 * (f.n_x + f.n_y + f.n_z);
-    f.ax0_x = 0; f.ax0_y = f.n_x; f.ax0_z = f.n_x + f.n_y;
-    f.gen = reinterpret_cast<const R4<float>*>(p); p += 4 * f.n_gen;
-    f.gen_obj = reinterpret_cast<const uint32_t*>(p); p += (f.n_gen + 3) / 4;
-    f.mat = reinterpret_cast<const float4*>(p);
+    f.sph = reinterpret_cast<const float4*>(blob + 2);
+    f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
+    f.axs = reinterpret_cast<const float4*>(blob + hd.off_axs);
+    f.ax0_x = 0; f.ax0_y = hd.n_x; f.ax0_z = hd.n_x + hd.n_y;
+    f.gen = reinterpret_cast<const R4<float>*>(blob + hd.off_gen);
+    f.gen_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_genobj);
+    f.mat = reinterpret_cast<const float4*>(blob + hd.off_mat);
     return f;
 }
 
@@ -543,27 +556,32 @@ __device__ __forceinline__ void fast_axis_list(const float4* __restrict__ axs, u
 {
     constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
     const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
-#pragma unroll 2
-    for (uint32_t s = first; s < first + n; s++) {   // n is even: lists are padded with a never-hit record
-        const float4 a = axs[2 * s];
-        const float hj = axs[2 * s + 1].x;
-        const float t = (a.x - ok) * inv_dk;                     // d_K == 0: +-inf or NaN, both rejected below (Plane.cu:55)
-        const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
-        const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
-        best.t = hit ? t : best.t;
-        best.code = hit ? (((uint32_t)(K + 1) << 28) | s) : best.code;
+    const float4* rec = axs + 2 * first;
+    for (uint32_t s = first; s < first + n; s += 2, rec += 4) {   // n is even: lists are padded with a never-hit record
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const float4 a = rec[2 * u];
+            const float hj = rec[2 * u + 1].x;
+            const float t = (a.x - ok) * inv_dk;                 // d_K == 0: +-inf or NaN, both rejected below (Plane.cu:55)
+            const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
+            const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
+            best.t = hit ? t : best.t;
+            best.code = hit ? (((uint32_t)(K + 1) << 28) | (s + u)) : best.code;
+        }
     }
 }
 
-// Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.
+// Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.  `self` is the hit CODE of
+// the surface the ray starts on (the fast kernel's queues are private to it), NO_OBJECT for camera rays.
 __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<float>& o, const V3<float>& d, uint32_t self, bool onSurf)
 {
     FastHit best;
     best.t = (float)IPT_INF; best.code = NO_OBJECT;
+    const uint32_t self_sphere = onSurf ? self : NO_OBJECT;      // sphere codes are plain list indices (kind 0)
 #pragma unroll 2
     for (uint32_t s = 0; s < f.n_sph; s++) {         // n_sph is even (padded with a never-hit sphere)
         const float4 sp = f.sph[s];
-        const bool selfS = onSurf && f.sph_obj[s] == self;       // start point lies ON this sphere: exact second root -2b
+        const bool selfS = s == self_sphere;                     // start point lies ON this sphere: exact second root -2b
         const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);
         const float b = dot(op, d);
         const float delta = fmaf(b, b, fmaf(sp.w, sp.w, -dot(op, op)));       // b*b - op.op + r*r   (Sphere.cu:31)
@@ -581,7 +599,7 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
     for (uint32_t s = 0; s < f.n_gen; s++) {
         Hit<float> h;
         h.t = best.t; h.obj = NO_OBJECT; h.slot = NO_OBJECT;     // obj = max: strict '<' within this (ordered) list
-        test_rect<float>(f.gen + 4 * s, s, f.gen_obj[s], o, d, self, h);
+        test_rect<float>(f.gen + 4 * s, s, (4u << 28) | s, o, d, self, h);   // compared with `self` only: codes on both sides
         if (h.slot != NO_OBJECT) { best.t = h.t; best.code = (4u << 28) | s; }
     }
     return best;

@@ -517,11 +517,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                     }
                     const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
                     has0 = alive;
-                    o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = hobj;
+                    o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.code;
                     const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
                     o0.meta = mcommon | (r.meta & 0x300u);
                     has1 = sp.has1;
-                    o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = hobj;
+                    o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
                     o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
                 }
             }

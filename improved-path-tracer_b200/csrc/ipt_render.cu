@@ -370,7 +370,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     if (!blob.empty()) {
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->fast_words = (uint32_t)(blob.size() / 4);
-        c->fast_hd = FastHeader{blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]};
+        c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
