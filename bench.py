@@ -31,12 +31,22 @@ WORKLOADS = {
     "spheres": dict(scene="spheres", width=None, height=None, depth=10, spp=40, flops=303, desc="scenes/spheres.json -d=10 -s=40 (configs[0])"),
     "mirrors": dict(scene="mirrors", width=None, height=None, depth=10, spp=40, flops=453, desc="scenes/mirrors.json -d=10 -s=40 (configs[1])"),
     "maze": dict(scene="maze", width=None, height=None, depth=10, spp=40, flops=1786, desc="scenes/maze.json -d=10 -s=40 (configs[2])"),
+    # configs[4]: generated on the fly by scripts/make_synthetic_scene.py (seeded); BVH path, flops not modelled
+    "synthetic1m": dict(scene="synthetic1m", width=None, height=None, depth=10, spp=256, flops=0,
+                        desc="synthetic 1M-primitive scene in the scenes/*.json schema -d=10 -s=256 (configs[4])"),
 }
 BYTES_PER_BOUNCE = 96          # fused extend+shade wavefront: 48 B ray record read + 48 B written
 FP32_LANES_PER_SM = 128
 
 
 def scene_file(name):
+    if name == "synthetic1m":
+        import subprocess
+        p = "/tmp/ipt_synthetic_1000000.json"
+        if not os.path.isfile(p):
+            subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), p + ".tmp", "1000000"], check=True)
+            os.replace(p + ".tmp", p)
+        return p
     p = os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".json")
     if not os.path.isfile(p):
         raise SystemExit(f"{p} missing: run `python -c 'import __graft_entry__ as g; g.build()'` where the reference is mounted")
@@ -328,7 +338,10 @@ def main():
             "clocks": clocks,
             "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if not wl["flops"]:
+            line["roofline"] = roof_hbm
+            line.pop("roofline_fp32")
+        if world == 1 and not args.no_cpu_baseline and wl["scene"] != "synthetic1m":
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
     ctx.close()

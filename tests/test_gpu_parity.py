@@ -379,3 +379,20 @@ def test_device_side_to_rgb_matches_host_mapping(pyipt, oracle, ctx, tmp_path):
     p = str(tmp_path / "m.png")
     assert pyipt.lib().ipt_host_write_png_rgb8(p.encode(), rgb8.ctypes.data, 333, 187) == 0
     assert np.array_equal(np.asarray(Image.open(p)), rgb8)
+
+
+def test_benchmark_driver_writes_reference_format(oracle, tmp_path):
+    """tools/trace_bench.py (the test_automation.py-compatible driver): one case -> `<id>;HH:MM:SS.ms;<cpuMiB>;<gpuMiB>\\n`."""
+    import shutil
+    import sys
+    (tmp_path / "scenes").mkdir()
+    j = json.load(open(oracle.scene_path("spheres")))
+    j["width"], j["height"] = 160, 90
+    (tmp_path / "scenes" / "spheres.json").write_text(json.dumps(j))
+    exe = os.path.join(ROOT, "improved-path-tracer_b200", "tracer")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "trace_bench.py"), "-o", "-s", "8", "-d", "5", "-p", "scenes/spheres.json",
+                        "--tracer", exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = (tmp_path / "benchmark.txt").read_text()
+    assert re.fullmatch(r"spheresD5S8;\d\d:\d\d:\d\d\.\d{1,3};\d+(\.\d+)?;\d+(\.\d+)?\n", line), line
+    assert (tmp_path / "spheresD5S8.png").exists()
