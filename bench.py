@@ -183,8 +183,8 @@ def main():
     ap.add_argument("--fp64", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
-    ap.add_argument("--ref-stride", type=int, default=11)
-    ap.add_argument("--ref-spp", type=int, default=8)
+    ap.add_argument("--ref-stride", type=int, default=4, help="reference arm: 1/stride of the reference's 484 thread cells are rendered per step")
+    ap.add_argument("--ref-spp", type=int, default=4)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,7 +320,8 @@ def main():
         roof_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak,
                     "traffic": None if traffic is None else traffic * my_bounces_per_step / max(1, launches / args.steps),
                     "peak_source": hbm_src, "algorithmic_bytes_per_bounce": BYTES_PER_BOUNCE,
-                    "kernel": "k_bounce (one launch per bounce per batch); achieved = bounces x bytes / sum of launch durations"}
+                    "kernel": ("k_extend_bvh + k_bounce<MODE_SHADE>" if wl["scene"] == "synthetic1m" else "k_bounce_fast") +
+                              " (one launch per bounce per batch); achieved = bounces x bytes / sum of launch durations; traffic = measured DRAM bytes per bounce (ncu) x bounces per launch"}
         binding = roof_hbm if roof_hbm["frac"] >= roof_fp32["frac"] else roof_fp32
         line = {
             "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
