@@ -46,6 +46,7 @@ template <typename R> struct KParams {
     unsigned long long* frame;  // 3 x 64-bit accumulators per pixel (fixed point, or fp64 bits with IPT_FLAG_FLOAT_ACCUM)
     double fixed_scale;
     uint32_t refill_min;        // k_extend_bvh: idle lanes per warp that trigger a refill
+    uint32_t descend_min;       // k_extend_bvh: the descent phase ends when fewer lanes than this are still descending
     uint2* hits;                // split pipeline: {t bits, slot} per ray of the current pass (k_extend_bvh -> k_bounce<MODE_SHADE>)
     const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
     uint32_t fast_words;
@@ -352,8 +353,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
         // Both phases are warp-synchronous loops driven by __any_sync: the warp reconverges before the leaf phase
         // (left to the compiler, lanes that found their leaf early ran the primitive tests one or two at a time).
         bool done = false;
-        // ---- phase 1: every lane with a ray descends inner nodes until it holds a leaf or runs out of nodes
-        while (__any_sync(0xffffffffu, has && !done && node >= 0)) {
+        // ---- phase 1: lanes with a ray descend inner nodes.  The phase ends when fewer than `descend_min` lanes are
+        // still descending and at least one lane holds a leaf to test (the stragglers keep their state and resume in
+        // the next round) — waiting for the slowest lane left this loop at 8.9 of 32 lanes active.
+        for (;;) {
+            const uint32_t desc = __ballot_sync(0xffffffffu, has && !done && node >= 0);
+            if (desc == 0) break;
+            if ((uint32_t)__popc(desc) < p.descend_min && __any_sync(0xffffffffu, has && !done && node < 0)) break;
             if (has && !done && node >= 0) {
                 float4 a, b, c, e;
                 if ((uint32_t)node < n_top) { const float4* q = top + 4 * node; a = q[0]; b = q[1]; c = q[2]; e = q[3]; }
@@ -384,15 +390,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
             }
         }
         // ---- phase 2: the lanes holding a leaf test its primitives, one primitive per lane per iteration
+        const bool at_leaf = has && !done && node < 0;
         uint32_t s_cur = 0, s_end = 0;
-        if (has && !done) {
+        if (at_leaf) {
             const uint32_t code = (uint32_t)(~node);
             s_cur = code >> 4; s_end = s_cur + (code & 15u) + 1u;
         }
         while (__any_sync(0xffffffffu, s_cur < s_end)) {
             if (s_cur < s_end) { test_bslot(sc, s_cur, o, d, inv, self, onSurf, best); s_cur++; }
         }
-        if (has && !done) {
+        if (at_leaf) {
             if (sp == 0) done = true;
             else node = stack[--sp];
         }

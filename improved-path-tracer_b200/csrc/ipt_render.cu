@@ -557,6 +557,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         c->hits_bytes = (size_t)cap * 8;
     }
     kp.hits = c->hits;
+    kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : 12u;
     kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
