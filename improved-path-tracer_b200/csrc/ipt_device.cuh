@@ -446,6 +446,7 @@ template <typename R> struct Spawn {
     V3<R> d0, d1;
     R w0, w1;
     bool has0, has1;
+    bool teleport;   // unknown material: the continuation is the reference's default RayData ray, origin = direction = 0
 };
 
 // Sphere.cu:41-56, Plane.cu:70-84, AObject.hpp:83-135.  `g0` is the first geometry vector of the hit slot.
@@ -462,7 +463,7 @@ __device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int ref
         n = dot(in, raw) < (R)0 ? -raw : raw;   // Sphere.cu:45: points ALONG the incoming ray (into the surface)
     }
     Spawn<R> s;
-    s.has0 = true; s.has1 = false; s.w0 = (R)1; s.w1 = (R)0;
+    s.has0 = true; s.has1 = false; s.w0 = (R)1; s.w1 = (R)0; s.teleport = false;
     s.d1 = mk<R>(0, 0, 0);
     if (reflection == 0) {                      // AObject.hpp:104-108
         s.d0 = diffuse_dir(n, rnd);
@@ -477,8 +478,13 @@ __device__ __forceinline__ Spawn<R> scatter(bool isRect, const R4<R> g0, int ref
         if (!refract_dir(in, raw, refr)) s.d0 = spec;
         else if (depth < 2) { s.d0 = refr; s.w0 = (R)0.95; s.d1 = spec; s.w1 = (R)0.05; s.has1 = true; }
         else s.d0 = (u23<R>(rnd.w) > (R)0.95) ? spec : refr;
-    } else {                                    // "Uknown reflection type": zero ray with weight 0 -> nothing to trace
-        s.has0 = false;
+    } else {
+        // "Uknown reflection type" (Sphere.cu:52-55): RayData{} = ray (0,0,0)->(0,0,0) with power 0.  firstLayer and
+        // secondLayer multiply by that power (nothing to trace), but deepLayers ignores it (Renderer.cu:208-209): from
+        // depth 2 on the path continues, at full weight, from the origin with a zero direction (it can only hit a
+        // sphere that contains the origin).
+        s.has0 = depth >= 2;
+        s.teleport = true;
         s.d0 = mk<R>(0, 0, 0);
     }
     return s;
@@ -656,7 +662,9 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
     s.d0.x = pickSpec ? spec.x : (pickRefr ? refr.x : diff.x);
     s.d0.y = pickSpec ? spec.y : (pickRefr ? refr.y : diff.y);
     s.d0.z = pickSpec ? spec.z : (pickRefr ? refr.z : diff.z);
-    s.has0 = reflection >= 0 && reflection <= 2;
+    s.teleport = reflection < 0 || reflection > 2;                            // unknown material: see scatter<R>
+    s.has0 = !s.teleport || depth >= 2;
+    if (s.teleport) { s.d0.x = 0.f; s.d0.y = 0.f; s.d0.z = 0.f; }
     s.has1 = early && (isSpec || (isRefr && refr_ok));                        // AObject.hpp:91-94, :122-125
     s.w0 = s.has1 ? (isSpec ? 0.92f : 0.95f) : 1.f;
     s.w1 = isSpec ? 0.08f : 0.05f;

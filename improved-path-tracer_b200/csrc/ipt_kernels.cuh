@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                                 has0 = true;
                                 o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.obj;
                                 o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
+                                if (sp.teleport) { o0.o = mk<R>(0, 0, 0); o0.self = NO_OBJECT; o0.meta = make_meta(depth + 1, lane_id, false, false, sample); }
                             }
                             if (sp.has1) {
                                 // depth 0: the second ray is an emission probe of the next surface (its deeper recursion
@@ -527,6 +528,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                     o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.code;
                     const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
                     o0.meta = mcommon | (r.meta & 0x300u);
+                    if (sp.teleport) { o0.o = mk<float>(0.f, 0.f, 0.f); o0.self = NO_OBJECT; o0.meta &= ~META_ONSURF; }
                     has1 = sp.has1;
                     o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
                     o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);

@@ -513,7 +513,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         double bound = std::max(c->max_emission, 1e-30) * 2.0 * (prm.max_depth + 1.0) * std::pow(mc, (double)prm.max_depth);
         bound *= (double)prm.samples;
         const int bits = 62 - (int)std::ceil(std::log2(bound));
-        if (!std::isfinite(bound) || bits < 16) float_accum = true;
+        // below 2^-30 resolution the quantisation would show in dim pixels: use fp64 atomics instead (not bit-reproducible)
+        if (!std::isfinite(bound) || bits < 30) float_accum = true;
         else scale = std::ldexp(1.0, std::min(bits, 40));
     }
     if (float_accum) kp.flags |= IPT_FLAG_FLOAT_ACCUM; else kp.flags &= ~IPT_FLAG_FLOAT_ACCUM;

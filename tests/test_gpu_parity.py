@@ -396,3 +396,82 @@ def test_benchmark_driver_writes_reference_format(oracle, tmp_path):
     line = (tmp_path / "benchmark.txt").read_text()
     assert re.fullmatch(r"spheresD5S8;\d\d:\d\d:\d\d\.\d{1,3};\d+(\.\d+)?;\d+(\.\d+)?\n", line), line
     assert (tmp_path / "spheresD5S8.png").exists()
+
+
+def test_degenerate_and_unknown_objects(pyipt, oracle, tmp_path):
+    """Edge cases the reference tolerates: a rectangle with north parallel to east (normal = NaN: never hit), a
+    skewed rectangle (rejected by the edge-distance test), a zero-radius sphere, an unknown reflection value (zero ray
+    of weight 0, Sphere.cu:52-55 — which deepLayers nevertheless keeps tracing from the origin), objects far outside.  fp64 kernels == oracle, brute force and BVH."""
+    from scene_util import room_objects, vec
+    objs = room_objects()
+    objs.insert(3, {"type": "plane", "position": vec((600, 300, 300)), "north": vec((0, 0, 50)), "east": vec((0, 0, 80)),
+                    "color": vec((.9, .1, .1)), "emission": vec((5, 5, 5)), "reflection": 0})                      # degenerate
+    objs.append({"type": "plane", "position": vec((500, 350, 200)), "north": vec((0, 0, 60)), "east": vec((70, 0, 25)),
+                 "color": vec((.2, .9, .2)), "emission": vec((0, 0, 0)), "reflection": 1})                         # skewed
+    objs.append({"type": "sphere", "radius": 0.0, "position": vec((640, 300, 360)), "color": vec((.5, .5, .5)), "emission": vec((9, 9, 9)), "reflection": 0})
+    objs.append({"type": "sphere", "radius": 120.0, "position": vec((420, 420, 200)), "color": vec((.8, .8, .3)), "emission": vec((0, 0, 0)), "reflection": 7})   # unknown material
+    objs.append({"type": "sphere", "radius": 90.0, "position": vec((880, 380, 160)), "color": vec((.9, .9, .9)), "emission": vec((0, 0, 0)), "reflection": 2})
+    objs.append({"type": "sphere", "radius": 50.0, "position": vec((1e6, 1e6, 1e6)), "color": vec((.9, .9, .9)), "emission": vec((3, 3, 3)), "reflection": 1})
+    # contains the origin: the only thing the zero ray of an unknown material (deepLayers ignores its weight 0) can hit
+    objs.append({"type": "sphere", "radius": 30.0, "position": vec((5, -8, 12)), "color": vec((.6, .6, .6)), "emission": vec((40, 10, 2)), "reflection": 0})
+    scene = {"width": 192, "height": 108, "camera": {"position": vec((640, 0, 360)), "direction": vec((0, 2, 0)), "orientation": vec((-3, 0, 0))},
+             "objects": objs}
+    path = write_scene(tmp_path / "edge.json", scene)
+    ref, cnt = oracle.render(oracle.Scene.load(path), 4, 7, rng=oracle.RNG_COUNTER, seed=21)
+    assert np.isfinite(ref).all() and ref.any()
+    for brute_max in (64, 4):
+        hs = pyipt.HostScene.load(path, brute_max=brute_max)
+        img, st = pyipt.render(hs, 4, 7, seed=21, flags=pyipt.FLAG_FP64)
+        assert frac_within(img, ref, 1e-9) >= 0.999, brute_max
+        assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-3 * cnt["casts_needed"]
+        img32, _ = pyipt.render(hs, 4, 7, seed=21)
+        assert np.isfinite(img32).all() and frac_within(img32, ref, 1e-3) >= 0.97, brute_max
+
+
+def test_large_bvh_scene_hits_and_means(pyipt, oracle, tmp_path):
+    """100k primitives (BASELINE config 5 at a tenth of its size): nearest hit vs the oracle's linear scan on random
+    rays, and fp32 vs fp64 frames on the same random stream."""
+    import subprocess, sys
+    path = str(tmp_path / "syn100k.json")
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), path, "100000", "256", "144"], check=True)
+    sc = oracle.Scene.load(path)
+    hs = pyipt.HostScene.load(path)
+    assert hs.view.contents.n_bvh_nodes > 10000
+    rng = np.random.default_rng(2)
+    m = 1500
+    o = rng.uniform([30, -480, 30], [1250, 680, 690], size=(m, 3)); d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1)
+    oi, ot = oracle.nearest_hit(sc, rays)
+    c = pyipt.Context(0); c.set_scene(hs)
+    gi, gt = c.trace(rays, pyipt.FLAG_FP64)
+    assert np.array_equal(gi, oi) and np.allclose(gt, ot, rtol=1e-10)
+    gi, gt = c.trace(rays, 0)
+    assert np.mean(gi == oi) >= 0.998
+    s64 = c.render(8, 10, seed=3, flags=pyipt.FLAG_FP64); a = c.download()
+    s32 = c.render(8, 10, seed=3); b = c.download()
+    assert frac_within(b, a, 1e-3) >= 0.93
+    assert abs(a.mean() - b.mean()) <= 3e-3 * a.mean()
+    assert abs(s32["traced_bounces"] - s64["traced_bounces"]) <= 3e-3 * s64["traced_bounces"]
+    c.close()
+
+
+def test_bright_colours_fall_back_to_floating_point_accumulation(pyipt, oracle, tmp_path):
+    """Colours above 1 make the radiance bound explode with depth: the fixed-point accumulator would not fit, so the
+    library switches to fp64 atomics (IPT_FLAG_FLOAT_ACCUM behaviour) — same image up to summation order."""
+    from scene_util import room_objects, vec
+    objs = room_objects()
+    for o in objs[:6]:
+        o["color"] = vec((1.6, 1.5, 1.7))
+    objs.append({"type": "sphere", "radius": 100.0, "position": vec((640, 400, 200)), "color": vec((1.2, 0.4, 0.4)), "emission": vec((-2, 0.5, 0)), "reflection": 1})
+    scene = {"width": 96, "height": 54, "camera": {"position": vec((640, 0, 360)), "direction": vec((0, 1, 0)), "orientation": vec((-1, 0, 0))}, "objects": objs}
+    path = write_scene(tmp_path / "bright.json", scene)
+    ref, _ = oracle.render(oracle.Scene.load(path), 4, 40, rng=oracle.RNG_COUNTER, seed=5)
+    assert ref.max() > 1e3 and ref.min() < 0
+    hs = pyipt.HostScene.load(path)
+    img, _ = pyipt.render(hs, 4, 40, seed=5, flags=pyipt.FLAG_FP64)
+    rel = np.abs(img - ref) / np.maximum(1.0, np.abs(ref))
+    # sums of terms up to 1e9 of both signs: forward accumulation vs the reference's back-to-front fold differ by rounding
+    assert np.mean(np.all(rel <= 1e-9, axis=2)) >= 0.999, (np.sort(rel.ravel())[-20:], np.mean(np.all(rel <= 1e-9, axis=2)))
+    img2, _ = pyipt.render(hs, 4, 12, seed=5, flags=pyipt.FLAG_FP64 | pyipt.FLAG_FLOAT_ACCUM)
+    ref2, _ = oracle.render(oracle.Scene.load(path), 4, 12, rng=oracle.RNG_COUNTER, seed=5)
+    assert np.mean(np.all(np.abs(img2 - ref2) <= 1e-9 * np.maximum(1.0, np.abs(ref2)), axis=2)) >= 0.999
