@@ -585,7 +585,7 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
     best.t = (float)IPT_INF; best.code = NO_OBJECT;
     const uint32_t self_sphere = onSurf ? self : NO_OBJECT;      // sphere codes are plain list indices (kind 0)
 #pragma unroll 2
-    for (uint32_t s = 0; s < f.n_sph; s++) {         // n_sph is even (padded with a never-hit sphere)
+    for (uint32_t s = 0; s < f.n_sph; s++) {
         const float4 sp = f.sph[s];
         const bool selfS = s == self_sphere;                     // start point lies ON this sphere: exact second root -2b
         const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);

@@ -188,10 +188,10 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         r.obj = s->rect_object[j] | RECT_BIT;
         ax[K].push_back(r);
     }
-    // every list is padded to an even length with a record that can never be hit (the device loops are unrolled by 2)
+    // the axis lists are padded to an even length with a record that can never be hit (their device loops step by 2)
     for (int k = 0; k < 3; k++)
         if (ax[k].size() & 1) ax[k].push_back(AxRect{3.0e38f, 0.f, 0.f, -1.f, -1.f, NO_OBJECT});
-    const uint32_t ns_real = s->n_spheres, ns = (ns_real + 1) & ~1u, ng = (uint32_t)gen.size(), no = s->n_objects;
+    const uint32_t ns_real = s->n_spheres, ns = ns_real, ng = (uint32_t)gen.size(), no = s->n_objects;
     const uint32_t words = fast_blob_words(ns, (uint32_t)ax[0].size(), (uint32_t)ax[1].size(), (uint32_t)ax[2].size(), ng, no);
     std::vector<uint32_t> blob((size_t)words * 4, 0u);
     auto F = [](double x) { float f = (float)x; uint32_t u; std::memcpy(&u, &f, 4); return u; };
