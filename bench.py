@@ -274,6 +274,7 @@ def main():
     tot_samples = allsum(samples) / args.steps
     tot_bounces = allsum(bounces) / args.steps
     tot_launches = int(allsum(launches))
+    allsum_active = allsum(st["active_pixels"])
     my_bounces_per_step = bounces / args.steps
 
     # ---- end to end through host buffers: upload from pinned memory + kernels + gather + download, every step
@@ -331,6 +332,7 @@ def main():
             "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],
                        "samples_per_step": int(tot_samples), "traced_bounces_per_step": int(tot_bounces),
+                       "pixels_with_camera_rays": int(allsum_active), "pixels": W * H,
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
                        "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray)", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

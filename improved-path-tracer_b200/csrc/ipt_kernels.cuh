@@ -38,6 +38,10 @@ template <typename R> struct KParams {
     const uint32_t* tile_ids;
     uint32_t n_tiles_local, tiles_x, tile_w, tile_h;
     uint32_t mt_x, mt_per_tile; // micro-tiles (8x4 pixels) per tile row / per tile
+    // the micro-tiles of this rank that can see the scene (k_active_microtiles), packed (y << 16 | x) in units of 8x4
+    // pixels, in tile-major order; the sample ids of a render enumerate only these
+    const uint32_t* mt_list;
+    uint32_t n_mt;
     // batch
     uint32_t base_mt, base_sample, n_first;   // pass 0: first micro-tile, first sample, number of sample ids in the batch
     Queue qin, qout;
@@ -79,12 +83,10 @@ __device__ __forceinline__ bool decode_sample(const KParams<R>& p, uint32_t sid,
     const uint32_t s = p.base_sample + g;
     sample = s % p.spp;
     const uint32_t mt = p.base_mt + s / p.spp;
-    const uint32_t lt = mt / p.mt_per_tile, m = mt % p.mt_per_tile;
-    if (lt >= p.n_tiles_local) return false;
-    const uint32_t tile = p.tile_ids[lt];
-    const uint32_t tx = tile % p.tiles_x, tz = tile / p.tiles_x;
-    px = tx * p.tile_w + (m % p.mt_x) * 8u + (l & 7u);
-    pz = tz * p.tile_h + (m / p.mt_x) * 4u + (l >> 3);
+    if (mt >= p.n_mt) return false;
+    const uint32_t xy = p.mt_list[mt];
+    px = (xy & 0xFFFFu) * 8u + (l & 7u);
+    pz = (xy >> 16) * 4u + (l >> 3);
     return px < p.W && pz < p.H;
 }
 
@@ -106,6 +108,53 @@ __device__ __forceinline__ void camera_ray(const KParams<R>& p, uint32_t px, uin
     r.pixel = pixel;
     r.meta = make_meta(0, 0, false, false, sample);
     r.self = NO_OBJECT;
+}
+
+// Exact pruning of camera rays (the counterpart of SURVEY.md App. A.8 for pass 0): a pixel whose UN-jittered camera ray
+// misses the scene's bounding box grown by `grow` (>= the +-1 pixel box jitter of Renderer.cu:133-138 plus rounding
+// slack) is exactly 0 for every sample — all its rays miss every object (Renderer.cu:153).  One thread per micro-tile
+// (8x4 pixels) of this rank, in tile-major order: flag = 1 iff any of its pixels can see the grown box.  fp64.
+struct ActiveParams {
+    double camO[3], camD[3], camX[3], camZ[3], fov, lo[3], hi[3];
+    uint32_t W, H;
+    const uint32_t* tile_ids;
+    uint32_t n_tiles_local, tiles_x, tile_w, tile_h, mt_x, mt_per_tile;
+    uint32_t* packed;   // out: (y << 16 | x) of the micro-tile
+    uint8_t* flags;     // out
+};
+__global__ void __launch_bounds__(256) k_active_microtiles(const __grid_constant__ ActiveParams p)
+{
+    const uint32_t total = p.n_tiles_local * p.mt_per_tile;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t lt = i / p.mt_per_tile, m = i % p.mt_per_tile;
+        const uint32_t tile = p.tile_ids[lt];
+        const uint32_t mx = (tile % p.tiles_x) * p.mt_x + m % p.mt_x, my = (tile / p.tiles_x) * (p.tile_h / 4) + m / p.mt_x;
+        p.packed[i] = (my << 16) | mx;
+        bool any = false;
+        for (uint32_t l = 0; l < 32 && !any; l++) {
+            const uint32_t px = mx * 8 + (l & 7), pz = my * 4 + (l >> 3);
+            if (px >= p.W || pz >= p.H) continue;
+            const double corr = (p.W % 2 == 0) ? 0.5 : 0.0;
+            const double stepX = (px < p.W / 2) ? (double)(p.W / 2 - px) - corr : ((double)p.W / 2 - px - 1.0) + ((corr == 0.0) ? 1.0 : corr);
+            const double stepZ = (pz < p.H / 2) ? (double)(p.H / 2 - pz) - corr : ((double)p.H / 2 - pz - 1.0) + ((corr == 0.0) ? 1.0 : corr);
+            double o[3], d[3], len = 0;
+            for (int k = 0; k < 3; k++) {
+                d[k] = p.camD[k] + p.camX[k] * stepX * p.fov + p.camZ[k] * stepZ * p.fov;
+                o[k] = p.camO[k] + p.camX[k] * stepX + p.camZ[k] * stepZ + p.camD[k] * IPT_VIEWPORT_DISTANCE;
+                len += d[k] * d[k];
+            }
+            (void)len;   // the slab test does not need a unit direction
+            double tn = 0.0, tf = 1e300;
+            bool miss = false;
+            for (int k = 0; k < 3; k++) {
+                if (d[k] == 0.0) { if (o[k] < p.lo[k] || o[k] > p.hi[k]) miss = true; continue; }
+                const double a = (p.lo[k] - o[k]) / d[k], b = (p.hi[k] - o[k]) / d[k];
+                tn = fmax(tn, fmin(a, b)); tf = fmin(tf, fmax(a, b));
+            }
+            any = !miss && tn <= tf;
+        }
+        p.flags[i] = any ? 1 : 0;
+    }
 }
 
 // Copies `n16` 16-byte words from global to shared memory with the whole CTA (128-bit, coalesced).

@@ -71,6 +71,8 @@ struct ipt_ctx {
     uint32_t W = 0, H = 0, n_slots = 0, n_spheres = 0, n_objects = 0, n_nodes = 0;
     double cam[9] = {0};
     double max_emission = 0, max_color = 0;
+    double scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};   // bounding box of everything a ray can hit
+    bool scene_box_valid = false;
     void *geom32 = nullptr, *geom64 = nullptr, *mat32 = nullptr, *mat64 = nullptr;
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
@@ -97,6 +99,12 @@ struct ipt_ctx {
     void* ipc_mapped = nullptr;
     uint32_t* tile_ids = nullptr;
     size_t tile_cap = 0;
+    uint32_t* mt_list = nullptr;     // active micro-tiles of this rank (see k_active_microtiles)
+    uint32_t* mt_packed = nullptr;
+    uint8_t* mt_flags = nullptr;
+    size_t mt_cap = 0;
+    uint32_t n_mt = 0;
+    uint64_t mt_key = 0, active_pixels = 0;
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[5] = {0, 0, 0, 0, 0};
     void* pinned = nullptr;
@@ -150,7 +158,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
-    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids);
+    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -381,6 +389,38 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
+    {   // bounding box of all primitives (for the exact camera-ray pruning): spheres c +- |r|; rectangles: the four
+        // corners of the accepted parallelogram, solved from n.r = 0, u.r = +-u_hi, v.r = +-v_hi (degenerate ones,
+        // whose normal is NaN, can never be hit and are skipped)
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        bool ok = true;
+        auto grow = [&](const double* q) { for (int k = 0; k < 3; k++) { if (!(q[k] == q[k])) { ok = false; } lo[k] = std::min(lo[k], q[k]); hi[k] = std::max(hi[k], q[k]); } };
+        for (uint32_t i = 0; i < s->n_spheres; i++) {
+            const double* sp = s->sphere_cxyzr + 4 * (size_t)i;
+            const double r = std::fabs(sp[3]);
+            const double a[3] = {sp[0] - r, sp[1] - r, sp[2] - r}, b[3] = {sp[0] + r, sp[1] + r, sp[2] + r};
+            grow(a); grow(b);
+        }
+        for (uint32_t j = 0; j < s->n_rects; j++) {
+            const double *n3 = s->rect_plane + 4 * (size_t)j, *u = s->rect_u + 4 * (size_t)j, *v = s->rect_v + 4 * (size_t)j, *b = s->rect_bounds + 4 * (size_t)j;
+            if (!(n3[0] == n3[0]) || !(u[0] == u[0]) || !(v[0] == v[0])) continue;   // NaN normal: never hit
+            // solve [n; u; v] x = rhs by Cramer's rule
+            const double det = n3[0] * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * v[1] - u[1] * v[0]);
+            if (!(std::fabs(det) > 1e-12)) { ok = false; continue; }
+            for (int su = -1; su <= 1; su += 2)
+                for (int sv = -1; sv <= 1; sv += 2) {
+                    const double r0 = n3[3], r1 = u[3] + su * b[1], r2 = v[3] + sv * b[3];
+                    double q[3];
+                    q[0] = (r0 * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (r1 * v[2] - u[2] * r2) + n3[2] * (r1 * v[1] - u[1] * r2)) / det;
+                    q[1] = (n3[0] * (r1 * v[2] - u[2] * r2) - r0 * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * r2 - r1 * v[0])) / det;
+                    q[2] = (n3[0] * (u[1] * r2 - r1 * v[1]) - n3[1] * (u[0] * r2 - r1 * v[0]) + r0 * (u[0] * v[1] - u[1] * v[0])) / det;
+                    grow(q);
+                }
+        }
+        c->scene_box_valid = ok && lo[0] <= hi[0];
+        for (int k = 0; k < 3; k++) { c->scene_lo[k] = lo[k]; c->scene_hi[k] = hi[k]; }
+        c->mt_key = 0;   // a new scene invalidates the active micro-tile list
+    }
     c->have_scene = true;
     // frame buffers
     const size_t px = (size_t)c->W * c->H;
@@ -480,6 +520,59 @@ static int build_tiles(ipt_ctx* c, uint32_t tile_w, uint32_t tile_h, uint32_t ra
     return IPT_OK;
 }
 
+// The active micro-tile list of this rank (exact camera-ray pruning, see k_active_microtiles).
+static int build_active_microtiles(ipt_ctx* c, uint32_t tile_w, uint32_t tile_h, uint32_t tiles_x, uint64_t key)
+{
+    if (c->mt_key == key && c->mt_list) return IPT_OK;
+    const uint32_t mt_x = tile_w / 8, mt_per_tile = mt_x * (tile_h / 4);
+    const size_t total = c->tile_host.size() * (size_t)mt_per_tile;
+    if (total > c->mt_cap || !c->mt_list) {
+        cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
+        c->mt_list = c->mt_packed = nullptr; c->mt_flags = nullptr; c->mt_cap = 0;
+        const size_t cap = std::max<size_t>(total, 1);
+        CK(cudaMalloc(&c->mt_list, cap * 4)); CK(cudaMalloc(&c->mt_packed, cap * 4)); CK(cudaMalloc(&c->mt_flags, cap));
+        c->mt_cap = cap;
+    }
+    c->n_mt = 0;
+    if (total == 0) { c->mt_key = key; return IPT_OK; }
+    ActiveParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    const double* D = c->cam + 3; const double* X = c->cam + 6;
+    double Z[3] = {D[1] * X[2] - D[2] * X[1], D[2] * X[0] - D[0] * X[2], D[0] * X[1] - D[1] * X[0]};
+    const double zl = 1.0 / std::sqrt(Z[0] * Z[0] + Z[1] * Z[1] + Z[2] * Z[2]);
+    const bool cull = c->scene_box_valid && !std::getenv("IPT_NO_CULL");
+    for (int k = 0; k < 3; k++) {
+        ap.camO[k] = c->cam[k]; ap.camD[k] = D[k]; ap.camX[k] = X[k]; ap.camZ[k] = Z[k] * zl;
+        // grown by the +-1 pixel jitter along X and Z (<= sqrt 2 per axis) plus slack for fp32 ray generation
+        const double ext = std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k]));
+        ap.lo[k] = cull ? c->scene_lo[k] - 2.0 - 1e-5 * ext : -1e300;
+        ap.hi[k] = cull ? c->scene_hi[k] + 2.0 + 1e-5 * ext : 1e300;
+    }
+    ap.fov = (double)0.0009f;
+    ap.W = c->W; ap.H = c->H; ap.tile_ids = c->tile_ids; ap.n_tiles_local = (uint32_t)c->tile_host.size(); ap.tiles_x = tiles_x;
+    ap.tile_w = tile_w; ap.tile_h = tile_h; ap.mt_x = mt_x; ap.mt_per_tile = mt_per_tile;
+    ap.packed = c->mt_packed; ap.flags = c->mt_flags;
+    k_active_microtiles<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, c->stream>>>(ap);
+    std::vector<uint32_t> packed(total);
+    std::vector<uint8_t> flags(total);
+    CK(cudaMemcpyAsync(packed.data(), c->mt_packed, total * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(flags.data(), c->mt_flags, total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> list;
+    list.reserve(total);
+    for (size_t i = 0; i < total; i++) if (flags[i]) list.push_back(packed[i]);   // order kept: tile-major
+    if (!list.empty()) CK(cudaMemcpyAsync(c->mt_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_mt = (uint32_t)list.size();
+    c->active_pixels = 0;
+    for (uint32_t xy : list) {
+        const uint32_t x0 = (xy & 0xFFFFu) * 8, z0 = (xy >> 16) * 4;
+        c->active_pixels += (uint64_t)(std::min(c->W, x0 + 8) - std::min(c->W, x0)) * (std::min(c->H, z0 + 4) - std::min(c->H, z0));
+    }
+    c->mt_key = key;
+    return IPT_OK;
+}
+
 template <typename R>
 static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint32_t tile_h, uint32_t tiles_x, ipt_stats* st)
 {
@@ -503,6 +596,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.keys = philox_expand((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
     kp.tile_ids = c->tile_ids; kp.n_tiles_local = (uint32_t)c->tile_host.size(); kp.tiles_x = tiles_x;
     kp.tile_w = tile_w; kp.tile_h = tile_h; kp.mt_x = tile_w / 8; kp.mt_per_tile = (tile_w / 8) * (tile_h / 4);
+    kp.mt_list = c->mt_list; kp.n_mt = c->n_mt;
     kp.counters = c->counters; kp.traced = c->traced; kp.frame = c->frame;
 
     // fixed-point scale: largest power of two such that spp * (bound on one sample's radiance) fits in 62 bits
@@ -521,7 +615,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.fixed_scale = scale;
 
     // batches
-    const uint64_t total_mt = (uint64_t)kp.n_tiles_local * kp.mt_per_tile;
+    const uint64_t total_mt = c->n_mt;   // only the micro-tiles whose camera rays can reach the scene
     const uint64_t total_groups = total_mt * prm.samples;
     // default batch: 64 Mi camera rays (2 x 6 GB fp32 ray queues) — measured on B200: 4 Mi 27.9, 16 Mi 34.4, 64 Mi 37.3
     // Gbounces/s on the 4K config (fewer launches, shorter tails); HBM capacity is not a constraint at 180 GB
@@ -622,6 +716,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         npx += (uint64_t)(std::min(c->W, x0 + tile_w) - x0) * (std::min(c->H, z0 + tile_h) - z0);
     }
     c->last.samples = npx * prm.samples;
+    c->last.active_pixels = c->active_pixels;
     if (st) *st = c->last;
     return IPT_OK;
 }
@@ -640,6 +735,9 @@ extern "C" int ipt_ctx_render(ipt_ctx* c, const ipt_params* prm, ipt_stats* st)
     CK(cudaSetDevice(c->device));
     uint32_t tiles_x = 0;
     int rc = build_tiles(c, tile_w, tile_h, prm->rank, world, &tiles_x);
+    if (rc) return rc;
+    const uint64_t mt_key = 1 + ((uint64_t)tile_w << 48 | (uint64_t)tile_h << 32 | (uint64_t)prm->rank << 16 | world) + (std::getenv("IPT_NO_CULL") ? (1ull << 62) : 0);
+    rc = build_active_microtiles(c, tile_w, tile_h, tiles_x, mt_key);
     if (rc) return rc;
     return (prm->flags & IPT_FLAG_FP64) ? render_typed<double>(c, *prm, tile_w, tile_h, tiles_x, st)
                                         : render_typed<float>(c, *prm, tile_w, tile_h, tiles_x, st);
@@ -798,6 +896,7 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
         for (int g = 0; g < n_gpus; g++) {
             stats->samples += sts[g].samples; stats->traced_bounces += sts[g].traced_bounces;
             stats->kernel_launches += sts[g].kernel_launches; stats->batches += sts[g].batches;
+            if (g > 0) stats->active_pixels += sts[g].active_pixels;
             stats->render_ms = std::max(stats->render_ms, sts[g].render_ms);
             stats->per_gpu_render_ms[g] = sts[g].render_ms; stats->per_gpu_bounces[g] = sts[g].traced_bounces;
         }

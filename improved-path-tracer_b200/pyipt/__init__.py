@@ -61,7 +61,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("samples", ctypes.c_uint64), ("traced_bounces", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("batches", ctypes.c_uint64), ("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double),
                 ("download_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
-                ("per_gpu_render_ms", ctypes.c_double * 8), ("per_gpu_bounces", ctypes.c_uint64 * 8)]
+                ("per_gpu_render_ms", ctypes.c_double * 8), ("per_gpu_bounces", ctypes.c_uint64 * 8),
+                ("active_pixels", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.startswith("per_gpu") else getattr(self, k)) for k, _ in self._fields_}

@@ -119,6 +119,8 @@ typedef struct ipt_stats {
     uint64_t h2d_bytes, d2h_bytes;
     double per_gpu_render_ms[8]; /* ipt_render() with n_gpus > 1                                      */
     uint64_t per_gpu_bounces[8];
+    uint64_t active_pixels;      /* pixels whose camera rays can reach the scene's bounding box; the others are exactly 0
+                                    for every sample and no ray is generated for them (they still count in `samples`)  */
 } ipt_stats;
 
 /* -- device probe (CudaUtils.cu:8-23) ------------------------------------------------------------------- */

@@ -475,3 +475,31 @@ def test_bright_colours_fall_back_to_floating_point_accumulation(pyipt, oracle, 
     img2, _ = pyipt.render(hs, 4, 12, seed=5, flags=pyipt.FLAG_FP64 | pyipt.FLAG_FLOAT_ACCUM)
     ref2, _ = oracle.render(oracle.Scene.load(path), 4, 12, rng=oracle.RNG_COUNTER, seed=5)
     assert np.mean(np.all(np.abs(img2 - ref2) <= 1e-9 * np.maximum(1.0, np.abs(ref2)), axis=2)) >= 0.999
+
+
+def test_camera_ray_culling_is_exact(pyipt, oracle, ctx, tmp_path, monkeypatch):
+    """Pixels whose un-jittered camera ray misses the scene's grown bounding box are skipped before any ray exists.
+    The frame must be bit-identical with the culling switched off (IPT_NO_CULL=1), on the literal 4K frame of config 4
+    (where it removes ~85 % of the pixels) and on a rotated camera that looks at the room from outside."""
+    from scene_util import room_objects, vec
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=1920, height=1080)
+    ctx.set_scene(hs)
+    st = ctx.render(4, 12, seed=2)
+    a = ctx.download(want64=False)
+    assert 0.05 < st["active_pixels"] / (1920 * 1080) < 0.6 and st["samples"] == 1920 * 1080 * 4
+    monkeypatch.setenv("IPT_NO_CULL", "1")
+    ctx.set_scene(hs)
+    st2 = ctx.render(4, 12, seed=2)
+    b = ctx.download(want64=False)
+    monkeypatch.delenv("IPT_NO_CULL")
+    assert st2["active_pixels"] == 1920 * 1080 and st2["traced_bounces"] > st["traced_bounces"]
+    assert np.array_equal(a, b)
+    # every pixel that was culled is black in the unculled frame too; culled == black only (never the reverse)
+    scene = {"width": 480, "height": 270, "camera": {"position": vec((-2500, -2500, 2600)), "direction": vec((0.6, 0.7, -0.4)), "orientation": vec((0.7, -0.6, 0.1))},
+             "objects": room_objects()}
+    path = write_scene(tmp_path / "outside.json", scene)
+    ref, _ = oracle.render(oracle.Scene.load(path), 2, 6, rng=oracle.RNG_COUNTER, seed=4)
+    hs2 = pyipt.HostScene.load(path)
+    img, st3 = pyipt.render(hs2, 2, 6, seed=4, flags=pyipt.FLAG_FP64)
+    assert 0 < st3["active_pixels"] < 480 * 270
+    assert frac_within(img, ref, 1e-9) >= 0.9995 and ref.any()
