@@ -498,7 +498,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <bool FIRST, int MINB>
+// EARLY = this pass is at depth 0 or 1, where specular / refractive hits split into two rays (AObject.hpp:91-94,
+// :122-125); from depth 2 on there is exactly one continuation, so the second output ray, its ballot and its stores
+// drop out of the code (fewer registers, fewer instructions) for the bulk of the passes.
+template <bool FIRST, bool EARLY, int MINB>
 __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
     extern __shared__ uint4 smem[];
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                     const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                     const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
                     const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
-                    const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, depth, rnd);
+                    const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, EARLY ? depth : 2u, rnd);
                     bool alive = sp.has0;
                     if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                         const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
@@ -578,17 +581,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                     const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
                     o0.meta = mcommon | (r.meta & 0x300u);
                     if (sp.teleport) { o0.o = mk<float>(0.f, 0.f, 0.f); o0.self = NO_OBJECT; o0.meta &= ~META_ONSURF; }
-                    has1 = sp.has1;
-                    o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
-                    o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
+                    if (EARLY) {
+                        has1 = sp.has1;
+                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
+                        o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
+                    }
                 }
             }
         }
         // ---- compaction into the warp's private output block
         const uint32_t m_live = __ballot_sync(0xffffffffu, live);
-        const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = __ballot_sync(0xffffffffu, has1);
+        const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = EARLY ? __ballot_sync(0xffffffffu, has1) : 0u;
         my_traced += __popc(m_live);
-        const uint32_t c0 = __popc(m0b), tot = c0 + __popc(m1b);
+        const uint32_t c0 = __popc(m0b), tot = c0 + (EARLY ? __popc(m1b) : 0u);
         if (tot) {
             // outputs fill the rest of the current block and spill into a freshly reserved one: no holes inside blocks
             const uint32_t room = OUT_BLOCK - blk_used;
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
             }
             const uint32_t j0 = __popc(m0b & lt_mask), j1 = c0 + __popc(m1b & lt_mask);
             if (has0) q_store(p.qout, j0 < room ? blk_base + blk_used + j0 : nb + (j0 - room), o0);
-            if (has1) q_store(p.qout, j1 < room ? blk_base + blk_used + j1 : nb + (j1 - room), o1);
+            if (EARLY && has1) q_store(p.qout, j1 < room ? blk_base + blk_used + j1 : nb + (j1 - room), o1);
             if (tot > room) { blk_base = nb; blk_used = tot - room; }
             else blk_used += tot;
         }

@@ -438,10 +438,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
 
-template <bool FIRST, int MINB>
+template <bool FIRST, bool EARLY, int MINB>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
-    auto kern = k_bounce_fast<FIRST, MINB>;
+    auto kern = k_bounce_fast<FIRST, EARLY, MINB>;
     const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * BLOCK_THREADS * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -661,7 +661,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
-    int grid_first = 0, grid_next = 0, split_grids[2] = {0, 0};
+    int grid_first = 0, grid_next = 0, grid_deep = 0, split_grids[2] = {0, 0};
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
     // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
@@ -683,8 +683,13 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             kp.qin = Queue{c->q[(d + 1) & 1], cap};
             kp.qout = Queue{c->q[d & 1], cap};
             int rc;
-            if (use_fast && fast_minb == 3) rc = d == 0 ? launch_bounce_fast<true, 3>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 3>(c, (const KParams<float>&)kp, &grid_next);
-            else if (use_fast) rc = d == 0 ? launch_bounce_fast<true, 4>(c, (const KParams<float>&)kp, &grid_first) : launch_bounce_fast<false, 4>(c, (const KParams<float>&)kp, &grid_next);
+            if (use_fast) {
+                const KParams<float>& kf = (const KParams<float>&)kp;
+                if (d == 0) rc = launch_bounce_fast<true, true, 3>(c, kf, &grid_first);
+                else if (d == 1) rc = launch_bounce_fast<false, true, 3>(c, kf, &grid_next);
+                else if (fast_minb == 4) rc = launch_bounce_fast<false, false, 4>(c, kf, &grid_deep);
+                else rc = launch_bounce_fast<false, false, 3>(c, kf, &grid_deep);
+            }
             else if (defer && d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true, true>(c, kp, smem, &grid_first);
             else if (defer) rc = bvh ? launch_bounce<R, MODE_BVH, false, true>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false, true>(c, kp, smem, &grid_next);
             else if (d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true>(c, kp, smem, &grid_first);
