@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_scene.hpp"
@@ -253,7 +254,50 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
                 r.p++;
                 if (r.eat(']')) continue;
                 bool oko = true;
-                do { objs.emplace_back(); oko = read_object(r, objs.back()); } while (oko && r.eat(','));
+                if (buf.size() < (8u << 20)) {
+                    do { objs.emplace_back(); oko = read_object(r, objs.back()); } while (oko && r.eat(','));
+                } else {
+                    // large scene (a 1M-object file is ~200 MB): one structural scan finds where every array element
+                    // starts, then the elements are parsed on all host threads into their slots (order preserved)
+                    std::vector<const char*> starts;
+                    const char* q = r.p;
+                    for (;;) {
+                        while (q < r.end && (*q == ' ' || *q == '\n' || *q == '\t' || *q == '\r')) q++;
+                        if (q >= r.end) { oko = false; break; }
+                        starts.push_back(q);
+                        int depth = 0;
+                        bool in_str = false;
+                        for (; q < r.end; q++) {               // skip one JSON value
+                            const char ch = *q;
+                            if (in_str) { if (ch == '\\') q++; else if (ch == '"') in_str = false; continue; }
+                            if (ch == '"') in_str = true;
+                            else if (ch == '{' || ch == '[') depth++;
+                            else if (ch == '}' || ch == ']') { if (depth == 0) break; depth--; }
+                            else if (ch == ',' && depth == 0) break;
+                        }
+                        if (q >= r.end) { oko = false; break; }
+                        if (*q == ',') { q++; continue; }
+                        break;                                 // the array's closing bracket
+                    }
+                    if (oko) {
+                        starts.push_back(q);
+                        const size_t n = starts.size() - 1;
+                        objs.resize(n);
+                        const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+                        std::vector<char> okv(T, 1);
+                        std::vector<std::thread> th;
+                        for (unsigned t = 0; t < T; t++)
+                            th.emplace_back([&, t] {
+                                for (size_t i = n * t / T; i < n * (t + 1) / T; i++) {
+                                    Reader e{starts[i], starts[i + 1]};
+                                    if (!read_object(e, objs[i]) || !e.ok) { okv[t] = 0; return; }
+                                }
+                            });
+                        for (auto& x : th) x.join();
+                        for (char v : okv) oko = oko && v;
+                        r.p = q;
+                    }
+                }
                 if (!oko || !r.eat(']')) { parsed = false; break; }
             } else if (!r.skip()) { parsed = false; break; }
         } while (r.eat(','));
