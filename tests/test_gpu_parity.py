@@ -503,3 +503,11 @@ def test_camera_ray_culling_is_exact(pyipt, oracle, ctx, tmp_path, monkeypatch):
     img, st3 = pyipt.render(hs2, 2, 6, seed=4, flags=pyipt.FLAG_FP64)
     assert 0 < st3["active_pixels"] < 480 * 270
     assert frac_within(img, ref, 1e-9) >= 0.9995 and ref.any()
+
+
+def test_every_kernel_variant_runs_small(pyipt):
+    """scripts/sanitize_smoke.py: tiny renders through every kernel variant (fast, generic fp64, BVH split pipeline,
+    DEFER, Russian roulette, rgb8, trace, 3-rank tiling) — the script written for compute-sanitizer (closed on this pool)."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sanitize_smoke.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sanitize smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
