@@ -32,6 +32,7 @@ template <typename R> struct KParams {
     R fov;                      // (R)0.0009f  (Renderer.cu:27 is a float constant)
     uint32_t W, H, spp, maxDepth;
     uint32_t depth;             // depth of every ray in this pass
+    uint32_t strat_n;           // floor(sqrt(spp)) for IPT_FLAG_STRATIFIED
     uint32_t flags;
     PhiloxKeys keys;
     // tile schedule of this rank: local tile lt -> global tile id tile_ids[lt]
@@ -100,7 +101,15 @@ __device__ __forceinline__ void camera_ray(const KParams<R>& p, uint32_t px, uin
     r.d = normalize(p.camD + p.camX * stepX * p.fov + p.camZ * stepZ * p.fov);                       // :127
     const uint32_t pixel = pz * p.W + px;
     const uint4 rnd = philox4x32_10(pixel, sample, NODE_CAMERA, CTR_TAG, p.keys);
-    const R jx = s24<R>(rnd.x), jz = s24<R>(rnd.y);                                                   // :133-134
+    R jx = s24<R>(rnd.x), jz = s24<R>(rnd.y);                                                         // :133-134
+    if (p.flags & 0x10u) {   // IPT_FLAG_STRATIFIED (extension): jitter of sample i drawn inside stratum i of an n x n grid
+        const uint32_t n = p.strat_n;
+        if (sample < n * n) {
+            const R inv = (R)1 / (R)n;
+            jx = ((R)(sample % n) + (jx + (R)1) * (R)0.5) * inv * (R)2 - (R)1;
+            jz = ((R)(sample / n) + (jz + (R)1) * (R)0.5) * inv * (R)2 - (R)1;
+        }
+    }
     const V3<R> tent = p.camX * jx + p.camZ * jz;                                                     // :135
     const V3<R> origin = p.camO + p.camX * stepX + p.camZ * stepZ + tent;                             // :138
     r.o = origin + p.camD * (R)IPT_VIEWPORT_DISTANCE;                                                 // :139

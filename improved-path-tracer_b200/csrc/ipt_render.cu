@@ -593,6 +593,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.fov = (R)0.0009f;
     kp.W = c->W; kp.H = c->H; kp.spp = prm.samples; kp.maxDepth = prm.max_depth;
     kp.flags = prm.flags;
+    kp.strat_n = (uint32_t)std::floor(std::sqrt((double)prm.samples));
     kp.keys = philox_expand((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
     kp.tile_ids = c->tile_ids; kp.n_tiles_local = (uint32_t)c->tile_host.size(); kp.tiles_x = tiles_x;
     kp.tile_w = tile_w; kp.tile_h = tile_h; kp.mt_x = tile_w / 8; kp.mt_per_tile = (tile_w / 8) * (tile_h / 4);

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libipt_b200.so")
 FLAG_FP64 = 0x1
 FLAG_FLOAT_ACCUM = 0x4
 FLAG_RUSSIAN_ROULETTE = 0x8
+FLAG_STRATIFIED = 0x10
 
 ABI_SYMBOLS = [
     "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_rgb8", "ipt_render_objects",

@@ -97,6 +97,8 @@ typedef struct ipt_scene {
 #define IPT_FLAG_FP64          0x1u  /* compute in fp64 with the reference's literal self-hit tests (parity mode)    */
 #define IPT_FLAG_FLOAT_ACCUM   0x4u  /* accumulate with floating-point atomics instead of deterministic fixed point  */
 #define IPT_FLAG_RUSSIAN_ROULETTE 0x8u /* extension, OFF for parity: unbiased roulette on throughput from depth >= 3 */
+#define IPT_FLAG_STRATIFIED    0x10u /* extension, OFF for parity: the two camera jitters of sample i are stratified on a
+                                        floor(sqrt(spp))^2 grid (unbiased: every stratum is sampled uniformly)           */
 
 typedef struct ipt_params {
     uint32_t samples;        /* per pixel; reference CLI range 4..65535 (InputParser.cpp:14-24), any >= 1 accepted */

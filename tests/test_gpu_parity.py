@@ -254,6 +254,19 @@ def test_russian_roulette_extension_is_unbiased(pyipt, oracle, ctx):
     assert abs(np.mean(a) - np.mean(b)) < 3.5 * sig
 
 
+def test_stratified_jitter_extension_is_unbiased(pyipt, oracle, ctx):
+    """Extension (off by default): stratifying the camera jitter must not move the mean."""
+    hs = pyipt.HostScene.load(oracle.scene_path("spheres"), width=320, height=180)
+    ctx.set_scene(hs)
+    a, b = [], []
+    for seed in range(6):
+        ctx.render(36, 10, seed=seed); a.append(ctx.download().mean())
+        ctx.render(36, 10, seed=seed, flags=pyipt.FLAG_STRATIFIED); b.append(ctx.download().mean())
+    sig = np.sqrt(np.var(a, ddof=1) / 6 + np.var(b, ddof=1) / 6)
+    assert abs(np.mean(a) - np.mean(b)) < 3.5 * sig
+    assert not np.allclose(a, b)
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_full_size_properties(pyipt, oracle, ctx, name):
     """BASELINE configs 1-3 at full size (1280x720, d=10, s=40): fp32 vs fp64 on the same stream agree per pixel on
