@@ -1,11 +1,18 @@
 // ipt_kernels.cuh — the wavefront kernels of the B200 radiance path.
 //
-// One *batch* is a contiguous range of camera samples.  A batch is advanced one bounce per kernel launch
-// ("pass"): pass p reads the ray queue written by pass p-1, finds the nearest hit, accumulates emission, scatters,
-// and appends the continuation rays to the other queue with warp-level compaction (ballot + popc + ONE atomic per
-// warp).  Pass 0 generates the camera rays in registers instead of reading a queue.  Every launch is a persistent
-// grid (a fixed number of CTAs per SM) whose warps pull chunks of rays from a global work counter, so launch
-// geometry never depends on the (device-resident) queue length and the host never synchronises inside a render.
+// One *batch* is a contiguous range of camera samples (default 64 Mi).  A batch is advanced one bounce per kernel launch
+// ("pass"): pass p reads the ray queue written by pass p-1, finds the nearest hit, accumulates emission, scatters, and
+// appends the continuation rays to the other queue, compacted with warp ballot + popc.  Queue lengths live on the
+// device and every launch is a persistent grid (a fixed number of CTAs per SM), so launch geometry never depends on
+// the queue length and the host never synchronises inside a render.  Three pipelines share the device functions of
+// ipt_device.cuh:
+//   k_bounce_fast<FIRST, EARLY>          fp32, scenes without a BVH (the shipped scenes, the 4K config): typed primitive
+//                                        lists in shared memory, static slice schedule with cp.async prefetch,
+//                                        warp-private output blocks (one atomic per 128 outputs);
+//   k_raygen -> k_extend_bvh -> k_bounce<float, MODE_SHADE>
+//                                        fp32, BVH scenes: traversal with lane-level refill split from shading;
+//   k_bounce<R, MODE_BRUTE|MODE_BVH, FIRST, DEFER>
+//                                        the generic fused step: fp64 parity mode, and maxDepth >= 130 (DEFER).
 //
 // Reference being replaced: the single kernel cudaMain<<<22,22>>> (Renderer.cu:254-265) in which each of 484 threads
 // walks ~1900 pixels x spp x bounces serially with recursion (firstLayer/secondLayer/deepLayers, :149-225).
@@ -17,7 +24,7 @@ namespace ipt {
 enum { MODE_BRUTE = 0, MODE_BVH = 1, MODE_SHADE = 2 };   // MODE_SHADE: hits were found by k_extend_bvh, k_bounce only shades
 
 static constexpr int BLOCK_THREADS = 256;
-static constexpr int GRAB = 128;          // rays a warp claims per atomic on the work counter (4 iterations of 32)
+static constexpr int GRAB = 128;          // generic kernels: rays a warp claims per atomic on the work counter (4 iterations of 32)
 static constexpr int BVH_TOP_NODES = 512; // top of the BVH staged in shared memory (32 KB)
 
 // counters[] layout (uint32): [CNT + p] rays queued for pass p, [WORK + p] work-claim counter of pass p
@@ -146,13 +153,11 @@ __global__ void __launch_bounds__(256) k_active_microtiles(const __grid_constant
             const double corr = (p.W % 2 == 0) ? 0.5 : 0.0;
             const double stepX = (px < p.W / 2) ? (double)(p.W / 2 - px) - corr : ((double)p.W / 2 - px - 1.0) + ((corr == 0.0) ? 1.0 : corr);
             const double stepZ = (pz < p.H / 2) ? (double)(p.H / 2 - pz) - corr : ((double)p.H / 2 - pz - 1.0) + ((corr == 0.0) ? 1.0 : corr);
-            double o[3], d[3], len = 0;
+            double o[3], d[3];   // the slab test does not need a unit direction
             for (int k = 0; k < 3; k++) {
                 d[k] = p.camD[k] + p.camX[k] * stepX * p.fov + p.camZ[k] * stepZ * p.fov;
                 o[k] = p.camO[k] + p.camX[k] * stepX + p.camZ[k] * stepZ + p.camD[k] * IPT_VIEWPORT_DISTANCE;
-                len += d[k] * d[k];
             }
-            (void)len;   // the slab test does not need a unit direction
             double tn = 0.0, tf = 1e300;
             bool miss = false;
             for (int k = 0; k < 3; k++) {
