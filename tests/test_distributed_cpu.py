@@ -39,3 +39,23 @@ def test_reference_arm_under_torchrun_runs_on_rank0_only(oracle):
     assert j["impl"] == "reference" and j["value"] > 0 and j["unit"] == "Msamples/s" and j["metric"] == "Msamples/s"
     assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ (produced on a B200 by `python bench.py` and `--impl reference`) carry
+    every key the measurement contract names."""
+    ours = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_default_4k_final.jsonl")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in ours, k
+    assert ours["metric"] == "Msamples/s" and ours["unit"] == "Msamples/s" and ours["dtype"] == "f32" and ours["vs_baseline"] is None
+    assert "workload" in ours["config"] and "model" not in ours["config"]
+    assert set(ours["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and ours["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(ours["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(ours["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and ours["cpu_baseline"]["kind"] == "reference"
+    assert set(ours["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert ours["gpu_launches"] > 0 and ours["value"] > 1000
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.jsonl")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["config"]["workload"] == ours["config"]["workload"] and ref["higher_is_better"] == ours["higher_is_better"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
