@@ -322,6 +322,16 @@ __device__ __forceinline__ Hit<R> nearest_bvh(const SceneView<R>& sc, const floa
     return best;
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): a 64-byte BVH node is two of these instead of four 128-bit
+// loads, a 32-byte leaf record one instead of two — half the L1 wavefronts of the divergent traversal loads.
+// `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 // fp32 BVH traversal (BASELINE config 5).  Differences from the generic nearest_bvh<R>:
 //  * while-while: every lane first descends inner nodes until it holds a leaf, then the warp tests leaf primitives
 //    together — inner-node and leaf code no longer serialise against each other inside one loop iteration;
@@ -334,7 +344,8 @@ __device__ __forceinline__ Hit<R> nearest_bvh(const SceneView<R>& sc, const floa
 __device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t slot, const V3<float>& o, const V3<float>& d,
                                            const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best)
 {
-    const float4 a = __ldg(sc.bslot + 2 * (size_t)slot), b = __ldg(sc.bslot + 2 * (size_t)slot + 1);
+    float4 a, b;
+    ldg256(sc.bslot + 2 * (size_t)slot, a, b);
     const uint32_t kind = __float_as_uint(b.x), obj = __float_as_uint(b.y);
     float t;
     bool hit;
@@ -385,7 +396,7 @@ __device__ __forceinline__ Hit<float> nearest_bvh_f32(const SceneView<float>& sc
         while (node >= 0) {
             float4 a, b, c, e;
             if ((uint32_t)node < n_top) { const float4* p = top + 4 * node; a = p[0]; b = p[1]; c = p[2]; e = p[3]; }
-            else { const float4* p = sc.nodes + 4 * (size_t)node; a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); e = __ldg(p + 3); }
+            else { const float4* p = sc.nodes + 4 * (size_t)node; ldg256(p, a, b); ldg256(p + 2, c, e); }
             float t0x = fmaf(a.x, bi.x, -oi.x), t1x = fmaf(a.w, bi.x, -oi.x);
             float t0y = fmaf(a.y, bi.y, -oi.y), t1y = fmaf(b.x, bi.y, -oi.y);
             float t0z = fmaf(a.z, bi.z, -oi.z), t1z = fmaf(b.y, bi.z, -oi.z);

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_const
             if (has && !done && node >= 0) {
                 float4 a, b, c, e;
                 if ((uint32_t)node < n_top) { const float4* q = top + 4 * node; a = q[0]; b = q[1]; c = q[2]; e = q[3]; }
-                else { const float4* q = sc.nodes + 4 * (size_t)node; a = __ldg(q); b = __ldg(q + 1); c = __ldg(q + 2); e = __ldg(q + 3); }
+                else { const float4* q = sc.nodes + 4 * (size_t)node; ldg256(q, a, b); ldg256(q + 2, c, e); }
                 float t0x = fmaf(a.x, bi.x, -oi.x), t1x = fmaf(a.w, bi.x, -oi.x);
                 float t0y = fmaf(a.y, bi.y, -oi.y), t1y = fmaf(b.x, bi.y, -oi.y);
                 float t0z = fmaf(a.z, bi.z, -oi.z), t1z = fmaf(b.y, bi.z, -oi.z);
