@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_raygen(const __grid_constant_
 // scene, profiles/r01_ncu_bvh_v1.txt); here a lane that has finished its ray writes the hit and, as soon as
 // `refill_min` lanes of the warp are idle, the idle lanes claim new rays with one warp-aggregated atomic.
 
-__global__ void __launch_bounds__(BLOCK_THREADS) k_extend_bvh(const __grid_constant__ KParams<float> p)
+__global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_constant__ KParams<float> p)
 {
     extern __shared__ uint4 smem[];
     const SceneView<float> sc = p.sc;
