@@ -524,3 +524,22 @@ def test_every_kernel_variant_runs_small(pyipt):
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sanitize_smoke.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sanitize smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_skewed_camera_odd_frame_and_many_samples(pyipt, oracle, tmp_path):
+    """Camera orientation NOT perpendicular to its direction (the reference never re-orthogonalises, SceneData.cpp:143-145
+    / RenderController.cu:39), odd width and height (Renderer.cu:118-125 uses the width's parity for both axes), and a
+    sample count beyond 8 bits (the sample index travels in 16 bits of the ray record)."""
+    j = json.load(open(oracle.scene_path("mirrors")))
+    j["width"], j["height"] = 37, 25
+    j["camera"]["orientation"] = {"xx": -3.0, "yy": 0.6, "zz": 0.4}
+    j["camera"]["direction"] = {"xx": 0.1, "yy": 2.0, "zz": -0.1}
+    path = tmp_path / "skew.json"
+    path.write_text(json.dumps(j))
+    ref, cnt = oracle.render(oracle.Scene.load(str(path)), 700, 6, rng=oracle.RNG_COUNTER, seed=12)
+    hs = pyipt.HostScene.load(str(path))
+    img, st = pyipt.render(hs, 700, 6, seed=12, flags=pyipt.FLAG_FP64)
+    assert frac_within(img, ref, 1e-9) >= 0.999
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-3 * cnt["casts_needed"]
+    img32, _ = pyipt.render(hs, 700, 6, seed=12)
+    assert frac_within(img32, ref, 1e-3) >= 0.98
