@@ -620,7 +620,9 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     const uint64_t total_groups = total_mt * prm.samples;
     // default batch: 64 Mi camera rays (2 x 6 GB fp32 ray queues) — measured on B200: 4 Mi 27.9, 16 Mi 34.4, 64 Mi 37.3
     // Gbounces/s on the 4K config (fewer launches, shorter tails); HBM capacity is not a constraint at 180 GB
-    uint64_t B = prm.batch_samples ? prm.batch_samples : (1u << 26);
+    // ... and allocating 2 x 6 GB costs ~110 ms, which a one-shot render of a few hundred M samples would notice: 16 / 32 Mi there
+    const uint64_t total_samples = total_groups * 32;
+    uint64_t B = prm.batch_samples ? prm.batch_samples : (total_samples >= (2ull << 30) ? (1u << 26) : total_samples >= (512ull << 20) ? (1u << 25) : (1u << 24));
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
     // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
