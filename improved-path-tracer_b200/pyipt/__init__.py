@@ -153,7 +153,7 @@ class HostScene:
         self.handle = handle
 
     @staticmethod
-    def load(path, width=None, height=None, leaf_size=4, brute_max=64):
+    def load(path, width=None, height=None, leaf_size=4, brute_max=192):
         msg = ctypes.create_string_buffer(256)
         h = lib().ipt_host_load_scene(os.fsencode(path), msg, 256)
         if not h:
@@ -165,7 +165,7 @@ class HostScene:
         return s
 
     @staticmethod
-    def from_objects(objects_bytes, n, width, height, camera9, leaf_size=4, brute_max=64):
+    def from_objects(objects_bytes, n, width, height, camera9, leaf_size=4, brute_max=192):
         cam = (ctypes.c_double * 9)(*camera9)
         buf = ctypes.create_string_buffer(bytes(objects_bytes), len(objects_bytes))
         h = lib().ipt_host_from_objects(buf, n, width, height, cam)
@@ -175,7 +175,7 @@ class HostScene:
         s.build_bvh(leaf_size, brute_max)
         return s
 
-    def build_bvh(self, leaf_size=4, brute_max=64):
+    def build_bvh(self, leaf_size=4, brute_max=192):
         n = lib().ipt_host_build_bvh(self.handle, leaf_size, brute_max)
         if n < 0:
             raise IptError("ipt_host_build_bvh failed")
