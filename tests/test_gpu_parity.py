@@ -485,6 +485,8 @@ def test_bright_colours_fall_back_to_floating_point_accumulation(pyipt, oracle, 
     rel = np.abs(img - ref) / np.maximum(1.0, np.abs(ref))
     # sums of terms up to 1e9 of both signs: forward accumulation vs the reference's back-to-front fold differ by rounding
     assert np.mean(np.all(rel <= 1e-9, axis=2)) >= 0.999, (np.sort(rel.ravel())[-20:], np.mean(np.all(rel <= 1e-9, axis=2)))
+    img32, _ = pyipt.render(hs, 4, 40, seed=5)   # fp32 fast kernel with the same fallback
+    assert np.isfinite(img32).all() and frac_within(img32, ref, 1e-3, floor=1.0) >= 0.9
     img2, _ = pyipt.render(hs, 4, 12, seed=5, flags=pyipt.FLAG_FP64 | pyipt.FLAG_FLOAT_ACCUM)
     ref2, _ = oracle.render(oracle.Scene.load(path), 4, 12, rng=oracle.RNG_COUNTER, seed=5)
     assert np.mean(np.all(np.abs(img2 - ref2) <= 1e-9 * np.maximum(1.0, np.abs(ref2)), axis=2)) >= 0.999
