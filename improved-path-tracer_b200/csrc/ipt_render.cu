@@ -751,6 +751,19 @@ extern "C" int ipt_ctx_render(ipt_ctx* c, const ipt_params* prm, ipt_stats* st)
                                         : render_typed<float>(c, *prm, tile_w, tile_h, tiles_x, st);
 }
 
+extern "C" void* ipt_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { set_err(std::string("ipt_alloc_pinned: ") + cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void ipt_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int ipt_ctx_download(ipt_ctx* c, float* out32, double* out64)
 {
     if (!c || !c->have_scene) { set_err("ipt_ctx_download: no frame"); return IPT_ERR_BAD_ARGUMENT; }

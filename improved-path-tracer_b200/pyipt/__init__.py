@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_rgb8", "ipt_render_objects",
     "ipt_ctx_create", "ipt_ctx_destroy", "ipt_ctx_set_scene", "ipt_ctx_render", "ipt_ctx_download", "ipt_ctx_download_rgb8",
     "ipt_ctx_export_frame", "ipt_ctx_set_gather_target_ipc", "ipt_ctx_set_gather_target", "ipt_tile_owner",
-    "ipt_ctx_trace",
+    "ipt_ctx_trace", "ipt_alloc_pinned", "ipt_free_pinned",
 ]
 HOST_SYMBOLS = [
     "ipt_host_load_scene", "ipt_host_from_objects", "ipt_host_free_scene", "ipt_host_scene_view", "ipt_host_set_size",
@@ -104,6 +104,10 @@ def lib():
     L.ipt_ctx_destroy.restype = None
     L.ipt_ctx_set_scene.argtypes = [vp, ctypes.POINTER(Scene)]
     L.ipt_ctx_render.argtypes = [vp, ctypes.POINTER(Params), ctypes.POINTER(Stats)]
+    L.ipt_alloc_pinned.restype = vp
+    L.ipt_alloc_pinned.argtypes = [ctypes.c_size_t]
+    L.ipt_free_pinned.restype = None
+    L.ipt_free_pinned.argtypes = [vp]
     L.ipt_ctx_download.argtypes = [vp, vp, vp]
     L.ipt_ctx_download_rgb8.argtypes = [vp, vp]
     L.ipt_ctx_export_frame.argtypes = [vp, vp]
@@ -249,6 +253,30 @@ def render_rgb8(scene, samples, depth, n_gpus=1, seed=123456, flags=0):
     st = Stats()
     _check(lib().ipt_render_rgb8(scene.view, ctypes.byref(p), n_gpus, out.ctypes.data, ctypes.byref(st)), "ipt_render_rgb8")
     return out, st.as_dict()
+
+
+class PinnedArray:
+    """numpy view of a page-locked host buffer from ipt_alloc_pinned (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().ipt_alloc_pinned(n)
+        if not self.ptr:
+            raise IptError("ipt_alloc_pinned: " + lib().ipt_last_error().decode(errors="replace"))
+        buf = (ctypes.c_char * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().ipt_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:

@@ -22,6 +22,7 @@
  */
 #ifndef IPT_ABI_H
 #define IPT_ABI_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -130,6 +131,13 @@ int ipt_abi_version(void);
 int ipt_device_count(void);
 const char* ipt_device_name(int device);
 const char* ipt_last_error(void);
+
+/* -- page-locked host buffers ---------------------------------------------------------------------------
+ * Optional: every entry point accepts any host pointer.  A frame buffer obtained here is copied at full PCIe
+ * rate (the reference returns a pageable std::vector, RenderController.cu:62-68; at 4K the float frame is
+ * 99.5 MB).  NULL on failure, text in ipt_last_error(). */
+void* ipt_alloc_pinned(size_t bytes);
+void ipt_free_pinned(void* p);
 
 /* -- one-shot renders -------------------------------------------------------------------------------------
  * n_gpus = 1, 2, 4 or 8 devices of this process: tiles are interleaved statically over the devices and the

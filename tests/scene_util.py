@@ -45,6 +45,20 @@ def synthetic_scene(n_small, seed, width=160, height=90, general_rects=True):
             "objects": objs}
 
 
+def scale_scene(scene, k):
+    """Every length of the scene times k (positions, radii, edge vectors, camera position, frame size): SURVEY.md §8d's
+    evenly loaded 4K variant of spheres.json is k = 3."""
+    out = json.loads(json.dumps(scene))
+    out["width"], out["height"] = int(out["width"] * k), int(out["height"] * k)
+    for o in [out["camera"]] + out["objects"]:
+        for key in ("position", "north", "east"):
+            if key in o:
+                o[key] = {a: float(k) * b for a, b in o[key].items()}
+        if "radius" in o:
+            o["radius"] = float(k) * o["radius"]
+    return out
+
+
 def write_scene(path, scene):
     with open(path, "w") as f:
         json.dump(scene, f)

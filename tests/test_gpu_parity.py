@@ -306,6 +306,39 @@ def test_4k_frame_properties(pyipt, oracle, ctx):
     assert np.array_equal(merged, full)
 
 
+def test_x3_room_fills_the_4k_frame(pyipt, oracle, ctx, tmp_path):
+    """The evenly loaded variant of config 4 (every length of spheres.json x3): coordinates up to ~3900
+    in fp32.  Reduced frame against the oracle pixel by pixel; the full 4K frame against the channel means the
+    reference's own routine gave for it (0.4625, 0.3962, 0.4631 at 4 spp), into a pinned buffer."""
+    import json
+    import scene_util
+    x3 = scene_util.scale_scene(json.load(open(oracle.scene_path("spheres"))), 3)
+    path = scene_util.write_scene(tmp_path / "spheres_x3.json", x3)
+    W, H, spp, depth, seed = 960, 540, 2, 12, 11
+    ref, cnt = oracle.render(oracle.Scene.load(path, W, H), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(path, width=W, height=H)
+    img64, _ = pyipt.render(hs, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
+    assert frac_within(img64, ref, 1e-9) >= 0.9999
+    img32, st = pyipt.render(hs, spp, depth, seed=seed)
+    assert frac_within(img32, ref, 1e-3) >= 0.99
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 2e-3 * cnt["casts_needed"]
+
+    hs = pyipt.HostScene.load(path)
+    assert (hs.width, hs.height) == (3840, 2160)
+    ctx.set_scene(hs)
+    st = ctx.render(4, 32, seed=5)
+    assert st["active_pixels"] == 3840 * 2160
+    pin = pyipt.PinnedArray((2160, 3840, 3), np.float32)
+    frame = ctx.download(out=pin.array)
+    means = frame.mean(axis=(0, 1), dtype=np.float64)
+    pageable = ctx.download(want64=False)
+    assert np.array_equal(pageable, frame)
+    del frame
+    pin.close()
+    assert np.all(np.abs(means - np.array([0.4625, 0.3962, 0.4631])) <= 0.01 * means), means
+    assert 25 < st["traced_bounces"] / st["samples"] < 40      # 36.3 casts per sample upstream, some pruned here
+
+
 def test_tracer_program_surface(pyipt, oracle, tmp_path):
     """`tracer -d=5 -s=4 scene.json`: stdout lines in the reference's order, <scene>D<d>S<s>.png = toRgb(frame),
     benchmark.txt record `<id>;HH:MM:SS.ms;` without newline."""
