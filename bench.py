@@ -48,8 +48,16 @@ def scene_file(name):
         import subprocess
         p = "/tmp/ipt_synthetic_1000000.json"
         if not os.path.isfile(p):
-            subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), p + ".tmp", "1000000"], check=True)
-            os.replace(p + ".tmp", p)
+            if int(os.environ.get("LOCAL_RANK", "0")) == 0:        # one writer per box, atomic rename; the others wait
+                tmp = f"{p}.{os.getpid()}.tmp"
+                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), tmp, "1000000"], check=True)
+                os.replace(tmp, p)
+            else:
+                t_end = time.time() + 600
+                while not os.path.isfile(p):
+                    if time.time() > t_end:
+                        raise SystemExit(f"{p}: rank 0 did not write the synthetic scene")
+                    time.sleep(0.2)
         return p
     if name.endswith("_x3"):
         src = json.load(open(scene_file(name[:-3])))

@@ -588,28 +588,66 @@ __device__ __forceinline__ void fast_axis_list(const float4* __restrict__ axs, u
     }
 }
 
+// The same for a list whose position and (even) length are compile-time constants: straight-line code, record loads
+// at constant offsets, hit codes as immediates.
+template <int K, int FIRST_REC, int N>
+__device__ __forceinline__ void fast_axis_fixed(const float4* __restrict__ axs, const V3<float>& o, const V3<float>& d, float inv_dk, FastHit& best)
+{
+    constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
+    const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        const float4 a = axs[2 * (FIRST_REC + u)];
+        const float hj = axs[2 * (FIRST_REC + u) + 1].x;
+        const float t = (a.x - ok) * inv_dk;
+        const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
+        const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
+        best.t = hit ? t : best.t;
+        best.code = hit ? (((uint32_t)(K + 1) << 28) | (uint32_t)(FIRST_REC + u)) : best.code;
+    }
+}
+
 // Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.  `self` is the hit CODE of
 // the surface the ray starts on (the fast kernel's queues are private to it), NO_OBJECT for camera rays.
+__device__ __forceinline__ void fast_sphere(const float4 sp, uint32_t s, uint32_t self_sphere, const V3<float>& o, const V3<float>& d, FastHit& best)
+{
+    const bool selfS = s == self_sphere;                         // start point lies ON this sphere: exact second root -2b
+    const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);
+    const float b = dot(op, d);
+    const float delta = fmaf(b, b, fmaf(sp.w, sp.w, -dot(op, op)));           // b*b - op.op + r*r   (Sphere.cu:31)
+    const float sq = sqrt_fast(fmaxf(delta, 0.f));
+    const float t1 = -b - sq, t2 = sq - b;
+    float t = t1 > (float)IPT_MARGIN ? t1 : t2;
+    t = selfS ? -2.f * b : t;
+    const bool hit = (delta >= 0.f || selfS) && t > (float)IPT_MARGIN && t < best.t;
+    best.t = hit ? t : best.t;
+    best.code = hit ? s : best.code;
+}
+
+// SHAPE: 0 = list lengths at run time (loops); k = 1..5 = "box room": exactly two rectangles per axis list (a closed
+// axis-aligned box, padded records included), no general rectangles and k-1 spheres.  Those lengths being compile-time
+// constants, the whole scan is straight-line code (spheres.json and every Cornell-box-like scene).
+__host__ __device__ inline int fast_shape(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen)
+{
+    return (nx == 2 && ny == 2 && nz == 2 && n_gen == 0 && n_sph <= 4) ? (int)n_sph + 1 : 0;
+}
+
+template <int SHAPE>
 __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<float>& o, const V3<float>& d, uint32_t self, bool onSurf)
 {
     FastHit best;
     best.t = (float)IPT_INF; best.code = NO_OBJECT;
     const uint32_t self_sphere = onSurf ? self : NO_OBJECT;      // sphere codes are plain list indices (kind 0)
-#pragma unroll 2
-    for (uint32_t s = 0; s < f.n_sph; s++) {
-        const float4 sp = f.sph[s];
-        const bool selfS = s == self_sphere;                     // start point lies ON this sphere: exact second root -2b
-        const V3<float> op = mk<float>(o.x - sp.x, o.y - sp.y, o.z - sp.z);
-        const float b = dot(op, d);
-        const float delta = fmaf(b, b, fmaf(sp.w, sp.w, -dot(op, op)));       // b*b - op.op + r*r   (Sphere.cu:31)
-        const float sq = sqrt_fast(fmaxf(delta, 0.f));
-        const float t1 = -b - sq, t2 = sq - b;
-        float t = t1 > (float)IPT_MARGIN ? t1 : t2;
-        t = selfS ? -2.f * b : t;
-        const bool hit = (delta >= 0.f || selfS) && t > (float)IPT_MARGIN && t < best.t;
-        best.t = hit ? t : best.t;
-        best.code = hit ? s : best.code;
+    if (SHAPE > 0) {
+#pragma unroll
+        for (int s = 0; s < SHAPE - 1; s++) fast_sphere(f.sph[s], (uint32_t)s, self_sphere, o, d, best);
+        fast_axis_fixed<0, 0, 2>(f.axs, o, d, rcp_fast(d.x), best);
+        fast_axis_fixed<1, 2, 2>(f.axs, o, d, rcp_fast(d.y), best);
+        fast_axis_fixed<2, 4, 2>(f.axs, o, d, rcp_fast(d.z), best);
+        return best;
     }
+#pragma unroll 2
+    for (uint32_t s = 0; s < f.n_sph; s++) fast_sphere(f.sph[s], s, self_sphere, o, d, best);
     fast_axis_list<0>(f.axs, f.ax0_x, f.n_x, o, d, rcp_fast(d.x), best);
     fast_axis_list<1>(f.axs, f.ax0_y, f.n_y, o, d, rcp_fast(d.y), best);
     fast_axis_list<2>(f.axs, f.ax0_z, f.n_z, o, d, rcp_fast(d.z), best);

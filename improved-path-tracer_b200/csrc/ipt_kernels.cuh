@@ -62,6 +62,10 @@ template <typename R> struct KParams {
     uint2* hits;                // split pipeline: {t bits, slot} per ray of the current pass (k_extend_bvh -> k_bounce<MODE_SHADE>)
     const uint4* fast_blob;     // fp32 brute-force layout (FastScene), null otherwise
     uint32_t fast_words;
+    uint32_t fast_k;            // k_bounce_fast, passes from depth 2 on: bounces a ray makes in registers per pass;
+                                // 0 = chosen on the device from the measured survival rate (fast_schedule)
+    uint32_t pass, n_passes;    // k_bounce_fast: index of this launch in its batch (0 and 1 are depth 0 and 1), launches per batch
+    uint32_t* fast_hint;        // k_bounce_fast: bounces per pass the previous batch settled on (device word, 0 = none yet)
     FastHeader fast_hd;
 };
 
@@ -512,12 +516,55 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Passes from depth 2 on advance every ray by nk bounces in registers before compacting (see the loop in the kernel).
+// Their schedule lives on the device, so the host never waits for a queue length: pass `p.pass` starts at the depth
+// the previous pass left in counters[WORK + pass] (pass 2 starts at depth 2) and leaves depth + nk for the next one.
+// nk comes from the survival rate the previous pass measured (queue length in / out): idle lanes cost about as much
+// as they save once nk * (fraction lost per bounce) exceeds ~0.2; a closed room loses < 1 % per bounce and gets the
+// cap of 8.  Pass 2 has no measurement of its own batch yet and starts from what the previous batch settled on
+// (*fast_hint; written only by passes > 2, read only by pass 2, so never inside one grid).  The host launches a fixed
+// number of passes per batch; the remaining depth is spread over the launches that are left when that is more than
+// the survival rate asks for (the last launch always finishes the paths), and surplus launches return at once.
+// Every thread of the grid computes the same values from the same finished counters.  Returns true when past maxDepth.
+static constexpr uint32_t FAST_K_MAX = 8;
+static constexpr uint32_t FAST_DEEP_LAUNCHES = 12;
+template <typename P>
+__device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& depth, uint32_t& nk)
+{
+    depth = p.pass == 2 ? 2u : p.counters[WORK + p.pass];
+    const bool publish = blockIdx.x == 0 && threadIdx.x == 0;
+    if (depth >= p.maxDepth) {
+        if (publish && p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = depth;
+        return true;
+    }
+    if (p.fast_k) nk = p.fast_k;
+    else if (p.pass == 2) { const uint32_t h = *p.fast_hint; nk = h ? h : 1u; }
+    else {
+        const uint32_t nk_prev = p.counters[WORK_EXTEND + p.pass - 1];
+        const uint32_t n_prev = p.counters[CNT + depth - nk_prev], n_cur = p.counters[CNT + depth];
+        const unsigned long long lost = n_prev > n_cur ? n_prev - n_cur : 1u;
+        const unsigned long long k = 22ull * n_prev * nk_prev / (100ull * lost);
+        nk = (uint32_t)(k < 1ull ? 1ull : (k > FAST_K_MAX ? FAST_K_MAX : k));
+        if (publish && n_prev > (1u << 20)) *p.fast_hint = nk;   // queues this long make the padding of block tails negligible
+    }
+    const uint32_t remaining = p.maxDepth - depth, launches_left = p.n_passes - p.pass;
+    nk = max(nk, (remaining + launches_left - 1) / launches_left);
+    nk = min(nk, remaining);
+    if (publish) {
+        if (p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = depth + nk;
+        p.counters[WORK_EXTEND + p.pass] = nk;
+    }
+    return false;
+}
+
 // EARLY = this pass is at depth 0 or 1, where specular / refractive hits split into two rays (AObject.hpp:91-94,
 // :122-125); from depth 2 on there is exactly one continuation, so the second output ray, its ballot and its stores
 // drop out of the code (fewer registers, fewer instructions) for the bulk of the passes.
-template <bool FIRST, bool EARLY, int MINB>
+template <bool FIRST, bool EARLY, int MINB, int SHAPE = 0>
 __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
+    uint32_t depth = p.depth, nk = 1;                   // nk: bounces a ray makes in this pass
+    if (!EARLY && fast_schedule(p, depth, nk)) return;  // past maxDepth: the batch finished in fewer passes than launched
     extern __shared__ uint4 smem[];
     uint4* stagebuf = smem + p.fast_words;              // [2 buffers][3 planes][BLOCK_THREADS]
     stage(smem, p.fast_blob, p.fast_words);
@@ -526,13 +573,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.depth];
-    const uint32_t depth = p.depth;
-    uint32_t* out_count = p.counters + CNT + depth + 1;
-    const bool may_continue = depth + 1 < p.maxDepth;
+    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + depth];
+    uint32_t* out_count = p.counters + CNT + depth + nk;
     const uint32_t warp_global = blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5);
     const uint32_t stride = gridDim.x * BLOCK_THREADS;   // rays per sweep of the whole grid
-    unsigned long long my_traced = 0;
+    uint32_t my_traced = 0;                              // per warp and pass: far below 2^32
     uint32_t blk_base = 0, blk_used = OUT_BLOCK;         // no block reserved yet
 
     uint32_t i = warp_global * 32u + lane;
@@ -552,7 +597,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
         } else {
             cp_async_wait_all();
             const uint32_t nxt = i + stride;
-            if (nxt < n_in)
+            if (nxt < n_in && nxt > i)
                 for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + ((buf ^ 1) * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + nxt);
             cp_async_commit();
             if (live) {
@@ -566,47 +611,58 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
             }
             buf ^= 1;
         }
-        bool has0 = false, has1 = false;
-        Ray<float> o0, o1;
-        if (live) {
-            const FastHit h = nearest_fast(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
-            if (h.code != NO_OBJECT) {
-                const uint32_t hobj = fast_hit_object(sc, h.code);
-                const uint32_t obj = hobj & ~RECT_BIT;
-                const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
-                if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
-                V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
-                const bool go = may_continue && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
-                if (go) {
-                    const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
-                    const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
-                    const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
-                    const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, EARLY ? depth : 2u, rnd);
-                    bool alive = sp.has0;
-                    if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
-                        const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
-                        const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
-                        if (u23<float>(rr.x) >= q) alive = false;
-                        else nthr = nthr * (1.f / q);
-                    }
-                    const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
-                    has0 = alive;
-                    o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.code;
-                    const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (depth + 1);
-                    o0.meta = mcommon | (r.meta & 0x300u);
-                    if (sp.teleport) { o0.o = mk<float>(0.f, 0.f, 0.f); o0.self = NO_OBJECT; o0.meta &= ~META_ONSURF; }
-                    if (EARLY) {
-                        has1 = sp.has1;
-                        o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
-                        o1.meta = mcommon | (depth == 0 ? (0x200u | META_PROBE) : 0x100u);
+        // One pass advances a ray by nk bounces in registers (nk = 1 at depth 0 and 1, where paths split).  A closed
+        // room loses well under 1 % of its rays per bounce, so compacting and round-tripping the queues through HBM
+        // only every nk-th bounce costs a few idle lanes and saves (nk-1)/nk of the queue traffic.  The RNG is keyed
+        // by (pixel, sample, lane, depth): the frame does not depend on nk.
+        bool has0 = live, has1 = false;
+        Ray<float> o0 = r, o1;
+        for (uint32_t k = 0; k < nk; k++) {
+            const uint32_t dk = depth + k;
+            const bool in = has0;
+            const uint32_t m_in = __ballot_sync(0xffffffffu, in);
+            if (!m_in) break;                              // every ray of this slice has ended
+            my_traced += __popc(m_in);
+            has0 = false;
+            if (in) {
+                const Ray<float> r = o0;
+                const FastHit h = nearest_fast<SHAPE>(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
+                if (h.code != NO_OBJECT) {
+                    const uint32_t hobj = fast_hit_object(sc, h.code);
+                    const uint32_t obj = hobj & ~RECT_BIT;
+                    const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
+                    if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
+                    V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
+                    const bool go = dk + 1 < p.maxDepth && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
+                    if (go) {
+                        const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
+                        const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
+                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
+                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, EARLY ? dk : 2u, rnd);
+                        bool alive = sp.has0;
+                        if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
+                            const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
+                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG + 1u, p.keys);
+                            if (u23<float>(rr.x) >= q) alive = false;
+                            else nthr = nthr * (1.f / q);
+                        }
+                        const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
+                        has0 = alive;
+                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.self = h.code;
+                        const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (dk + 1);
+                        o0.meta = mcommon | (r.meta & 0x300u);
+                        if (sp.teleport) { o0.o = mk<float>(0.f, 0.f, 0.f); o0.self = NO_OBJECT; o0.meta &= ~META_ONSURF; }
+                        if (EARLY) {
+                            has1 = sp.has1;
+                            o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
+                            o1.meta = mcommon | (dk == 0 ? (0x200u | META_PROBE) : 0x100u);
+                        }
                     }
                 }
             }
         }
         // ---- compaction into the warp's private output block
-        const uint32_t m_live = __ballot_sync(0xffffffffu, live);
         const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = EARLY ? __ballot_sync(0xffffffffu, has1) : 0u;
-        my_traced += __popc(m_live);
         const uint32_t c0 = __popc(m0b), tot = c0 + (EARLY ? __popc(m1b) : 0u);
         if (tot) {
             // outputs fill the rest of the current block and spill into a freshly reserved one: no holes inside blocks
@@ -625,7 +681,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
     }
     // the unused tail of the last block: dead records (skipped by the next pass)
     for (uint32_t s = blk_used + lane; s < OUT_BLOCK; s += 32) p.qout.base[2u * p.qout.capacity + blk_base + s] = make_uint4(0u, 0u, META_DEAD, NO_OBJECT);
-    if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
+    if (lane == 0 && my_traced) atomicAdd(p.traced, (unsigned long long)my_traced);
+}
+
+// Diagnostic (IPT_PASS_TIMES): SM clock right now, from ~8 us of %clock64 against %globaltimer on one warp.
+__global__ void k_clock_probe(float* out_mhz)
+{
+    if (threadIdx.x != 0) return;
+    unsigned long long t0, t1, c0, c1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    c0 = clock64();
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 8000ull);
+    c1 = clock64();
+    *out_mhz = (float)((double)(c1 - c0) / (double)(t1 - t0) * 1e3);
 }
 
 // Frame accumulators -> mean radiance per pixel (Renderer.cu:142-144), for the tiles this rank owns.  `dst32/dst64`

@@ -88,6 +88,7 @@ struct ipt_ctx {
     size_t hits_bytes = 0;
     uint32_t* counters = nullptr;
     unsigned long long* traced = nullptr;
+    uint32_t* fast_hint = nullptr;          // fast_schedule: bounces per pass the last batch settled on (cleared by set_scene)
     unsigned long long* frame = nullptr;
     size_t frame_pixels = 0;
     float* out32 = nullptr;
@@ -133,7 +134,8 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 8) != cudaSuccess) {
+        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 8) != cudaSuccess ||
+        cudaMalloc(&c->fast_hint, 4) != cudaSuccess || cudaMemset(c->fast_hint, 0, 4) != cudaSuccess) {
         set_err(std::string("ipt_ctx_create: ") + cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -157,7 +159,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
-    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->frame);
+    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->fast_hint); cudaFree(c->frame);
     cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -422,6 +424,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         c->mt_key = 0;   // a new scene invalidates the active micro-tile list
     }
     c->have_scene = true;
+    CK(cudaMemsetAsync(c->fast_hint, 0, 4, c->stream));   // a new scene: no survival measurement yet
     // frame buffers
     const size_t px = (size_t)c->W * c->H;
     if (px != c->frame_pixels) {
@@ -438,10 +441,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
 
-template <bool FIRST, bool EARLY, int MINB>
+template <bool FIRST, bool EARLY, int MINB, int SHAPE = 0>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
-    auto kern = k_bounce_fast<FIRST, EARLY, MINB>;
+    auto kern = k_bounce_fast<FIRST, EARLY, MINB, SHAPE>;
     const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * BLOCK_THREADS * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -661,10 +664,23 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 3;   // A/B knob: CTAs per SM the fast kernel is compiled for (3: 78 regs, no spill; 4: 64 regs, spills)
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
+    const bool sync_passes = std::getenv("IPT_SYNC_PASSES") != nullptr;   // diagnostic: drain the GPU between passes
+    // A/B knob: fixed number of bounces per pass for the fast kernel's passes from depth 2 on (default 0 = adaptive)
+    const uint32_t fast_k = std::getenv("IPT_FAST_K") ? (uint32_t)std::min(64, std::max(0, std::atoi(std::getenv("IPT_FAST_K")))) : 0u;
+    // fast kernel: depth 0, depth 1, then launches that advance several bounces each (fast_schedule)
+    const uint32_t passes_per_batch = (use_fast && prm.max_depth > 2)
+        ? 2 + (fast_k ? (prm.max_depth - 2 + fast_k - 1) / fast_k : std::min(prm.max_depth - 2, FAST_DEEP_LAUNCHES)) : prm.max_depth;
+    kp.fast_hint = c->fast_hint;
+    const int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     int grid_first = 0, grid_next = 0, grid_deep = 0, split_grids[2] = {0, 0};
+    // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
+    const bool pass_times = std::getenv("IPT_PASS_TIMES") != nullptr && !use_split;
+    std::vector<cudaEvent_t> pass_events;
+    float* clock_probe = nullptr;     // SM MHz sampled after each of the first 4096 passes
+    if (pass_times && std::getenv("IPT_PASS_CLOCKS")) CK(cudaMallocManaged(&clock_probe, 4096 * sizeof(float)));
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
     // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
@@ -681,17 +697,34 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             batches++;
             continue;
         }
-        for (uint32_t d = 0; d < prm.max_depth; d++) {
+        const uint32_t n_passes = passes_per_batch;
+        kp.n_passes = n_passes;
+        for (uint32_t pass = 0; pass < n_passes; pass++) {
+            const uint32_t d = pass;                       // the depth of the pass, except for the fast kernel's passes > 2
+            if (pass_times) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, c->stream)); pass_events.push_back(e); }
             kp.depth = d;
-            kp.qin = Queue{c->q[(d + 1) & 1], cap};
-            kp.qout = Queue{c->q[d & 1], cap};
+            kp.pass = pass;
+            kp.fast_k = fast_k;
+            kp.qin = Queue{c->q[(pass + 1) & 1], cap};
+            kp.qout = Queue{c->q[pass & 1], cap};
             int rc;
             if (use_fast) {
                 const KParams<float>& kf = (const KParams<float>&)kp;
-                if (d == 0) rc = launch_bounce_fast<true, true, 3>(c, kf, &grid_first);
-                else if (d == 1) rc = launch_bounce_fast<false, true, 3>(c, kf, &grid_next);
+                // box rooms (fast_shape): the scan is straight-line code, one instantiation per sphere count
+#define IPT_FAST_BY_SHAPE(FIRST, EARLY, GRID)                                                                 \
+    switch (shape) {                                                                                          \
+        case 1: rc = launch_bounce_fast<FIRST, EARLY, 3, 1>(c, kf, GRID); break;                              \
+        case 2: rc = launch_bounce_fast<FIRST, EARLY, 3, 2>(c, kf, GRID); break;                              \
+        case 3: rc = launch_bounce_fast<FIRST, EARLY, 3, 3>(c, kf, GRID); break;                              \
+        case 4: rc = launch_bounce_fast<FIRST, EARLY, 3, 4>(c, kf, GRID); break;                              \
+        case 5: rc = launch_bounce_fast<FIRST, EARLY, 3, 5>(c, kf, GRID); break;                              \
+        default: rc = launch_bounce_fast<FIRST, EARLY, 3, 0>(c, kf, GRID); break;                             \
+    }
+                if (d == 0) IPT_FAST_BY_SHAPE(true, true, &grid_first)
+                else if (d == 1) IPT_FAST_BY_SHAPE(false, true, &grid_next)
                 else if (fast_minb == 4) rc = launch_bounce_fast<false, false, 4>(c, kf, &grid_deep);
-                else rc = launch_bounce_fast<false, false, 3>(c, kf, &grid_deep);
+                else IPT_FAST_BY_SHAPE(false, false, &grid_deep)
+#undef IPT_FAST_BY_SHAPE
             }
             else if (defer && d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true, true>(c, kp, smem, &grid_first);
             else if (defer) rc = bvh ? launch_bounce<R, MODE_BVH, false, true>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false, true>(c, kp, smem, &grid_next);
@@ -699,9 +732,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             else rc = bvh ? launch_bounce<R, MODE_BVH, false>(c, kp, smem, &grid_next) : launch_bounce<R, MODE_BRUTE, false>(c, kp, smem, &grid_next);
             if (rc) return rc;
             launches++;
+            if (pass_times && clock_probe && pass_events.size() <= 4096) k_clock_probe<<<1, 32, 0, c->stream>>>(clock_probe + pass_events.size() - 1);
+            if (sync_passes) CK(cudaStreamSynchronize(c->stream));
         }
         batches++;
     }
+    if (pass_times) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, c->stream)); pass_events.push_back(e); }
     // resolve (and gather: dst may be a peer GPU's frame)
     ResolveParams rp;
     rp.frame = c->frame; rp.dst32 = c->gather32; rp.dst64 = c->gather64; rp.tile_ids = c->tile_ids;
@@ -715,6 +751,26 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (pass_times && pass_events.size() > 1) {
+        std::vector<double> per_depth(passes_per_batch, 0.0);
+        for (size_t i = 0; i + 1 < pass_events.size(); i++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, pass_events[i], pass_events[i + 1]);
+            per_depth[i % passes_per_batch] += t;
+        }
+        std::fprintf(stderr, "[ipt] pass times over %llu batch(es), ms per pass:", (unsigned long long)batches);
+        for (uint32_t d = 0; d < passes_per_batch; d++) std::fprintf(stderr, " %.3f", per_depth[d]);
+        std::fprintf(stderr, "  (total %.3f)\n", ms);
+        if (clock_probe) {
+            std::vector<double> mhz(passes_per_batch, 0.0); std::vector<int> cnt(passes_per_batch, 0);
+            for (size_t i = 0; i + 1 < pass_events.size() && i < 4096; i++) { mhz[i % passes_per_batch] += clock_probe[i]; cnt[i % passes_per_batch]++; }
+            std::fprintf(stderr, "[ipt] SM MHz after each pass:");
+            for (uint32_t d = 0; d < passes_per_batch; d++) std::fprintf(stderr, " %.0f", cnt[d] ? mhz[d] / cnt[d] : 0.0);
+            std::fprintf(stderr, "\n");
+        }
+    }
+    if (clock_probe) cudaFree(clock_probe);
+    for (cudaEvent_t e : pass_events) cudaEventDestroy(e);
     unsigned long long traced = 0;
     CK(cudaMemcpy(&traced, c->traced, 8, cudaMemcpyDeviceToHost));
     c->last.render_ms = ms; c->last.traced_bounces = traced; c->last.kernel_launches = launches; c->last.batches = batches;

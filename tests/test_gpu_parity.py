@@ -553,6 +553,70 @@ def test_camera_ray_culling_is_exact(pyipt, oracle, ctx, tmp_path, monkeypatch):
     assert frac_within(img, ref, 1e-9) >= 0.9995 and ref.any()
 
 
+@pytest.mark.parametrize("n_spheres", [0, 1, 2, 3, 4, 5])
+def test_box_room_shapes_match_the_list_kernel_and_the_oracle(pyipt, oracle, tmp_path, monkeypatch, n_spheres):
+    """Closed axis-aligned room (two rectangles per axis) with 0..4 spheres runs the straight-line instantiations of
+    k_bounce_fast (fast_shape 1..5); 5 spheres falls back to the list loops.  Same frame as the loop kernel
+    (IPT_NO_SHAPE=1) and as the oracle."""
+    from scene_util import room_objects, vec, write_scene
+    objs = room_objects()[:6]
+    balls = [dict(radius=600.0, position=(640, 95, 1320), color=(0, 0, 0), emission=(20, 20, 20), reflection=0),
+             dict(radius=150.0, position=(300, 300, 140), color=(.9, .9, .9), emission=(0, 0, 0), reflection=1),
+             dict(radius=150.0, position=(900, 200, 140), color=(.9, .9, .9), emission=(0, 0, 0), reflection=2),
+             dict(radius=90.0, position=(640, 450, 400), color=(.3, .8, .4), emission=(0, 0, 0), reflection=0),
+             dict(radius=60.0, position=(200, 100, 500), color=(.2, .2, .2), emission=(6, 3, 1), reflection=0)]
+    if n_spheres == 0:    # no sphere at all: light the room from a wall
+        objs[4]["emission"] = vec((4, 4, 4))
+    for b in balls[:n_spheres]:
+        objs.append({"type": "sphere", "radius": b["radius"], "position": vec(b["position"]), "color": vec(b["color"]),
+                     "emission": vec(b["emission"]), "reflection": b["reflection"]})
+    scene = {"width": 320, "height": 180, "camera": {"position": vec((640, 0, 360)), "direction": vec((0, 1, 0)), "orientation": vec((-1, 0, 0))},
+             "objects": objs}
+    path = write_scene(tmp_path / f"room{n_spheres}.json", scene)
+    spp, depth, seed = 6, 9, 31
+    ref, cnt = oracle.render(oracle.Scene.load(path), spp, depth, rng=oracle.RNG_COUNTER, seed=seed)
+    hs = pyipt.HostScene.load(path)
+    img, st = pyipt.render(hs, spp, depth, seed=seed)
+    monkeypatch.setenv("IPT_NO_SHAPE", "1")
+    loop, st_loop = pyipt.render(hs, spp, depth, seed=seed)
+    monkeypatch.delenv("IPT_NO_SHAPE")
+    assert ref.any()
+    assert frac_within(img, ref, 1e-3) >= 0.99
+    assert frac_within(img, loop, 1e-4) >= 0.999
+    assert abs(st["traced_bounces"] - st_loop["traced_bounces"]) <= 1e-4 * st_loop["traced_bounces"]
+    assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 2e-3 * cnt["casts_needed"]
+
+
+@pytest.mark.parametrize("which,depth", [("spheres", 10), ("spheres", 40), ("leaky", 40), ("leaky", 5), ("maze", 3)])
+def test_bounces_per_pass_do_not_change_the_frame(pyipt, oracle, tmp_path, monkeypatch, which, depth):
+    """From depth 2 on the typed-list kernel advances rays several bounces per pass, the count chosen on the device from
+    the measured survival rate (fast_schedule) within a fixed launch budget.  The RNG is keyed by depth and the
+    accumulation is fixed point, so the frame and the cast count are bit-identical for every choice: adaptive
+    (default), one bounce per pass, and fixed 3 / 8."""
+    from scene_util import synthetic_scene, write_scene
+    if which == "leaky":      # room with the front wall removed and 60 small objects: a third of the rays leave per bounce
+        sc = synthetic_scene(60, seed=5, width=192, height=108, general_rects=True)
+        del sc["objects"][5]
+        path = write_scene(tmp_path / "leaky.json", sc)
+        hs = pyipt.HostScene.load(path)
+    else:
+        path = oracle.scene_path(which)
+        hs = pyipt.HostScene.load(path, width=192, height=108)
+    frames, casts = [], []
+    for k in ("", "1", "3", "8"):
+        if k:
+            monkeypatch.setenv("IPT_FAST_K", k)
+        img, st = pyipt.render(hs, 5, depth, seed=9, want64=False)
+        monkeypatch.delenv("IPT_FAST_K", raising=False)
+        frames.append(img); casts.append(st["traced_bounces"])
+    assert frames[0].any()
+    for f, c in zip(frames[1:], casts[1:]):
+        assert np.array_equal(f, frames[0]) and c == casts[0]
+    ref, cnt = oracle.render(oracle.Scene.load(path, 192, 108), 5, depth, rng=oracle.RNG_COUNTER, seed=9)
+    assert frac_within(frames[0], ref, 1e-3) >= 0.99
+    assert abs(casts[0] - cnt["casts_needed"]) <= 3e-3 * cnt["casts_needed"]
+
+
 def test_every_kernel_variant_runs_small(pyipt):
     """scripts/sanitize_smoke.py: tiny renders through every kernel variant (fast, generic fp64, BVH split pipeline,
     DEFER, Russian roulette, rgb8, trace, 3-rank tiling) — the script written for compute-sanitizer (closed on this pool)."""
