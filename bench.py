@@ -39,7 +39,7 @@ WORKLOADS = {
     "synthetic1m": dict(scene="synthetic1m", width=None, height=None, depth=10, spp=256, flops=0,
                         desc="synthetic 1M-primitive scene in the scenes/*.json schema -d=10 -s=256 (configs[4])"),
 }
-BYTES_PER_BOUNCE = 96          # fused extend+shade wavefront: 48 B ray record read + 48 B written
+BYTES_PER_BOUNCE = 96          # a wavefront that compacts after every bounce: 48 B ray record read + 48 B written
 FP32_LANES_PER_SM = 128
 
 
@@ -84,12 +84,14 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.power, self.power_limit = [], None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1e3
         except Exception:
             self.nv = None
 
@@ -103,20 +105,23 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def result(self):
         self.stop_flag = True
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        pw = sorted(self.power) or [None]
+        return {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w": pw[len(pw) // 2], "power_w_max": pw[-1], "power_limit_w": self.power_limit}
 
 
 def physical_gpu_index(local):
@@ -289,10 +294,11 @@ def main():
     sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
-    dev_ms, bounces, samples, launches = 0.0, 0, 0, 0
+    dev_ms, bounces, samples, launches, qbytes = 0.0, 0, 0, 0, 0
     for _ in range(args.steps):
         st = step()
         dev_ms += st["render_ms"]; bounces += st["traced_bounces"]; samples += st["samples"]; launches += st["kernel_launches"]
+        qbytes += st["queue_bytes"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.result()
@@ -335,11 +341,16 @@ def main():
         # per-GPU figures of rank 0 (the kernels are the same on every rank)
         r0_ms = dev_ms / args.steps
         ach_fp32 = my_bounces_per_step * wl["flops"] / (r0_ms * 1e-3) / 1e12
-        ach_hbm = my_bounces_per_step * BYTES_PER_BOUNCE / (r0_ms * 1e-3) / 1e9
-        traffic = None
+        # HBM: the ray-queue bytes this design moves (records written + read back, counted on the device); a pass that
+        # advances rays k bounces in registers moves 96/k bytes per bounce
+        my_qbytes_per_step = qbytes / args.steps
+        ach_hbm = my_qbytes_per_step / (r0_ms * 1e-3) / 1e9
+        bytes_per_bounce = my_qbytes_per_step / max(1.0, my_bounces_per_step)
+        traffic = wi = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-            traffic = tr.get(args.workload, {}).get("dram_bytes_per_bounce")
+            traffic = tr.get(args.workload, {}).get("dram_bytes_per_queue_byte")
+            wi = tr.get(args.workload, {}).get("warp_instructions_per_bounce")
         except Exception:
             pass
         roof_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_fp32 / fp32_peak,
@@ -347,11 +358,20 @@ def main():
                      "frac_at_observed_clock": ach_fp32 / (sm_count * FP32_LANES_PER_SM * 2 * clk * 1e6 / 1e12),
                      "algorithmic_flops_per_bounce": wl["flops"]}
         roof_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak,
-                    "traffic": None if traffic is None else traffic * my_bounces_per_step / max(1, launches / args.steps),
-                    "peak_source": hbm_src, "algorithmic_bytes_per_bounce": BYTES_PER_BOUNCE,
+                    "traffic": None if traffic is None else traffic * my_qbytes_per_step / max(1, launches / args.steps),
+                    "peak_source": hbm_src, "algorithmic_bytes_per_bounce": bytes_per_bounce,
+                    "one_bounce_per_pass_equivalent_gbs": my_bounces_per_step * BYTES_PER_BOUNCE / (r0_ms * 1e-3) / 1e9,
                     "kernel": ("k_extend_bvh + k_bounce<MODE_SHADE>" if wl["scene"] == "synthetic1m" else "k_bounce_fast") +
-                              " (one launch per bounce per batch); achieved = bounces x bytes / sum of launch durations; traffic = measured DRAM bytes per bounce (ncu) x bounces per launch"}
+                              "; achieved = ray-queue bytes written + read (ipt_stats.queue_bytes) / sum of launch durations; "
+                              "traffic = measured DRAM bytes (ncu) per queue byte x queue bytes per launch"}
         binding = roof_hbm if roof_hbm["frac"] >= roof_fp32["frac"] else roof_fp32
+        # what actually limits the typed-list kernel: warp-instruction issue slots (4 schedulers per SM, one per clock)
+        roof_issue = None
+        if wi:
+            issue_peak = sm_count * 4 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e9
+            ach_issue = my_bounces_per_step * wi / (r0_ms * 1e-3) / 1e9
+            roof_issue = {"bound": "issue", "achieved": ach_issue, "peak": issue_peak, "unit": "G warp-inst/s", "frac": ach_issue / issue_peak,
+                          "warp_instructions_per_bounce": wi, "source": "instruction count of the ncu capture in profiles/ (smsp__inst_executed.sum / rays / bounces)"}
         line = {
             "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
             "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
@@ -362,13 +382,15 @@ def main():
                        "samples_per_step": int(tot_samples), "traced_bounces_per_step": int(tot_bounces),
                        "pixels_with_camera_rays": int(allsum_active), "pixels": W * H,
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
-                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray)", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
+                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": tot_launches,
             "clocks": clocks,
             "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
         }
+        if roof_issue:
+            line["roofline_issue"] = roof_issue
         if not wl["flops"]:
             line["roofline"] = roof_hbm
             line.pop("roofline_fp32")

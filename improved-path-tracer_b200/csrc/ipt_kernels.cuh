@@ -684,6 +684,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
     if (lane == 0 && my_traced) atomicAdd(p.traced, (unsigned long long)my_traced);
 }
 
+// End of a batch: every queue record was written once and read once, and counters[CNT + d] is the length of the queue
+// a pass at depth d read (0 for depths no pass started at).  stats[1] += 2 * sum of those (ipt_stats.queue_bytes).
+__global__ void k_batch_stats(const uint32_t* __restrict__ counters, unsigned long long* stats)
+{
+    unsigned long long s = 0;
+    for (int d = threadIdx.x; d < MAX_PASSES; d += 32) s += counters[CNT + d];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) stats[1] += 2ull * s;
+}
+
 // Diagnostic (IPT_PASS_TIMES): SM clock right now, from ~8 us of %clock64 against %globaltimer on one warp.
 __global__ void k_clock_probe(float* out_mhz)
 {

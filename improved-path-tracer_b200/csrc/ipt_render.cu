@@ -134,7 +134,7 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 8) != cudaSuccess ||
+        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 16) != cudaSuccess ||
         cudaMalloc(&c->fast_hint, 4) != cudaSuccess || cudaMemset(c->fast_hint, 0, 4) != cudaSuccess) {
         set_err(std::string("ipt_ctx_create: ") + cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -673,7 +673,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.fast_hint = c->fast_hint;
     const int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
-    CK(cudaMemsetAsync(c->traced, 0, 8, c->stream));
+    CK(cudaMemsetAsync(c->traced, 0, 16, c->stream));   // [0] casts, [1] queue records moved
     CK(cudaEventRecord(c->ev0, c->stream));
     int grid_first = 0, grid_next = 0, grid_deep = 0, split_grids[2] = {0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
@@ -694,6 +694,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         if (use_split) {
             int rc = launch_split_batch(c, (KParams<float>&)kp, prm.max_depth, cap, smem, split_grids, &launches);
             if (rc) return rc;
+            k_batch_stats<<<1, 32, 0, c->stream>>>(c->counters, c->traced);
+            launches++;
             batches++;
             continue;
         }
@@ -735,6 +737,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             if (pass_times && clock_probe && pass_events.size() <= 4096) k_clock_probe<<<1, 32, 0, c->stream>>>(clock_probe + pass_events.size() - 1);
             if (sync_passes) CK(cudaStreamSynchronize(c->stream));
         }
+        k_batch_stats<<<1, 32, 0, c->stream>>>(c->counters, c->traced);
+        launches++;
         batches++;
     }
     if (pass_times) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, c->stream)); pass_events.push_back(e); }
@@ -771,9 +775,11 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     }
     if (clock_probe) cudaFree(clock_probe);
     for (cudaEvent_t e : pass_events) cudaEventDestroy(e);
-    unsigned long long traced = 0;
-    CK(cudaMemcpy(&traced, c->traced, 8, cudaMemcpyDeviceToHost));
-    c->last.render_ms = ms; c->last.traced_bounces = traced; c->last.kernel_launches = launches; c->last.batches = batches;
+    unsigned long long traced[2] = {0, 0};
+    CK(cudaMemcpy(traced, c->traced, 16, cudaMemcpyDeviceToHost));
+    const size_t record_bytes = (sizeof(R) == 4 ? 48 : 96) + (defer ? (sizeof(R) == 4 ? 16 : 32) : 0);
+    c->last.queue_bytes = traced[1] * record_bytes;
+    c->last.render_ms = ms; c->last.traced_bounces = traced[0]; c->last.kernel_launches = launches; c->last.batches = batches;
     uint64_t npx = 0;
     for (uint32_t t : c->tile_host) {
         const uint32_t x0 = (t % tiles_x) * tile_w, z0 = (t / tiles_x) * tile_h;
@@ -970,7 +976,9 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
     if (rc == IPT_OK && stats) {
         *stats = sts[0];
         stats->samples = 0; stats->traced_bounces = 0; stats->kernel_launches = 0; stats->batches = 0; stats->render_ms = 0;
+        stats->queue_bytes = 0;
         for (int g = 0; g < n_gpus; g++) {
+            stats->queue_bytes += sts[g].queue_bytes;
             stats->samples += sts[g].samples; stats->traced_bounces += sts[g].traced_bounces;
             stats->kernel_launches += sts[g].kernel_launches; stats->batches += sts[g].batches;
             if (g > 0) stats->active_pixels += sts[g].active_pixels;

@@ -63,7 +63,7 @@ class Stats(ctypes.Structure):
                 ("batches", ctypes.c_uint64), ("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double),
                 ("download_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("per_gpu_render_ms", ctypes.c_double * 8), ("per_gpu_bounces", ctypes.c_uint64 * 8),
-                ("active_pixels", ctypes.c_uint64)]
+                ("active_pixels", ctypes.c_uint64), ("queue_bytes", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.startswith("per_gpu") else getattr(self, k)) for k, _ in self._fields_}

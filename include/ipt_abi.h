@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IPT_ABI_VERSION 1
+#define IPT_ABI_VERSION 2
 
 typedef enum ipt_status {
     IPT_OK = 0,
@@ -124,6 +124,8 @@ typedef struct ipt_stats {
     uint64_t per_gpu_bounces[8];
     uint64_t active_pixels;      /* pixels whose camera rays can reach the scene's bounding box; the others are exactly 0
                                     for every sample and no ray is generated for them (they still count in `samples`)  */
+    uint64_t queue_bytes;        /* ray-queue bytes written + read back by the wavefront passes (records x record size): the
+                                    traffic the design sends through HBM, counted on the device                         */
 } ipt_stats;
 
 /* -- device probe (CudaUtils.cu:8-23) ------------------------------------------------------------------- */

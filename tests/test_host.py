@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pyipt):
     L = pyipt.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ipt_abi_version() == 1
+    assert L.ipt_abi_version() == 2
 
 
 def test_no_torch_and_no_oracle_in_the_product():
