@@ -516,55 +516,65 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Passes from depth 2 on advance every ray by nk bounces in registers before compacting (see the loop in the kernel).
-// Their schedule lives on the device, so the host never waits for a queue length: pass `p.pass` starts at the depth
-// the previous pass left in counters[WORK + pass] (pass 2 starts at depth 2) and leaves depth + nk for the next one.
-// nk comes from the survival rate the previous pass measured (queue length in / out): idle lanes cost about as much
-// as they save once nk * (fraction lost per bounce) exceeds ~0.2; a closed room loses < 1 % per bounce and gets the
-// cap of 8.  Pass 2 has no measurement of its own batch yet and starts from what the previous batch settled on
-// (*fast_hint; written only by passes > 2, read only by pass 2, so never inside one grid).  The host launches a fixed
-// number of passes per batch; the remaining depth is spread over the launches that are left when that is more than
-// the survival rate asks for (the last launch always finishes the paths), and surplus launches return at once.
-// Every thread of the grid computes the same values from the same finished counters.  Returns true when past maxDepth.
+// One pass of the typed-list kernel advances every ray by up to nk bounces in registers before it compacts the
+// survivors into the next queue.  A closed room loses well under 1 % of its rays per bounce, so compacting and
+// round-tripping 96 B per ray through HBM after every bounce buys nothing there; with nk = 8 the queue traffic drops
+// to an eighth and, with it, the board power that capped the one-bounce-per-pass kernel.
+//
+// Pass 0 generates the camera rays and makes the bounces at depth 0 and 1 itself, because those are the ones where a
+// path can split (AObject.hpp:91-94, :122-125): the depth-0 split's second ray is a one-cast emission probe
+//  and is cast on the spot, the depth-1 split's second ray is appended to the queue next to the
+// main ray, both at depth 2.  Later passes only ever see rays that cannot split, all at the same depth (each ray
+// carries its depth in meta bits 0-7).  The RNG is keyed by (pixel, sample, lane, depth) and the accumulation is
+// fixed point, so the frame and the cast count do not depend on nk.
+//
+// The schedule lives on the device, so the host never waits for a queue length: pass `p.pass` finds the smallest depth
+// its rays can have in counters[WORK + pass] and leaves that + nk for the next one.  nk comes from the survival rate
+// the previous pass measured (queue length in / out): idle lanes cost about as much as they save once
+// nk * (fraction lost per bounce) exceeds ~0.2 - a leaky scene gets 1-2, a closed room the cap of 8.  Pass 1 has no
+// usable measurement of its own batch (camera misses and splits distort it) and starts from what the previous batch
+// settled on (*fast_hint: written only by passes >= 2, read only by pass 1, so never inside one grid).  The host launches a fixed number of passes per batch; the remaining depth is spread over the launches
+// that are left when that is more than the survival rate asks for (the last launch always finishes the paths), and
+// surplus launches return at once.  Every thread of the grid computes the same values from the same finished
+// counters.  Returns true when every path of the batch has already ended.
 static constexpr uint32_t FAST_K_MAX = 8;
-static constexpr uint32_t FAST_DEEP_LAUNCHES = 12;
+static constexpr uint32_t FAST_LATER_LAUNCHES = 12;      // launches per batch after pass 0 in adaptive mode
 template <typename P>
-__device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& depth, uint32_t& nk)
+__device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 {
-    depth = p.pass == 2 ? 2u : p.counters[WORK + p.pass];
+    const uint32_t dmin = p.pass == 0 ? 0u : p.counters[WORK + p.pass];
     const bool publish = blockIdx.x == 0 && threadIdx.x == 0;
-    if (depth >= p.maxDepth) {
-        if (publish && p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = depth;
+    if (dmin >= p.maxDepth) {
+        if (publish && p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = dmin;
         return true;
     }
-    if (p.fast_k) nk = p.fast_k;
-    else if (p.pass == 2) { const uint32_t h = *p.fast_hint; nk = h ? h : 1u; }
+    if (p.pass == 0) nk = 2;                             // exactly depth 0 and 1: every ray it queues is at depth 2
+    else if (p.fast_k) nk = p.fast_k;
+    else if (p.pass == 1) { const uint32_t h = *p.fast_hint; nk = h ? h : 2u; }
     else {
         const uint32_t nk_prev = p.counters[WORK_EXTEND + p.pass - 1];
-        const uint32_t n_prev = p.counters[CNT + depth - nk_prev], n_cur = p.counters[CNT + depth];
+        const uint32_t n_prev = p.counters[CNT + p.pass - 1], n_cur = p.counters[CNT + p.pass];
         const unsigned long long lost = n_prev > n_cur ? n_prev - n_cur : 1u;
         const unsigned long long k = 22ull * n_prev * nk_prev / (100ull * lost);
         nk = (uint32_t)(k < 1ull ? 1ull : (k > FAST_K_MAX ? FAST_K_MAX : k));
         if (publish && n_prev > (1u << 20)) *p.fast_hint = nk;   // queues this long make the padding of block tails negligible
     }
-    const uint32_t remaining = p.maxDepth - depth, launches_left = p.n_passes - p.pass;
-    nk = max(nk, (remaining + launches_left - 1) / launches_left);
+    const uint32_t remaining = p.maxDepth - dmin, launches_left = p.n_passes - p.pass;
+    if (p.pass) nk = max(nk, (remaining + launches_left - 1) / launches_left);
+    if (p.pass && !p.fast_k && remaining <= nk + nk / 2) nk = remaining;   // no short trailing pass: a round trip for < nk/2 bounces
     nk = min(nk, remaining);
     if (publish) {
-        if (p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = depth + nk;
+        if (p.pass + 1 < p.n_passes) p.counters[WORK + p.pass + 1] = dmin + nk;
         p.counters[WORK_EXTEND + p.pass] = nk;
     }
     return false;
 }
 
-// EARLY = this pass is at depth 0 or 1, where specular / refractive hits split into two rays (AObject.hpp:91-94,
-// :122-125); from depth 2 on there is exactly one continuation, so the second output ray, its ballot and its stores
-// drop out of the code (fewer registers, fewer instructions) for the bulk of the passes.
-template <bool FIRST, bool EARLY, int MINB, int SHAPE = 0>
-__global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __grid_constant__ KParams<float> p)
+template <bool FIRST, int SHAPE = 0>
+__global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
-    uint32_t depth = p.depth, nk = 1;                   // nk: bounces a ray makes in this pass
-    if (!EARLY && fast_schedule(p, depth, nk)) return;  // past maxDepth: the batch finished in fewer passes than launched
+    uint32_t nk = 1;                                    // bounces a ray makes in this pass
+    if (fast_schedule(p, nk)) return;                   // the batch finished in fewer passes than were launched
     extern __shared__ uint4 smem[];
     uint4* stagebuf = smem + p.fast_words;              // [2 buffers][3 planes][BLOCK_THREADS]
     stage(smem, p.fast_blob, p.fast_words);
@@ -573,12 +583,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + depth];
-    uint32_t* out_count = p.counters + CNT + depth + nk;
+    const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.pass];
+    uint32_t* out_count = p.counters + CNT + p.pass + 1;
     const uint32_t warp_global = blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5);
     const uint32_t stride = gridDim.x * BLOCK_THREADS;   // rays per sweep of the whole grid
     uint32_t my_traced = 0;                              // per warp and pass: far below 2^32
     uint32_t blk_base = 0, blk_used = OUT_BLOCK;         // no block reserved yet
+
+    // Compaction into the warp's private output block: the rays of the lanes in `mask` fill the rest of the current
+    // block and spill into a freshly reserved one (one atomic per OUT_BLOCK outputs, no holes inside blocks).
+    auto emit = [&](bool has, uint32_t mask, const Ray<float>& ray) {
+        const uint32_t tot = __popc(mask);
+        const uint32_t room = OUT_BLOCK - blk_used;
+        uint32_t nb = blk_base;
+        if (tot > room) {
+            if (lane == 0) nb = atomicAdd(out_count, OUT_BLOCK);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+        }
+        const uint32_t j = __popc(mask & lt_mask);
+        if (has) q_store(p.qout, j < room ? blk_base + blk_used + j : nb + (j - room), ray);
+        if (tot > room) { blk_base = nb; blk_used = tot - room; }
+        else blk_used += tot;
+    };
 
     uint32_t i = warp_global * 32u + lane;
     int buf = 0;
@@ -611,25 +637,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
             }
             buf ^= 1;
         }
-        // One pass advances a ray by nk bounces in registers (nk = 1 at depth 0 and 1, where paths split).  A closed
-        // room loses well under 1 % of its rays per bounce, so compacting and round-tripping the queues through HBM
-        // only every nk-th bounce costs a few idle lanes and saves (nk-1)/nk of the queue traffic.  The RNG is keyed
-        // by (pixel, sample, lane, depth): the frame does not depend on nk.
-        bool has0 = live, has1 = false;
-        Ray<float> o0 = r, o1;
+        bool has0 = live;
         for (uint32_t k = 0; k < nk; k++) {
-            const uint32_t dk = depth + k;
             const bool in = has0;
             const uint32_t m_in = __ballot_sync(0xffffffffu, in);
             if (!m_in) break;                              // every ray of this slice has ended
             my_traced += __popc(m_in);
             has0 = false;
+            bool has1 = false;
+            Ray<float> o1;
             if (in) {
-                const Ray<float> r = o0;
+                const uint32_t dk = FIRST ? k : (r.meta & 0xFFu);
                 const FastHit h = nearest_fast<SHAPE>(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
                 if (h.code != NO_OBJECT) {
-                    const uint32_t hobj = fast_hit_object(sc, h.code);
-                    const uint32_t obj = hobj & ~RECT_BIT;
+                    const uint32_t obj = fast_hit_object(sc, h.code) & ~RECT_BIT;
                     const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
                     if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
                     V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                         const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
                         const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
-                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, EARLY ? dk : 2u, rnd);
+                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
                         bool alive = sp.has0;
                         if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
@@ -647,37 +668,37 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_bounce_fast(const __gri
                             else nthr = nthr * (1.f / q);
                         }
                         const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
-                        has0 = alive;
-                        o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.self = h.code;
                         const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (dk + 1);
-                        o0.meta = mcommon | (r.meta & 0x300u);
-                        if (sp.teleport) { o0.o = mk<float>(0.f, 0.f, 0.f); o0.self = NO_OBJECT; o0.meta &= ~META_ONSURF; }
-                        if (EARLY) {
+                        if (FIRST && k < 2) {
                             has1 = sp.has1;
                             o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
-                            o1.meta = mcommon | (dk == 0 ? (0x200u | META_PROBE) : 0x100u);
+                            o1.meta = mcommon | (k == 0 ? (0x200u | META_PROBE) : 0x100u);
                         }
+                        has0 = alive;
+                        r.o = P; r.d = sp.d0; r.thr = nthr * sp.w0; r.self = h.code;
+                        r.meta = mcommon | (r.meta & 0x300u);
+                        if (sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; r.meta &= ~META_ONSURF; }
                     }
                 }
             }
-        }
-        // ---- compaction into the warp's private output block
-        const uint32_t m0b = __ballot_sync(0xffffffffu, has0), m1b = EARLY ? __ballot_sync(0xffffffffu, has1) : 0u;
-        const uint32_t c0 = __popc(m0b), tot = c0 + (EARLY ? __popc(m1b) : 0u);
-        if (tot) {
-            // outputs fill the rest of the current block and spill into a freshly reserved one: no holes inside blocks
-            const uint32_t room = OUT_BLOCK - blk_used;
-            uint32_t nb = blk_base;
-            if (tot > room) {
-                if (lane == 0) nb = atomicAdd(out_count, OUT_BLOCK);
-                nb = __shfl_sync(0xffffffffu, nb, 0);
+            if (FIRST && k < 2) {
+                const uint32_t m1b = __ballot_sync(0xffffffffu, has1);
+                if (m1b && k == 0) {
+                    // the second ray of a depth-0 split only ever contributes the emission of the first thing it hits
+                    // (SURVEY.md App. A.6): cast it here instead of sending it through a queue
+                    my_traced += __popc(m1b);
+                    if (has1) {
+                        const FastHit hp = nearest_fast<SHAPE>(sc, o1.o, o1.d, o1.self, (o1.meta & META_ONSURF) != 0);
+                        if (hp.code != NO_OBJECT) {
+                            const float4 e = sc.mat[2 * (fast_hit_object(sc, hp.code) & ~RECT_BIT) + 1];
+                            if (e.w != 0.f) accumulate_fast(p, o1.pixel, mul(o1.thr, mk<float>(e.x, e.y, e.z)));
+                        }
+                    }
+                } else if (m1b) emit(has1, m1b, o1);       // depth-1 split: a full path from depth 2 on
             }
-            const uint32_t j0 = __popc(m0b & lt_mask), j1 = c0 + __popc(m1b & lt_mask);
-            if (has0) q_store(p.qout, j0 < room ? blk_base + blk_used + j0 : nb + (j0 - room), o0);
-            if (EARLY && has1) q_store(p.qout, j1 < room ? blk_base + blk_used + j1 : nb + (j1 - room), o1);
-            if (tot > room) { blk_base = nb; blk_used = tot - room; }
-            else blk_used += tot;
         }
+        const uint32_t m0b = __ballot_sync(0xffffffffu, has0);
+        if (m0b) emit(has0, m0b, r);
     }
     // the unused tail of the last block: dead records (skipped by the next pass)
     for (uint32_t s = blk_used + lane; s < OUT_BLOCK; s += 32) p.qout.base[2u * p.qout.capacity + blk_base + s] = make_uint4(0u, 0u, META_DEAD, NO_OBJECT);

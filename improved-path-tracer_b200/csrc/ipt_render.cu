@@ -441,10 +441,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
 
-template <bool FIRST, bool EARLY, int MINB, int SHAPE = 0>
+template <bool FIRST, int SHAPE = 0>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
-    auto kern = k_bounce_fast<FIRST, EARLY, MINB, SHAPE>;
+    auto kern = k_bounce_fast<FIRST, SHAPE>;
     const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * BLOCK_THREADS * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -662,20 +662,24 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
-    const int fast_minb = std::getenv("IPT_FAST_MINB") ? std::atoi(std::getenv("IPT_FAST_MINB")) : 3;   // A/B knob: CTAs per SM the fast kernel is compiled for (3: 78 regs, no spill; 4: 64 regs, spills)
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     const bool sync_passes = std::getenv("IPT_SYNC_PASSES") != nullptr;   // diagnostic: drain the GPU between passes
     // A/B knob: fixed number of bounces per pass for the fast kernel's passes from depth 2 on (default 0 = adaptive)
     const uint32_t fast_k = std::getenv("IPT_FAST_K") ? (uint32_t)std::min(64, std::max(0, std::atoi(std::getenv("IPT_FAST_K")))) : 0u;
-    // fast kernel: depth 0, depth 1, then launches that advance several bounces each (fast_schedule)
-    const uint32_t passes_per_batch = (use_fast && prm.max_depth > 2)
-        ? 2 + (fast_k ? (prm.max_depth - 2 + fast_k - 1) / fast_k : std::min(prm.max_depth - 2, FAST_DEEP_LAUNCHES)) : prm.max_depth;
+    // fast kernel: pass 0 (camera rays, at least the bounces at depth 0 and 1), then launches that advance several
+    // bounces each (fast_schedule); with a fixed IPT_FAST_K the host knows how many are needed
+    uint32_t passes_per_batch = prm.max_depth;
+    if (use_fast) {
+        const uint32_t first = std::min(2u, prm.max_depth);
+        passes_per_batch = 1 + (fast_k ? (prm.max_depth - first + fast_k - 1) / fast_k
+                                       : std::min(prm.max_depth - first, FAST_LATER_LAUNCHES));
+    }
     kp.fast_hint = c->fast_hint;
     const int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 16, c->stream));   // [0] casts, [1] queue records moved
     CK(cudaEventRecord(c->ev0, c->stream));
-    int grid_first = 0, grid_next = 0, grid_deep = 0, split_grids[2] = {0, 0};
+    int grid_first = 0, grid_next = 0, split_grids[2] = {0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
     const bool pass_times = std::getenv("IPT_PASS_TIMES") != nullptr && !use_split;
     std::vector<cudaEvent_t> pass_events;
@@ -702,7 +706,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         const uint32_t n_passes = passes_per_batch;
         kp.n_passes = n_passes;
         for (uint32_t pass = 0; pass < n_passes; pass++) {
-            const uint32_t d = pass;                       // the depth of the pass, except for the fast kernel's passes > 2
+            const uint32_t d = pass;                       // the depth of the pass, except for the fast kernel (fast_schedule)
             if (pass_times) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, c->stream)); pass_events.push_back(e); }
             kp.depth = d;
             kp.pass = pass;
@@ -713,19 +717,17 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             if (use_fast) {
                 const KParams<float>& kf = (const KParams<float>&)kp;
                 // box rooms (fast_shape): the scan is straight-line code, one instantiation per sphere count
-#define IPT_FAST_BY_SHAPE(FIRST, EARLY, GRID)                                                                 \
-    switch (shape) {                                                                                          \
-        case 1: rc = launch_bounce_fast<FIRST, EARLY, 3, 1>(c, kf, GRID); break;                              \
-        case 2: rc = launch_bounce_fast<FIRST, EARLY, 3, 2>(c, kf, GRID); break;                              \
-        case 3: rc = launch_bounce_fast<FIRST, EARLY, 3, 3>(c, kf, GRID); break;                              \
-        case 4: rc = launch_bounce_fast<FIRST, EARLY, 3, 4>(c, kf, GRID); break;                              \
-        case 5: rc = launch_bounce_fast<FIRST, EARLY, 3, 5>(c, kf, GRID); break;                              \
-        default: rc = launch_bounce_fast<FIRST, EARLY, 3, 0>(c, kf, GRID); break;                             \
+#define IPT_FAST_BY_SHAPE(FIRST, GRID)                                                                 \
+    switch (shape) {                                                                                   \
+        case 1: rc = launch_bounce_fast<FIRST, 1>(c, kf, GRID); break;                                 \
+        case 2: rc = launch_bounce_fast<FIRST, 2>(c, kf, GRID); break;                                 \
+        case 3: rc = launch_bounce_fast<FIRST, 3>(c, kf, GRID); break;                                 \
+        case 4: rc = launch_bounce_fast<FIRST, 4>(c, kf, GRID); break;                                 \
+        case 5: rc = launch_bounce_fast<FIRST, 5>(c, kf, GRID); break;                                 \
+        default: rc = launch_bounce_fast<FIRST, 0>(c, kf, GRID); break;                                \
     }
-                if (d == 0) IPT_FAST_BY_SHAPE(true, true, &grid_first)
-                else if (d == 1) IPT_FAST_BY_SHAPE(false, true, &grid_next)
-                else if (fast_minb == 4) rc = launch_bounce_fast<false, false, 4>(c, kf, &grid_deep);
-                else IPT_FAST_BY_SHAPE(false, false, &grid_deep)
+                if (pass == 0) IPT_FAST_BY_SHAPE(true, &grid_first)
+                else IPT_FAST_BY_SHAPE(false, &grid_next)
 #undef IPT_FAST_BY_SHAPE
             }
             else if (defer && d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true, true>(c, kp, smem, &grid_first);
