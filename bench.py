@@ -303,6 +303,12 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.result()
     ms_dev = allmax(dev_ms) / args.steps                 # CUDA events on the rendering stream, max over ranks
+    per_rank_ms = [dev_ms / args.steps]
+    if dist is not None:
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = dev_ms / args.steps
+        dist.all_reduce(t)
+        per_rank_ms = [float(x) for x in t.tolist()]
     ms_wall = allmax(t_wall * 1e3) / args.steps
     tot_samples = allsum(samples) / args.steps
     tot_bounces = allsum(bounces) / args.steps
@@ -376,6 +382,7 @@ def main():
             "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
             "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "ms_per_step_wall": ms_wall,
+            "ms_per_step_per_rank": per_rank_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],

@@ -538,7 +538,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // surplus launches return at once.  Every thread of the grid computes the same values from the same finished
 // counters.  Returns true when every path of the batch has already ended.
 static constexpr uint32_t FAST_K_MAX = 8;
-static constexpr uint32_t FAST_LATER_LAUNCHES = 12;      // launches per batch after pass 0 in adaptive mode
+static constexpr uint32_t FAST_LATER_LAUNCHES = 8;       // launches per batch after pass 0 in adaptive mode
 template <typename P>
 __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 {
