@@ -1,13 +1,15 @@
 // ipt_kernels.cuh — the wavefront kernels of the B200 radiance path.
 //
-// One *batch* is a contiguous range of camera samples (default 64 Mi).  A batch is advanced one bounce per kernel launch
-// ("pass"): pass p reads the ray queue written by pass p-1, finds the nearest hit, accumulates emission, scatters, and
-// appends the continuation rays to the other queue, compacted with warp ballot + popc.  Queue lengths live on the
-// device and every launch is a persistent grid (a fixed number of CTAs per SM), so launch geometry never depends on
-// the queue length and the host never synchronises inside a render.  Three pipelines share the device functions of
-// ipt_device.cuh:
-//   k_bounce_fast<FIRST, EARLY>          fp32, scenes without a BVH (the shipped scenes, the 4K config): typed primitive
-//                                        lists in shared memory, static slice schedule with cp.async prefetch,
+// One *batch* is a contiguous range of camera samples (default 64 Mi).  A batch is advanced by kernel launches
+// ("passes"): pass p reads the ray queue written by pass p-1, finds the nearest hit, accumulates emission, scatters, and
+// appends the continuation rays to the other queue, compacted with warp ballot + popc - one bounce per pass in the
+// generic and BVH pipelines, several in the typed-list kernel.  Queue lengths live on the device and every launch is
+// a persistent grid (a fixed number of CTAs per SM), so launch geometry never depends on the queue length and the
+// host never synchronises inside a render.  Three pipelines share the device functions of ipt_device.cuh:
+//   k_bounce_fast<FIRST, SHAPE>          fp32, scenes without a BVH (the shipped scenes, the 4K config): typed primitive
+//                                        lists in shared memory (straight-line scan for box rooms), static slice
+//                                        schedule with cp.async prefetch, up to 8 bounces per ray in registers between
+//                                        two queue round trips (schedule kept on the device, fast_schedule),
 //                                        warp-private output blocks (one atomic per 128 outputs);
 //   k_raygen -> k_extend_bvh -> k_bounce<float, MODE_SHADE>
 //                                        fp32, BVH scenes: traversal with lane-level refill split from shading;
@@ -28,6 +30,7 @@ static constexpr int GRAB = 128;          // generic kernels: rays a warp claims
 static constexpr int BVH_TOP_NODES = 512; // top of the BVH staged in shared memory (32 KB)
 
 // counters[] layout (uint32): [CNT + p] rays queued for pass p, [WORK + p] work-claim counter of pass p
+// (k_bounce_fast claims no work: there [WORK + p] is the depth pass p starts at and [WORK_EXTEND + p] its bounce count)
 static constexpr int MAX_PASSES = 256;
 static constexpr int CNT = 0, WORK = MAX_PASSES, WORK_EXTEND = 2 * MAX_PASSES;   // WORK_EXTEND: claim counter of k_extend_bvh
 static constexpr int N_COUNTERS = 3 * MAX_PASSES;
