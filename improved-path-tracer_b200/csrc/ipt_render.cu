@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -112,6 +113,22 @@ struct ipt_ctx {
     size_t pinned_bytes = 0;
     ipt_stats last = {};
 };
+
+// Host-side packing of large scenes (a million primitives is ~250 MB of staging): index ranges over a few threads.
+template <class F>
+static void parallel_ranges(size_t n, F f)
+{
+    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = std::getenv("IPT_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+    if (n < (size_t)1 << 16 || nt <= 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t b = std::min(n, t * chunk), e = std::min(n, b + chunk);
+        if (b < e) th.emplace_back([=, &f] { f(b, e); });
+    }
+    for (auto& t : th) t.join();
+}
 
 static int ensure_pinned(ipt_ctx* c, size_t bytes)
 {
@@ -264,14 +281,15 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     float* m32 = (float*)(pin + b_geom64 + b_geom32 + b_mat64);
     uint32_t* so = (uint32_t*)(pin + b_geom64 + b_geom32 + b_mat64 + b_mat32);
     float* nd = (float*)(pin + b_geom64 + b_geom32 + b_mat64 + b_mat32 + b_slot);
-    std::memset(g64, 0, b_geom64);
-    std::memset(so, 0xFF, b_slot);
-    for (uint32_t slot = 0; slot < n; slot++) {
-        uint32_t prim = bvh ? s->bvh_slot_prim[slot] : (slot < ns ? slot : (RECT_BIT | (slot - ns)));
+    std::memset(so + n, 0xFF, b_slot - (size_t)n * 4);
+    std::atomic<const char*> bad{nullptr};              // first inconsistency a packing thread found
+    parallel_ranges(n, [&](size_t lo_, size_t hi_) {
+      for (size_t slot = lo_; slot < hi_; slot++) {
+        uint32_t prim = bvh ? s->bvh_slot_prim[slot] : (slot < ns ? (uint32_t)slot : (RECT_BIT | ((uint32_t)slot - ns)));
         const bool rect = (prim & RECT_BIT) != 0;
         const uint32_t idx = prim & ~RECT_BIT;
-        if ((rect && idx >= s->n_rects) || (!rect && idx >= ns)) { set_err("ipt_ctx_set_scene: bad BVH slot"); return IPT_ERR_BAD_ARGUMENT; }
-        double* g = g64 + (size_t)slot * 16;
+        if ((rect && idx >= s->n_rects) || (!rect && idx >= ns)) { bad = "ipt_ctx_set_scene: bad BVH slot"; return; }
+        double* g = g64 + slot * 16;
         if (rect) {
             std::memcpy(g, s->rect_plane + 4 * (size_t)idx, 32);
             std::memcpy(g + 4, s->rect_u + 4 * (size_t)idx, 32);
@@ -280,27 +298,37 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
             so[slot] = s->rect_object[idx] | RECT_BIT;
         } else {
             std::memcpy(g, s->sphere_cxyzr + 4 * (size_t)idx, 32);
+            std::memset(g + 4, 0, 96);
             so[slot] = s->sphere_object[idx];
         }
-        if ((so[slot] & ~RECT_BIT) >= n) { set_err("ipt_ctx_set_scene: object index out of range"); return IPT_ERR_BAD_ARGUMENT; }
-    }
-    for (size_t i = 0; i < (size_t)n * 16; i++) g32[i] = (float)g64[i];
+        if ((so[slot] & ~RECT_BIT) >= n) { bad = "ipt_ctx_set_scene: object index out of range"; return; }
+        for (int i = 0; i < 16; i++) g32[slot * 16 + i] = (float)g[i];
+      }
+    });
+    if (bad.load()) { set_err(bad.load()); return IPT_ERR_BAD_ARGUMENT; }
     double maxE = 0, maxC = 0;
-    for (uint32_t k = 0; k < n; k++) {
-        double* m = m64 + (size_t)k * 8;
+    std::mutex max_lock;
+    parallel_ranges(n, [&](size_t lo_, size_t hi_) {
+      double mE = 0, mC = 0;
+      for (size_t k = lo_; k < hi_; k++) {
+        double* m = m64 + k * 8;
         bool anyE = false;
         for (int j = 0; j < 3; j++) {
-            m[j] = s->mat_color[3 * (size_t)k + j];
-            m[4 + j] = s->mat_emission[3 * (size_t)k + j];
+            m[j] = s->mat_color[3 * k + j];
+            m[4 + j] = s->mat_emission[3 * k + j];
             anyE = anyE || m[4 + j] != 0.0;
-            maxE = std::max(maxE, std::fabs(m[4 + j]));
-            maxC = std::max(maxC, std::fabs(m[j]));
+            mE = std::max(mE, std::fabs(m[4 + j]));
+            mC = std::max(mC, std::fabs(m[j]));
         }
         m[3] = (double)s->mat_reflection[k];
         m[7] = anyE ? 1.0 : 0.0;
-    }
-    for (size_t i = 0; i < (size_t)n * 8; i++) m32[i] = (float)m64[i];
-    for (uint32_t i = 0; i < s->n_bvh_nodes; i++) {
+        for (int i = 0; i < 8; i++) m32[k * 8 + i] = (float)m[i];
+      }
+      std::lock_guard<std::mutex> g(max_lock);
+      maxE = std::max(maxE, mE); maxC = std::max(maxC, mC);
+    });
+    parallel_ranges(s->n_bvh_nodes, [&](size_t lo_, size_t hi_) {
+      for (size_t i = lo_; i < hi_; i++) {
         const ipt_bvh_node& b = s->bvh_nodes[i];
         float* o = nd + (size_t)i * 16;
         o[0] = b.lo0[0]; o[1] = b.lo0[1]; o[2] = b.lo0[2]; o[3] = b.hi0[0];
@@ -309,17 +337,19 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         int32_t ch[2];
         for (int k = 0; k < 2; k++) {
             if (b.child[k] >= 0) {
-                if ((uint32_t)b.child[k] >= s->n_bvh_nodes) { set_err("ipt_ctx_set_scene: bad BVH child"); return IPT_ERR_BAD_ARGUMENT; }
+                if ((uint32_t)b.child[k] >= s->n_bvh_nodes) { bad = "ipt_ctx_set_scene: bad BVH child"; return; }
                 ch[k] = b.child[k];
             } else {
                 const uint32_t first = (uint32_t)(~b.child[k]), cnt = b.count[k];
-                if (cnt < 1 || cnt > 16 || (size_t)first + cnt > n || first >= (1u << 27)) { set_err("ipt_ctx_set_scene: bad BVH leaf"); return IPT_ERR_BAD_ARGUMENT; }
+                if (cnt < 1 || cnt > 16 || (size_t)first + cnt > n || first >= (1u << 27)) { bad = "ipt_ctx_set_scene: bad BVH leaf"; return; }
                 ch[k] = ~(int32_t)((first << 4) | (cnt - 1));
             }
         }
         std::memcpy(o + 12, ch, 8);
         o[14] = 0; o[15] = 0;
-    }
+      }
+    });
+    if (bad.load()) { set_err(bad.load()); return IPT_ERR_BAD_ARGUMENT; }
     std::vector<uint32_t> blob;
     if (!bvh) { blob = build_fast_blob(s); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
     // fp32 BVH leaf records: typed 32-byte entries in leaf (slot) order
@@ -334,9 +364,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
             }
             return k >= 0;
         };
-        for (uint32_t slot = 0; slot < n; slot++) {
+        parallel_ranges(n, [&](size_t lo_, size_t hi_) {
+          for (size_t slot = lo_; slot < hi_; slot++) {
             const uint32_t prim = s->bvh_slot_prim[slot], idx = prim & ~RECT_BIT;
-            float* o8 = &bs[(size_t)slot * 8];
+            float* o8 = &bs[slot * 8];
             uint32_t kind, obj;
             if (!(prim & RECT_BIT)) {
                 for (int k = 0; k < 4; k++) o8[k] = (float)s->sphere_cxyzr[4 * (size_t)idx + k];
@@ -355,7 +386,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
                 } else kind = 4;
             }
             std::memcpy(o8 + 4, &kind, 4); std::memcpy(o8 + 5, &obj, 4);
-        }
+          }
+        });
     }
     const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4};
     if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom64) {
