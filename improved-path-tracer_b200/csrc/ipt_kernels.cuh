@@ -573,9 +573,17 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
     return false;
 }
 
+// Threads per CTA and CTAs per SM of the passes after pass 0 (pass 0 uses BLOCK_THREADS x 3)
+#ifndef IPT_FAST_THREADS
+#define IPT_FAST_THREADS 256
+#define IPT_FAST_CTAS 3
+#endif
+template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? 3 : IPT_FAST_CTAS; };
+
 template <bool FIRST, int SHAPE = 0>
-__global__ void __launch_bounds__(BLOCK_THREADS, 3) k_bounce_fast(const __grid_constant__ KParams<float> p)
+__global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
+    constexpr int BLOCK_THREADS = FastCfg<FIRST>::THREADS;   // shadows the file-wide constant inside this kernel
     uint32_t nk = 1;                                    // bounces a ray makes in this pass
     if (fast_schedule(p, nk)) return;                   // the batch finished in fewer passes than were launched
     extern __shared__ uint4 smem[];

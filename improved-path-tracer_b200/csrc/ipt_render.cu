@@ -477,15 +477,16 @@ template <bool FIRST, int SHAPE = 0>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
     auto kern = k_bounce_fast<FIRST, SHAPE>;
-    const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * BLOCK_THREADS * 16;   // scene lists + double-buffered ray staging
+    constexpr int threads = FastCfg<FIRST>::THREADS;
+    const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * threads * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) { set_err("fast kernel does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
         *grid_cache = per_sm * c->sm_count;
     }
-    kern<<<*grid_cache, BLOCK_THREADS, smem, c->stream>>>(kp);
+    kern<<<*grid_cache, threads, smem, c->stream>>>(kp);
     return IPT_OK;
 }
 
