@@ -680,6 +680,8 @@ __device__ __forceinline__ V3<float> fast_hit_point(const FastScene& f, uint32_t
 }
 
 // Branch-free variant of scatter<float>: all candidate directions are computed, the material selects.
+// NO_GEN: the scene has no general (non axis-aligned) rectangle, so hit kind 4 cannot occur.
+template <bool NO_GEN = false>
 __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_t code, int reflection, V3<float> P, V3<float> in,
                                                      uint32_t depth, uint4 rnd)
 {
@@ -689,12 +691,16 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
         const float4 sp = f.sph[idx];
         raw = normalize(mk<float>(P.x - sp.x, P.y - sp.y, P.z - sp.z));       // Sphere.cu:44
         n = dot(in, raw) < 0.f ? -raw : raw;                                  // Sphere.cu:45
-    } else {
-        V3<float> pn;
-        if (kind == 4) pn = xyz(f.gen[4 * idx]);
-        else pn = mk<float>(kind == 1 ? 1.f : 0.f, kind == 2 ? 1.f : 0.f, kind == 3 ? 1.f : 0.f);
-        n = dot(in, pn) < 0.f ? pn : -pn;                                     // Plane.cu:73
+    } else if (NO_GEN || kind != 4) {
+        // normal +-e_K: Plane.cu:73's test n.d < 0 is the sign of the ray's K component
+        const float ik = kind == 1 ? in.x : (kind == 2 ? in.y : in.z);
+        const float sg = ik < 0.f ? 1.f : -1.f;
+        n = mk<float>(kind == 1 ? sg : 0.f, kind == 2 ? sg : 0.f, kind == 3 ? sg : 0.f);
         raw = n;                                                              // Plane.cu:79
+    } else {
+        const V3<float> pn = xyz(f.gen[4 * idx]);
+        n = dot(in, pn) < 0.f ? pn : -pn;                                     // Plane.cu:73
+        raw = n;
     }
     const V3<float> diff = diffuse_dir(n, rnd);                               // AObject.hpp:35-45
     const V3<float> spec = reflect_dir(in, n);                                // AObject.hpp:30-33

@@ -665,12 +665,12 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                     const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
                     if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
                     V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
-                    const bool go = dk + 1 < p.maxDepth && !(r.meta & META_PROBE) && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);
+                    const bool go = dk + 1 < p.maxDepth && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);   // no probes in these queues
                     if (go) {
                         const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
                         const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
-                        const Spawn<float> sp = scatter_fast(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
+                        const Spawn<float> sp = scatter_fast<(SHAPE > 0)>(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
                         bool alive = sp.has0;
                         if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
