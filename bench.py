@@ -322,12 +322,20 @@ def main():
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    phase = [0.0, 0.0, 0.0, 0.0]                        # this rank's wall time in set_scene / render / barrier / download
     for _ in range(args.steps):
+        ta = time.perf_counter()
         ctx.set_scene(hs)
+        tb = time.perf_counter()
         st = step()
+        tc = time.perf_counter()
         barrier()
+        td = time.perf_counter()
         if rank == 0:
             ctx.download(out=frame)
+        te = time.perf_counter()
+        for k, v in enumerate((tb - ta, tc - tb, td - tc, te - td)):
+            phase[k] += v * 1e3 / args.steps
     barrier()
     e2e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
     h2d = int(ctx_last(pyipt, ctx, "h2d"))
@@ -391,7 +399,8 @@ def main():
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
                        "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms,
+                    "rank0_ms": {"set_scene": phase[0], "render_call": phase[1], "wait_for_ranks": phase[2], "download": phase[3]}},
             "gpu_launches": tot_launches,
             "clocks": clocks,
             "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
