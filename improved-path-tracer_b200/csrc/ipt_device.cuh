@@ -327,7 +327,8 @@ __device__ __forceinline__ Hit<R> nearest_bvh(const SceneView<R>& sc, const floa
 // `p` must be 32-byte aligned.
 __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
 {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // evict_last: nodes and leaf records are what L1 should keep; the ray records are read with streaming loads
+    asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }

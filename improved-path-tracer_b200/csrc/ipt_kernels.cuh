@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
             if (!has) {
                 idx = base + __popc(idle & lt_mask);
                 if (idx < n_in) {
-                    const uint4 a = p.qin.base[idx], b = p.qin.base[p.qin.capacity + idx], c = p.qin.base[2u * p.qin.capacity + idx];
+                    // streaming loads / stores for the ray and hit records: read once, they should not displace BVH nodes in L1
+                    const uint4 a = __ldcs(p.qin.base + idx), b = __ldcs(p.qin.base + p.qin.capacity + idx), c = __ldcs(p.qin.base + 2u * p.qin.capacity + idx);
                     o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                     d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
                     onSurf = (c.z & META_ONSURF) != 0; self = c.w;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
             else node = stack[--sp];
         }
         if (has && done) {
-            p.hits[idx] = make_uint2(__float_as_uint(best.t), best.slot);
+            __stcs(p.hits + idx, make_uint2(__float_as_uint(best.t), best.slot));
             has = false;
         }
     }
