@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (the line then says so)")
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--leaf", type=int, default=4, help="primitives per BVH leaf (A/B knob; BVH scenes only)")
     ap.add_argument("--fp64", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
@@ -271,7 +272,7 @@ def main():
     if pyipt.lib().ipt_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device — there is no CPU path to time (use --impl reference for the CPU baseline)")
 
-    hs = pyipt.HostScene.load(scene_file(wl["scene"]), width=wl["width"], height=wl["height"])
+    hs = pyipt.HostScene.load(scene_file(wl["scene"]), width=wl["width"], height=wl["height"], leaf_size=args.leaf)
     W, H = hs.width, hs.height
     ctx = pyipt.Context(local)
     ctx.set_scene(hs)

@@ -66,17 +66,41 @@ struct Builder {
         if (count <= leaf_size) return first;
         // binned SAH over the centroid bounds, 16 bins per axis
         constexpr int NB = 16;
+        constexpr uint32_t SMALL = 16;
         int bestAxis = -1, bestSplit = -1;
         double bestCost = DBL_MAX;
-        if (count <= 12) {
-            // tiny ranges (the bulk of the nodes): median split along the widest centroid axis — initialising 48 bins
-            // per node cost more than the whole SAH evaluation down here
-            int ax = 0;
-            for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
-            const uint32_t mid = first + count / 2;
-            std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
-                             [ax](const Prim& a, const Prim& b) { return a.c[ax] < b.c[ax]; });
-            return mid;
+        if (count <= SMALL) {
+            // small ranges (the bulk of the nodes, and the ones whose boxes a ray grazes most often): exact SAH - sort by
+            // centroid along each axis and evaluate every split position (48 bins per node would cost more than this)
+            static const bool median_only = std::getenv("IPT_BVH_MEDIAN_SMALL") != nullptr;   // A/B knob: the old rule
+            if (median_only) {
+                int ax = 0;
+                for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+                const uint32_t mid = first + count / 2;
+                std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
+                                 [ax](const Prim& a, const Prim& b) { return a.c[ax] < b.c[ax]; });
+                return mid;
+            }
+            uint32_t order[3][SMALL];
+            double rightArea[SMALL];
+            int bestAx = -1; uint32_t bestK = 0;
+            for (int ax = 0; ax < 3; ax++) {
+                uint32_t* o = order[ax];
+                for (uint32_t i = 0; i < count; i++) o[i] = first + i;
+                std::sort(o, o + count, [&](uint32_t a, uint32_t b) { return prims[a].c[ax] < prims[b].c[ax] || (prims[a].c[ax] == prims[b].c[ax] && a < b); });
+                Box acc;
+                for (uint32_t i = count - 1; i > 0; i--) { acc.grow(prims[o[i]].box); rightArea[i] = acc.area(); }
+                acc = Box();
+                for (uint32_t k = 1; k < count; k++) {          // left = o[0..k), right = o[k..count)
+                    acc.grow(prims[o[k - 1]].box);
+                    const double cost = acc.area() * k + rightArea[k] * (count - k);
+                    if (cost < bestCost) { bestCost = cost; bestAx = ax; bestK = k; }
+                }
+            }
+            Prim tmp[SMALL];
+            for (uint32_t i = 0; i < count; i++) tmp[i] = prims[order[bestAx][i]];
+            for (uint32_t i = 0; i < count; i++) prims[first + i] = tmp[i];
+            return first + bestK;
         }
         // one pass over the primitives fills the bins of all three axes (chunks of a large range on several threads)
         struct Bins { Box bb[3][NB]; uint32_t bc[3][NB]; Bins() { std::memset(bc, 0, sizeof(bc)); } };
