@@ -715,8 +715,13 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     int grid_first = 0, grid_next = 0, split_grids[2] = {0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
     const bool pass_times = std::getenv("IPT_PASS_TIMES") != nullptr && !use_split;
-    std::vector<cudaEvent_t> pass_events;
-    float* clock_probe = nullptr;     // SM MHz sampled after each of the first 4096 passes
+    struct PassDiag {                 // released on every return path
+        std::vector<cudaEvent_t> events;
+        float* mhz = nullptr;         // SM MHz sampled after each of the first 4096 passes (IPT_PASS_CLOCKS)
+        ~PassDiag() { for (cudaEvent_t e : events) cudaEventDestroy(e); if (mhz) cudaFree(mhz); }
+    } diag;
+    std::vector<cudaEvent_t>& pass_events = diag.events;
+    float*& clock_probe = diag.mhz;
     if (pass_times && std::getenv("IPT_PASS_CLOCKS")) CK(cudaMallocManaged(&clock_probe, 4096 * sizeof(float)));
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
@@ -808,8 +813,6 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             std::fprintf(stderr, "\n");
         }
     }
-    if (clock_probe) cudaFree(clock_probe);
-    for (cudaEvent_t e : pass_events) cudaEventDestroy(e);
     unsigned long long traced[2] = {0, 0};
     CK(cudaMemcpy(traced, c->traced, 16, cudaMemcpyDeviceToHost));
     const size_t record_bytes = (sizeof(R) == 4 ? 48 : 96) + (defer ? (sizeof(R) == 4 ? 16 : 32) : 0);
