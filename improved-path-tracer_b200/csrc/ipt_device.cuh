@@ -23,6 +23,7 @@ static constexpr uint32_t RECT_BIT = 0x80000000u;
 // ray meta word: depth[0:8) lane[8:10) probe[10] onSurf[11] sample[12:28)
 static constexpr uint32_t META_PROBE = 1u << 10;
 static constexpr uint32_t META_ONSURF = 1u << 11;
+static constexpr uint32_t META_NEE = 1u << 28;    // the hit this ray started from sampled the emissive spheres explicitly
 static constexpr uint32_t META_DEAD = 1u << 31;   // padding slot at the end of a warp's output block (k_bounce_fast): not a ray
 __host__ __device__ inline uint32_t make_meta(uint32_t depth, uint32_t lane, bool probe, bool onSurf, uint32_t sample)
 {
@@ -48,6 +49,7 @@ __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b
 __device__ __forceinline__ float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
+template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) { return mk<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * rsqrt_(dot(a, a)); }
 
 // ---------------------------------------------------------------------------------------------- RNG
@@ -187,6 +189,8 @@ template <typename R> struct SceneView {
     const float4* nodes;           // BVH: 4 x float4 per node (see unpack in traverse), may be null
     uint32_t n_nodes;
     const float4* bslot;           // fp32 BVH leaf records, 2 x float4 per slot (see nearest_bvh_f32), may be null
+    const double* lights;          // IPT_FLAG_NEXT_EVENT: 8 doubles per emissive sphere {c.xyz, r, E.rgb, object index}
+    uint32_t n_lights;
 };
 
 template <typename R> struct Hit {

@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
     const uint32_t depth = p.depth;
     uint32_t* work = p.counters + WORK + depth;
     uint32_t* out_count = p.counters + CNT + depth + 1;
-    unsigned long long my_traced = 0;
+    unsigned long long my_traced = 0;       // warp-uniform: casts of the rays this warp processed
+    uint32_t my_shadow = 0;                 // per lane: visibility casts of the next-event extension
 
     for (;;) {
         uint32_t base = 0;
@@ -278,7 +279,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                     const bool isRect = (h.obj & RECT_BIT) != 0;
                     const uint32_t obj = h.obj & ~RECT_BIT;
                     const R4<R> m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
-                    if (m1.w != (R)0) {   // E of every hit counts (Renderer.cu:170,193,211)
+                    bool count_emission = m1.w != (R)0;   // E of every hit counts (Renderer.cu:170,193,211)
+                    if (count_emission && (r.meta & META_NEE) && !isRect) {
+                        // next-event extension: the hit this ray left sampled the emissive spheres it lies outside of
+                        // explicitly; their emission must not be counted a second time by the ray that found them by chance
+                        const R4<R> g = sc.geom[4 * (size_t)h.slot];
+                        const V3<R> oc = r.o - xyz(g);
+                        const R rr1 = g.w * ((R)1 + (R)1e-4);
+                        count_emission = !(dot(oc, oc) > rr1 * rr1);
+                    }
+                    if (count_emission) {
                         if (deep) acc = acc + mul(r.thr, xyz(m1));
                         else accumulate(p, r.pixel, mul(r.thr, xyz(m1)));
                     }
@@ -290,22 +300,65 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                         V3<R> nthr = mul(r.thr, xyz(m0));
                         const bool pending = deep && (acc.x != (R)0 || acc.y != (R)0 || acc.z != (R)0);
                         if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0 || pending) {
-                            const uint32_t lane_id = (r.meta >> 8) & 3u, sample = r.meta >> 12;
+                            const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                             const V3<R> P = r.o + r.d * h.t;                                       // :156,:179,:207
                             const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
                             const Spawn<R> sp = scatter<R>(isRect, sc.geom[4 * (size_t)h.slot], (int)m0.w, P, r.d, depth, rnd);
                             bool alive = sp.has0;
+                            const bool onS = isRect || fabs(dot(r.d, r.d) - (R)1) < (R)1e-3;
+                            bool nee = false;
+                            if constexpr (MODE != MODE_SHADE)
+                            if ((p.flags & 0x20u) && sc.n_lights && (int)m0.w == 0 && alive) {
+                                // IPT_FLAG_NEXT_EVENT (extension, off by default): at a diffuse hit one emissive sphere is
+                                // chosen uniformly and a direction uniformly inside the cone it subtends; the reference's
+                                // "diffuse" lobe (AObject.hpp:35-45: cube-normalised, flipped into the hemisphere of N,
+                                // weight = colour) has density 1 / (12 max|w_i|^3) there, which weights the sample.
+                                nee = true;
+                                const uint4 rl = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 2u, p.keys);
+                                const uint32_t li = min((uint32_t)(u23<R>(rl.x) * (R)sc.n_lights), sc.n_lights - 1u);
+                                const double* L = sc.lights + 8 * (size_t)li;
+                                const V3<R> lc = mk<R>((R)__ldg(L), (R)__ldg(L + 1), (R)__ldg(L + 2));
+                                const R lr = (R)__ldg(L + 3);
+                                const V3<R> w = lc - P;
+                                const R dist2 = dot(w, w), rr1 = lr * ((R)1 + (R)1e-4);
+                                if (dist2 > rr1 * rr1) {
+                                    const V3<R> g0n = xyz(sc.geom[4 * (size_t)h.slot]);
+                                    V3<R> N;                                                      // A.3 conventions, as in scatter()
+                                    if (isRect) N = dot(r.d, g0n) < (R)0 ? g0n : -g0n;
+                                    else { const V3<R> raw = normalize(P - g0n); N = dot(r.d, raw) < (R)0 ? -raw : raw; }
+                                    const R sin2 = lr * lr / dist2, cosmax = sqrt(fmax((R)0, (R)1 - sin2));
+                                    const R omc = sin2 / ((R)1 + cosmax);                          // 1 - cosmax without cancellation
+                                    const R omt = u23<R>(rl.y) * omc, ct = (R)1 - omt, st = sqrt(omt * ((R)1 + ct));
+                                    const R phi = (R)6.283185307179586 * u23<R>(rl.z);
+                                    const V3<R> a = w * ((R)1 / sqrt(dist2));
+                                    const V3<R> up = fabs(a.x) < (R)0.57 ? mk<R>(1, 0, 0) : mk<R>(0, 1, 0);
+                                    const V3<R> t1 = normalize(cross(a, up)), t2 = cross(a, t1);
+                                    const V3<R> wl = a * ct + (t1 * cos(phi) + t2 * sin(phi)) * st;
+                                    if (dot(wl, N) > (R)0) {
+                                        const R m = fmax(fabs(wl.x), fmax(fabs(wl.y), fabs(wl.z)));
+                                        const R lobe = (R)1 / ((R)12 * m * m * m);
+                                        const R inv_q = (R)6.283185307179586 * omc;               // 1 / cone density
+                                        my_shadow++;
+                                        const Hit<R> hs = nearest_any<R, MODE>(sc, top, n_top, P, wl, h.obj, onS);
+                                        if (hs.slot != NO_OBJECT && hs.obj == (uint32_t)__ldg(L + 7)) {
+                                            const V3<R> Le = mk<R>((R)__ldg(L + 4), (R)__ldg(L + 5), (R)__ldg(L + 6));
+                                            const V3<R> c = mul(nthr, Le) * (lobe * inv_q * (R)sc.n_lights);
+                                            if (deep) acc = acc + c;
+                                            else accumulate(p, r.pixel, c);
+                                        }
+                                    }
+                                }
+                            }
                             if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension, off by default)
                                 const R q = fmin((R)1, fmax((R)0.05, fmax(nthr.x, fmax(nthr.y, nthr.z))));
                                 const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
                                 if (u23<R>(rr.x) >= q) alive = false;
                                 else nthr = nthr * ((R)1 / q);
                             }
-                            const bool onS = isRect || fabs(dot(r.d, r.d) - (R)1) < (R)1e-3;
                             if (alive) {
                                 has0 = true;
                                 o0.o = P; o0.d = sp.d0; o0.thr = nthr * sp.w0; o0.pixel = r.pixel; o0.self = h.obj;
-                                o0.meta = make_meta(depth + 1, lane_id, false, onS, sample);
+                                o0.meta = make_meta(depth + 1, lane_id, false, onS, sample) | (nee ? META_NEE : 0u);
                                 if (sp.teleport) { o0.o = mk<R>(0, 0, 0); o0.self = NO_OBJECT; o0.meta = make_meta(depth + 1, lane_id, false, false, sample); }
                             }
                             if (sp.has1) {
@@ -341,6 +394,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
             }
         }
     }
+    my_traced += __reduce_add_sync(0xffffffffu, my_shadow);
     if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
 }
 

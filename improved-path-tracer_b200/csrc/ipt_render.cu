@@ -89,6 +89,8 @@ struct ipt_ctx {
     size_t hits_bytes = 0;
     uint32_t* counters = nullptr;
     unsigned long long* traced = nullptr;
+    double* lights = nullptr;               // IPT_FLAG_NEXT_EVENT: 8 doubles per emissive sphere {c.xyz, r, E.rgb, object index}
+    uint32_t n_lights = 0;
     uint32_t* fast_hint = nullptr;          // fast_schedule: bounces per pass the last batch settled on (cleared by set_scene)
     unsigned long long* frame = nullptr;
     size_t frame_pixels = 0;
@@ -176,7 +178,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
-    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->fast_hint); cudaFree(c->frame);
+    cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->fast_hint); cudaFree(c->lights); cudaFree(c->frame);
     cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -455,6 +457,23 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         for (int k = 0; k < 3; k++) { c->scene_lo[k] = lo[k]; c->scene_hi[k] = hi[k]; }
         c->mt_key = 0;   // a new scene invalidates the active micro-tile list
     }
+    {   // emissive spheres, for the next-event extension
+        std::vector<double> L;
+        for (uint32_t i = 0; i < s->n_spheres; i++) {
+            const uint32_t obj = s->sphere_object[i];
+            const double* E = s->mat_emission + 3 * (size_t)obj;
+            if (E[0] == 0.0 && E[1] == 0.0 && E[2] == 0.0) continue;
+            const double* sp = s->sphere_cxyzr + 4 * (size_t)i;
+            const double rec[8] = {sp[0], sp[1], sp[2], std::fabs(sp[3]), E[0], E[1], E[2], (double)obj};
+            L.insert(L.end(), rec, rec + 8);
+        }
+        cudaFree(c->lights); c->lights = nullptr;
+        c->n_lights = (uint32_t)(L.size() / 8);
+        if (c->n_lights) {
+            CK(cudaMalloc(&c->lights, L.size() * sizeof(double)));
+            CK(cudaMemcpy(c->lights, L.data(), L.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     c->have_scene = true;
     CK(cudaMemsetAsync(c->fast_hint, 0, 4, c->stream));   // a new scene: no survival measurement yet
     // frame buffers
@@ -620,6 +639,9 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.sc.slot_obj = c->slot_obj;
     kp.sc.n_slots = c->n_slots; kp.sc.n_spheres = c->n_spheres; kp.sc.n_objects = c->n_objects;
     kp.sc.nodes = c->nodes; kp.sc.n_nodes = c->n_nodes; kp.sc.bslot = std::getenv("IPT_GENERIC_KERNEL") ? nullptr : c->bslot;
+    // the next-event extension lives in the generic fused kernels only
+    const bool nee = (prm.flags & IPT_FLAG_NEXT_EVENT) != 0 && c->n_lights > 0;
+    kp.sc.lights = nee ? c->lights : nullptr; kp.sc.n_lights = nee ? c->n_lights : 0;
     // camera: vecZ = normalize(direction x orientation) in fp64 on the host (RenderController.cu:39)
     const double* D = c->cam + 3; const double* X = c->cam + 6;
     double Z[3] = {D[1] * X[2] - D[2] * X[1], D[2] * X[0] - D[0] * X[2], D[0] * X[1] - D[1] * X[0]};
@@ -684,7 +706,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     if (smem > 227 * 1024) { set_err("scene too large for the shared-memory path: pass a BVH"); return IPT_ERR_BAD_ARGUMENT; }
 
     // fp32 + BVH: split pipeline (raygen -> [extend with lane refill -> shade + compact] per bounce)
-    const bool use_split = sizeof(R) == 4 && bvh && kp.sc.bslot != nullptr && !defer && !std::getenv("IPT_FUSED_BVH");
+    const bool use_split = sizeof(R) == 4 && bvh && kp.sc.bslot != nullptr && !defer && !nee && !std::getenv("IPT_FUSED_BVH");
     if (use_split && (size_t)cap * 8 > c->hits_bytes) {
         cudaFree(c->hits); c->hits = nullptr; c->hits_bytes = 0;
         CK(cudaMalloc(&c->hits, (size_t)cap * 8));
@@ -694,7 +716,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : 12u;
     kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
-    const bool use_fast = sizeof(R) == 4 && !bvh && !defer && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
+    const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     const bool sync_passes = std::getenv("IPT_SYNC_PASSES") != nullptr;   // diagnostic: drain the GPU between passes
     // A/B knob: fixed number of bounces per pass for the fast kernel's passes from depth 2 on (default 0 = adaptive)
@@ -1058,6 +1080,7 @@ extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_
         sv.geom = (const R4<R>*)(f64 ? c->geom64 : c->geom32); sv.mat = (const R4<R>*)(f64 ? c->mat64 : c->mat32);
         sv.slot_obj = c->slot_obj; sv.n_slots = c->n_slots; sv.n_spheres = c->n_spheres; sv.n_objects = c->n_objects;
         sv.nodes = c->nodes; sv.n_nodes = c->n_nodes; sv.bslot = c->bslot;
+        sv.lights = nullptr; sv.n_lights = 0;
     };
     if (f64) {
         SceneView<double> sv; fill(sv, double());

@@ -17,6 +17,7 @@ FLAG_FP64 = 0x1
 FLAG_FLOAT_ACCUM = 0x4
 FLAG_RUSSIAN_ROULETTE = 0x8
 FLAG_STRATIFIED = 0x10
+FLAG_NEXT_EVENT = 0x20
 
 ABI_SYMBOLS = [
     "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_rgb8", "ipt_render_objects",

@@ -101,6 +101,11 @@ typedef struct ipt_scene {
 #define IPT_FLAG_STRATIFIED    0x10u /* extension, OFF for parity: the two camera jitters of sample i are stratified on a
                                         floor(sqrt(spp))^2 grid (unbiased: every stratum is sampled uniformly)           */
 
+#define IPT_FLAG_NEXT_EVENT    0x20u /* extension, OFF for parity: next-event estimation towards the emissive spheres at
+                                        diffuse hits (one light, one visibility cast per hit); the estimator stays
+                                        unbiased: the lobe's density is carried as a weight and a continuation ray does
+                                        not count the emission of a sphere that was sampled explicitly              */
+
 typedef struct ipt_params {
     uint32_t samples;        /* per pixel; reference CLI range 4..65535 (InputParser.cpp:14-24), any >= 1 accepted */
     uint32_t max_depth;      /* reference CLI range 3..255; 1..255 accepted                                        */

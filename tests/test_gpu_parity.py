@@ -268,6 +268,33 @@ def test_stratified_jitter_extension_is_unbiased(pyipt, oracle, ctx):
     assert not np.allclose(a, b)
 
 
+@pytest.mark.parametrize("name,fp64", [("spheres", False), ("maze", False), ("mirrors", True)])
+def test_next_event_extension_is_unbiased(pyipt, oracle, ctx, name, fp64):
+    """Extension (off by default): explicit sampling of the emissive spheres at diffuse hits.  The frame's mean, its
+    channel means and the means of a 4x4 grid of regions must not move (3.5 sigma over 6 seeds), although every diffuse
+    hit casts a second ray; on spheres.json, where the light is large and visible from everywhere, the noise drops."""
+    hs = pyipt.HostScene.load(oracle.scene_path(name), width=256, height=144)
+    ctx.set_scene(hs)
+    fl = pyipt.FLAG_FP64 if fp64 else 0
+    A, B = [], []
+    for seed in range(6):
+        s0 = ctx.render(48, 8, seed=seed, flags=fl); A.append(ctx.download())
+        s1 = ctx.render(48, 8, seed=seed, flags=fl | pyipt.FLAG_NEXT_EVENT); B.append(ctx.download())
+    A, B = np.array(A), np.array(B)
+    assert s1["traced_bounces"] > 1.2 * s0["traced_bounces"]
+
+    def check(f):
+        a, b = f(A), f(B)                      # [seed, ...]
+        sig = np.sqrt(a.var(axis=0, ddof=1) / 6 + b.var(axis=0, ddof=1) / 6)
+        assert np.all(np.abs(a.mean(axis=0) - b.mean(axis=0)) <= 3.5 * sig + 1e-12), (a.mean(axis=0), b.mean(axis=0), sig)
+    check(lambda X: X.mean(axis=(1, 2, 3)))
+    check(lambda X: X.mean(axis=(1, 2)))
+    check(lambda X: X.reshape(6, 4, 36, 4, 64, 3).mean(axis=(2, 4, 5)))
+    if name == "spheres":
+        ref = 0.5 * (A.mean(axis=0) + B.mean(axis=0))
+        assert np.mean((B[0] - ref) ** 2) < 0.8 * np.mean((A[0] - ref) ** 2)
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_full_size_properties(pyipt, oracle, ctx, name):
     """BASELINE configs 1-3 at full size (1280x720, d=10, s=40): fp32 vs fp64 on the same stream agree per pixel on
