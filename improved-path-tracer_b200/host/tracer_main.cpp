@@ -42,6 +42,10 @@ int main(int argc, char* argv[])
     params.max_depth = cli.max_depth;
     params.seed = std::getenv("IPT_SEED") ? std::strtoull(std::getenv("IPT_SEED"), nullptr, 10) : 123456ull;
     if (std::getenv("IPT_FP64") && std::atoi(std::getenv("IPT_FP64"))) params.flags |= IPT_FLAG_FP64;
+    // opt-in variance reduction (none of it is in the reference; the CLI grammar stays the reference's)
+    if (std::getenv("IPT_ROULETTE") && std::atoi(std::getenv("IPT_ROULETTE"))) params.flags |= IPT_FLAG_RUSSIAN_ROULETTE;
+    if (std::getenv("IPT_STRATIFIED") && std::atoi(std::getenv("IPT_STRATIFIED"))) params.flags |= IPT_FLAG_STRATIFIED;
+    if (std::getenv("IPT_NEXT_EVENT") && std::atoi(std::getenv("IPT_NEXT_EVENT"))) params.flags |= IPT_FLAG_NEXT_EVENT;
     int gpus = std::getenv("IPT_GPUS") ? std::atoi(std::getenv("IPT_GPUS")) : 1;
     if (gpus < 1) gpus = 1;
 
