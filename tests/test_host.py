@@ -325,3 +325,19 @@ def test_no_device_fails_loudly(pyipt, oracle):
         pyipt.Context(0)
     r = subprocess.run([os.path.join(ROOT, "improved-path-tracer_b200", "tracer"), oracle.scene_path("spheres")], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout == "CUDA capable device not found! Cannot continue"
+
+
+def test_bvh_traversal_equals_linear_scan_on_cpu(tmp_path):
+    """tools/bvh_stats.cpp in check mode: ordered traversal of the host-built BVH (the pruning k_extend_bvh uses) finds
+    exactly the nearest distance of a scan over every primitive, for leaf sizes 1, 4 and 16, on 6000 primitives."""
+    import subprocess, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scene_util import synthetic_scene, write_scene
+    exe = str(tmp_path / "bvh_stats")
+    pkg = os.path.join(ROOT, "improved-path-tracer_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "bvh_stats.cpp"),
+                    "-L" + pkg, "-lipt_b200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    path = write_scene(tmp_path / "syn6000.json", synthetic_scene(6000, seed=11, general_rects=True))
+    for leaf in (1, 4, 16):
+        r = subprocess.run([exe, path, str(leaf), "3000", "check"], capture_output=True, text=True)
+        assert r.returncode == 0 and "check: 0 of 3000" in r.stdout, r.stdout + r.stderr

@@ -1,13 +1,16 @@
 // bvh_stats — development tool: how much traversal work does the host-built BVH ask of a ray?
 //   g++ -O2 -std=c++17 -Iinclude tools/bvh_stats.cpp -Limproved-path-tracer_b200 -lipt_b200 -Wl,-rpath,$PWD/improved-path-tracer_b200 -o /tmp/bvh_stats
-//   /tmp/bvh_stats scene.json [leaf_size=4] [rays=20000]
+//   /tmp/bvh_stats scene.json [leaf_size=4] [rays=20000] [check]
 // Random rays inside the scene's bounding box, nearest hit by ordered (near child first) traversal with the same
-// pruning as k_extend_bvh (ipt_kernels.cuh); prints node visits, leaf visits and primitive tests per ray.  CPU only.
+// pruning as k_extend_bvh (ipt_kernels.cuh); prints node visits, leaf visits and primitive tests per ray.  With
+// `check` every ray is also tested against every primitive: the tree must report the same nearest distance (exit 1
+// otherwise) - the builder's boxes are conservative and every primitive sits in exactly one leaf.  CPU only.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 #include "ipt_host.h"
 
@@ -52,6 +55,7 @@ int main(int argc, char** argv)
     if (argc < 2) { std::fprintf(stderr, "usage: bvh_stats scene.json [leaf_size] [rays]\n"); return 2; }
     const uint32_t leaf = argc > 2 ? (uint32_t)std::atoi(argv[2]) : IPT_DEFAULT_LEAF_SIZE;
     const int n_rays = argc > 3 ? std::atoi(argv[3]) : 20000;
+    const bool check = argc > 4 && std::string(argv[4]) == "check";
     char msg[256];
     ipt_host_scene* hs = ipt_host_load_scene(argv[1], msg, sizeof msg);
     if (!hs) { std::fprintf(stderr, "%s\n", msg); return 1; }
@@ -62,7 +66,7 @@ int main(int argc, char** argv)
     std::uniform_real_distribution<double> U(0.0, 1.0);
     std::normal_distribution<double> N(0.0, 1.0);
     const double lo[3] = {30, -480, 30}, hi[3] = {1250, 680, 690};   // inside the synthetic room (scripts/make_synthetic_scene.py)
-    unsigned long long nodes = 0, leaves = 0, prims = 0, hits = 0;
+    unsigned long long nodes = 0, leaves = 0, prims = 0, hits = 0, wrong = 0;
     std::vector<int> stack(256);
     for (int i = 0; i < n_rays; i++) {
         Ray r;
@@ -94,9 +98,16 @@ int main(int argc, char** argv)
             }
         }
         hits += best < 1e20;
+        if (check) {
+            double lin = 1e20;
+            for (uint32_t k = 0; k < s->n_spheres; k++) lin = hit_prim(s, k, r, lin);
+            for (uint32_t k = 0; k < s->n_rects; k++) lin = hit_prim(s, 0x80000000u | k, r, lin);
+            wrong += lin != best;
+        }
     }
     std::printf("leaf_size %u: %u nodes; per ray: %.1f node visits, %.1f leaf visits, %.1f primitive tests; %.1f %% of the rays hit\n", leaf,
                 s->n_bvh_nodes, (double)nodes / n_rays, (double)leaves / n_rays, (double)prims / n_rays, 100.0 * hits / n_rays);
+    if (check) std::printf("check: %llu of %d rays differ from the linear scan\n", wrong, n_rays);
     ipt_host_free_scene(hs);
-    return 0;
+    return wrong ? 1 : 0;
 }
