@@ -4,6 +4,7 @@
 // the launches of a render and no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -983,10 +984,19 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
     std::vector<int> rcs(n_gpus, 0);
     std::vector<ipt_stats> sts(n_gpus);
     int rc = IPT_OK;
+    // IPT_VERBOSE: wall time of the phases of a one-shot render (what the reference's measure() region contains)
+    const bool verbose = std::getenv("IPT_VERBOSE") != nullptr;
+    auto T = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (verbose) std::fprintf(stderr, "[ipt] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - T).count());
+        T = now;
+    };
     for (int g = 0; g < n_gpus && rc == IPT_OK; g++) {
         ctx[g] = ipt_ctx_create(g);
         if (!ctx[g]) rc = IPT_ERR_CUDA;
     }
+    lap("contexts");
     bool host_merge = false;
     if (rc == IPT_OK) {
         // upload (one host thread per GPU), set gather targets, render
@@ -995,6 +1005,7 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
         for (auto& t : th) t.join();
         for (int g = 0; g < n_gpus; g++) if (rcs[g]) rc = rcs[g];
     }
+    lap("scene upload");
     if (rc == IPT_OK) {
         for (int g = 1; g < n_gpus; g++)
             if (ipt_ctx_set_gather_target(ctx[g], ctx[0]) != IPT_OK) host_merge = true;
@@ -1009,6 +1020,7 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
         for (auto& t : th) t.join();
         for (int g = 0; g < n_gpus; g++) if (rcs[g]) rc = rcs[g];
     }
+    lap("queues + kernels");
     if (rc == IPT_OK && out8) {
         if (host_merge && n_gpus > 1) { set_err("ipt_render_rgb8: needs peer access between the GPUs"); rc = IPT_ERR_CUDA; }
         else rc = ipt_ctx_download_rgb8(ctx[0], out8);
@@ -1047,7 +1059,9 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
         }
         stats->download_ms = ctx[0]->last.download_ms; stats->d2h_bytes = ctx[0]->last.d2h_bytes;
     }
+    lap("download");
     for (int g = 0; g < n_gpus; g++) ipt_ctx_destroy(ctx[g]);
+    lap("release");
     return rc;
 }
 
