@@ -268,12 +268,17 @@ def test_stratified_jitter_extension_is_unbiased(pyipt, oracle, ctx):
     assert not np.allclose(a, b)
 
 
-@pytest.mark.parametrize("name,fp64", [("spheres", False), ("maze", False), ("mirrors", True)])
-def test_next_event_extension_is_unbiased(pyipt, oracle, ctx, name, fp64):
+@pytest.mark.parametrize("name,fp64", [("spheres", False), ("maze", False), ("mirrors", True), ("bvh1500", False)])
+def test_next_event_extension_is_unbiased(pyipt, oracle, ctx, tmp_path, name, fp64):
     """Extension (off by default): explicit sampling of the emissive spheres at diffuse hits.  The frame's mean, its
     channel means and the means of a 4x4 grid of regions must not move (3.5 sigma over 6 seeds), although every diffuse
     hit casts a second ray; on spheres.json, where the light is large and visible from everywhere, the noise drops."""
-    hs = pyipt.HostScene.load(oracle.scene_path(name), width=256, height=144)
+    if name == "bvh1500":     # a BVH scene with ~45 small emissive spheres besides the big light (fused BVH kernel)
+        from scene_util import synthetic_scene, write_scene
+        hs = pyipt.HostScene.load(write_scene(tmp_path / "syn1500.json", synthetic_scene(1500, seed=3, width=256, height=144)))
+        assert hs.view.contents.n_bvh_nodes > 0
+    else:
+        hs = pyipt.HostScene.load(oracle.scene_path(name), width=256, height=144)
     ctx.set_scene(hs)
     fl = pyipt.FLAG_FP64 if fp64 else 0
     A, B = [], []
