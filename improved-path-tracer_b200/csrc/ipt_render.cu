@@ -864,14 +864,23 @@ extern "C" int ipt_ctx_render(ipt_ctx* c, const ipt_params* prm, ipt_stats* st)
     const uint32_t world = prm->world ? prm->world : 1;
     if (tile_w % 8 || tile_h % 4 || prm->rank >= world) { set_err("ipt_ctx_render: tile size must be a multiple of 8x4, rank < world"); return IPT_ERR_BAD_ARGUMENT; }
     CK(cudaSetDevice(c->device));
+    const auto t_call = std::chrono::steady_clock::now();
     uint32_t tiles_x = 0;
     int rc = build_tiles(c, tile_w, tile_h, prm->rank, world, &tiles_x);
     if (rc) return rc;
     const uint64_t mt_key = 1 + ((uint64_t)tile_w << 48 | (uint64_t)tile_h << 32 | (uint64_t)prm->rank << 16 | world) + (std::getenv("IPT_NO_CULL") ? (1ull << 62) : 0);
     rc = build_active_microtiles(c, tile_w, tile_h, tiles_x, mt_key);
     if (rc) return rc;
-    return (prm->flags & IPT_FLAG_FP64) ? render_typed<double>(c, *prm, tile_w, tile_h, tiles_x, st)
-                                        : render_typed<float>(c, *prm, tile_w, tile_h, tiles_x, st);
+    const auto t_tiles = std::chrono::steady_clock::now();
+    rc = (prm->flags & IPT_FLAG_FP64) ? render_typed<double>(c, *prm, tile_w, tile_h, tiles_x, st)
+                                      : render_typed<float>(c, *prm, tile_w, tile_h, tiles_x, st);
+    if (std::getenv("IPT_VERBOSE")) {   // host view of one resident render: tile lists, then enqueue + wait, against the kernels' own time
+        const auto t_end = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ipt] rank %u render: tile and micro-tile lists %.2f ms, enqueue + wait %.2f ms, kernels %.2f ms\n", prm->rank,
+                     std::chrono::duration<double, std::milli>(t_tiles - t_call).count(),
+                     std::chrono::duration<double, std::milli>(t_end - t_tiles).count(), c->last.render_ms);
+    }
+    return rc;
 }
 
 extern "C" void* ipt_alloc_pinned(size_t bytes)
