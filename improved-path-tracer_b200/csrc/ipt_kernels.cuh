@@ -633,7 +633,10 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 #define IPT_FAST_THREADS 256
 #define IPT_FAST_CTAS 3
 #endif
-template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? 3 : IPT_FAST_CTAS; };
+#ifndef IPT_FIRST_CTAS
+#define IPT_FIRST_CTAS 3
+#endif
+template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? IPT_FIRST_CTAS : IPT_FAST_CTAS; };
 
 template <bool FIRST, int SHAPE = 0>
 __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS) k_bounce_fast(const __grid_constant__ KParams<float> p)

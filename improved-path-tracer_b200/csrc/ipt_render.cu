@@ -828,6 +828,13 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         std::fprintf(stderr, "[ipt] pass times over %llu batch(es), ms per pass:", (unsigned long long)batches);
         for (uint32_t d = 0; d < passes_per_batch; d++) std::fprintf(stderr, " %.3f", per_depth[d]);
         std::fprintf(stderr, "  (total %.3f)\n", ms);
+        if (use_fast) {   // the schedule the device chose for the last batch: bounces per pass, and queue lengths read
+            std::vector<uint32_t> cnt(N_COUNTERS);
+            CK(cudaMemcpy(cnt.data(), c->counters, N_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            std::fprintf(stderr, "[ipt] last batch, bounces per pass (queue length read):");
+            for (uint32_t q = 0; q < passes_per_batch; q++) std::fprintf(stderr, " %u (%u)", cnt[WORK_EXTEND + q], cnt[CNT + q]);
+            std::fprintf(stderr, "\n");
+        }
         if (clock_probe) {
             std::vector<double> mhz(passes_per_batch, 0.0); std::vector<int> cnt(passes_per_batch, 0);
             for (size_t i = 0; i + 1 < pass_events.size() && i < 4096; i++) { mhz[i % passes_per_batch] += clock_probe[i]; cnt[i % passes_per_batch]++; }
