@@ -150,7 +150,7 @@ def run_reference(args, wl, rank):
     if not O.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_host.so not built"}))
         return
-    cores = os.cpu_count() or 1
+    cores = args.ref_threads or os.cpu_count() or 1
     W, H = wl["width"] or 1280, wl["height"] or 720
     n_cells = O.ref().ref_num_cells(W, H)
     # bounded sample: every `stride`-th reference cell (a cell = one reference CUDA thread's pixel rectangle,
@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
     ap.add_argument("--ref-stride", type=int, default=4, help="reference arm: 1/stride of the reference's 484 thread cells are rendered per step")
     ap.add_argument("--ref-spp", type=int, default=4)
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: host threads (0 = all cores)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
