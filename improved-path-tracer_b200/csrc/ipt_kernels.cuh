@@ -20,6 +20,7 @@
 // walks ~1900 pixels x spp x bounces serially with recursion (firstLayer/secondLayer/deepLayers, :149-225).
 #pragma once
 #include "ipt_device.cuh"
+#include "ipt_wide.h"
 
 namespace ipt {
 
@@ -70,6 +71,9 @@ template <typename R> struct KParams {
     uint32_t pass, n_passes;    // k_bounce_fast: index of this launch in its batch (0 and 1 are depth 0 and 1), launches per batch
     uint32_t* fast_hint;        // k_bounce_fast: bounces per pass the previous batch settled on (device word, 0 = none yet)
     FastHeader fast_hd;
+    const WideNode* wide;       // k_extend_wide: the 8-wide quantised tree (ipt_wide.h), null = 2-wide traversal (k_extend_bvh)
+    uint2* wide_spill;          // k_extend_wide: stack entries beyond WIDE_SMEM_STACK, wide_spill_cap per resident ray
+    uint32_t wide_spill_cap;
 };
 
 // Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
@@ -535,6 +539,242 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
         }
     }
     if (my_traced) atomicAdd(p.traced, my_traced);
+}
+
+// ---------------------------------------------------------------------------------------------- 8-wide traversal
+// Stage 2 of the split pipeline over the 8-wide quantised tree (ipt_wide.h).  LPR lanes (1, 2 or 4) walk one ray
+// together, each decoding 8 / LPR children of the node, so a warp holds 32 / LPR rays.  What the capture of the 2-wide
+// k_extend_bvh asked for (profiles/r02_ncu_extend_v7.txt: L1 wavefronts 86 %, L1 hit rate 3 %, 15 of 32 lanes
+// active, 391 warp instructions per ray, 53 node visits of 64 bytes per ray):
+//  * a third of the steps (13.5 node + 5.4 leaf steps per ray on the 1M-primitive scene, tools/wide_stats.cpp), and the
+//    lanes of a ray read ONE 128-byte node line per step: header by a broadcast 256-bit load, child boxes and links by
+//    one vector load each;
+//  * byte -> plane distance in two instructions: PRMT drops the byte into the mantissa of 2^23, and
+//    t = (2^23 + q) * A + (B - 2^23 A) with A = scale / d, B = (origin - o) / d per node and axis (the half step this
+//    can be off by is inside the builder's one-step padding); near / far byte chosen by the ray's direction signs, so
+//    the slab interval is two FMNMX3 and two FMNMX per child;
+//  * the nearest hit child (by entry distance) is entered at once, every other hit child is pushed - with its entry
+//    distance - on the PRIVATE stack of the lane that decoded it (no ranks, no cross-lane positions); a pop takes, of
+//    the lanes' tops, the one with the smallest entry distance and drops it if that lies behind the nearest hit so
+//    far.  On the CPU model this visits the same number of nodes as a single stack in the builder's per-octant order;
+//  * stacks live in shared memory ([entry][lane], conflict-free for equal depths), deeper entries spill to global
+//    memory (per lane, sized from the tree: WideTree::stack_need);
+//  * a leaf's primitives (<= 16) are tested LPR at a time by the same typed 32-byte records and the same arithmetic
+//    as the 2-wide path (test_bslot), reduced over the ray's lanes with the reference's tie rule (Renderer.cu:235):
+//    frames are bit-identical with the 2-wide traversal;
+//  * everything that steers a ray is identical in its lanes; node and leaf steps are warp-synchronous phases chosen by
+//    majority (descend_min), rays come from a warp-private chunk of the queue (one atomic per 64 rays).
+static constexpr uint32_t WIDE_CHUNK = 64;
+template <int LPR> struct WideCfg {
+    static constexpr int CPL = 8 / LPR;                               // children per lane
+    static constexpr uint32_t CAP = LPR == 4 ? 8 : (LPR == 2 ? 12 : 16);   // stack entries per lane in shared memory
+    static constexpr uint32_t SMEM = (BLOCK_THREADS / 32) * CAP * 32 * 8;
+};
+
+__device__ __forceinline__ float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+// 2^23 + (byte `sel & 3` of w) as a float: the byte goes into the low mantissa bits of 0x4B000000
+__device__ __forceinline__ float u8m(uint32_t w, uint32_t sel) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel)); return __uint_as_float(r); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; }
+
+template <int LPR> __device__ __forceinline__ void wide_load_children(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk);
+template <> __device__ __forceinline__ void wide_load_children<4>(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk)
+{
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(nd->q) + sub);
+    const int2 l = __ldg(reinterpret_cast<const int2*>(nd->link) + sub);
+    qw[0] = q.x; qw[1] = q.y; qw[2] = q.z; qw[3] = q.w; lk[0] = l.x; lk[1] = l.y;
+}
+template <> __device__ __forceinline__ void wide_load_children<2>(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk)
+{
+    float4 a, b;
+    ldg256(reinterpret_cast<const float4*>(nd->q) + 2 * sub, a, b);
+    const int4 l = __ldg(reinterpret_cast<const int4*>(nd->link) + sub);
+    qw[0] = __float_as_uint(a.x); qw[1] = __float_as_uint(a.y); qw[2] = __float_as_uint(a.z); qw[3] = __float_as_uint(a.w);
+    qw[4] = __float_as_uint(b.x); qw[5] = __float_as_uint(b.y); qw[6] = __float_as_uint(b.z); qw[7] = __float_as_uint(b.w);
+    lk[0] = l.x; lk[1] = l.y; lk[2] = l.z; lk[3] = l.w;
+}
+template <> __device__ __forceinline__ void wide_load_children<1>(const WideNode* nd, uint32_t, uint32_t* qw, int32_t* lk)
+{
+    float4 a, b, c, e, f, g;
+    ldg256(reinterpret_cast<const float4*>(nd->q), a, b);
+    ldg256(reinterpret_cast<const float4*>(nd->q) + 2, c, e);
+    ldg256(reinterpret_cast<const float4*>(nd->link), f, g);
+    const float4 v[4] = {a, b, c, e};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { qw[4 * i] = __float_as_uint(v[i].x); qw[4 * i + 1] = __float_as_uint(v[i].y); qw[4 * i + 2] = __float_as_uint(v[i].z); qw[4 * i + 3] = __float_as_uint(v[i].w); }
+    lk[0] = __float_as_int(f.x); lk[1] = __float_as_int(f.y); lk[2] = __float_as_int(f.z); lk[3] = __float_as_int(f.w);
+    lk[4] = __float_as_int(g.x); lk[5] = __float_as_int(g.y); lk[6] = __float_as_int(g.z); lk[7] = __float_as_int(g.w);
+}
+
+#ifndef IPT_WIDE_CTAS
+#define IPT_WIDE_CTAS 4
+#endif
+template <int LPR>
+__global__ void __launch_bounds__(BLOCK_THREADS, IPT_WIDE_CTAS) k_extend_wide(const __grid_constant__ KParams<float> p)
+{
+    constexpr int CPL = WideCfg<LPR>::CPL;
+    constexpr uint32_t CAP = WideCfg<LPR>::CAP;
+    constexpr uint32_t RAY_LANE0 = LPR == 4 ? 0x11111111u : (LPR == 2 ? 0x55555555u : 0xFFFFFFFFu);   // first lane of every ray
+    constexpr uint32_t N_RAYS = 32 / LPR;
+    extern __shared__ uint4 smem[];
+    const SceneView<float> sc = p.sc;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & (LPR - 1), gshift = lane & ~(uint32_t)(LPR - 1);
+    // this lane's stack: entry e at sbase + e * 256 (32 lanes x 8 bytes per entry row of the warp)
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + ((threadIdx.x >> 5) * CAP * 32u + lane) * 8u;
+    uint2* spill = p.wide_spill + ((size_t)blockIdx.x * BLOCK_THREADS + threadIdx.x) * p.wide_spill_cap;
+    const uint32_t n_in = p.counters[CNT + p.depth];
+    uint32_t* work = p.counters + WORK_EXTEND + p.depth;
+    const float slack = 1.0000004f, tiny = 1e-18f;
+
+    uint32_t pool_next = 0, pool_end = 0;                                    // warp-uniform: the warp's chunk of the queue
+    bool exhausted = false;
+    uint32_t my_traced = 0;
+
+    // per ray (identical in its lanes), except sp: the depth of this lane's own stack
+    bool has = false;
+    uint32_t idx = 0, self = NO_OBJECT, sp = 0;
+    bool onSurf = false;
+    int32_t cur = WIDE_EMPTY;
+    V3<float> o = mk<float>(0, 0, 0), d = o, bi = o, oi = o;
+    uint32_t selNx = 0, selFx = 0, selNy = 0, selFy = 0, selNz = 0, selFz = 0;
+    Hit<float> best;
+    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+
+    for (;;) {
+        // ---- refill: idle rays take the next indices of the warp's chunk
+        const uint32_t idle = __ballot_sync(0xffffffffu, !has) & RAY_LANE0;
+        if (!exhausted && (idle == RAY_LANE0 || (uint32_t)__popc(idle) >= p.refill_min)) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work, WIDE_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                pool_next = base; pool_end = min(base + WIDE_CHUNK, n_in);
+                exhausted = base >= n_in;
+            }
+            if (!exhausted) {
+                const uint32_t take = min((uint32_t)__popc(idle), pool_end - pool_next);
+                const uint32_t rank = __popc(idle & ((1u << gshift) - 1u));
+                if (!has && rank < take) {
+                    idx = pool_next + rank;
+                    const uint4 a = __ldcs(p.qin.base + idx), b = __ldcs(p.qin.base + p.qin.capacity + idx), c = __ldcs(p.qin.base + 2u * p.qin.capacity + idx);
+                    o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+                    d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+                    onSurf = (c.z & META_ONSURF) != 0; self = c.w;
+                    // box tests: t = plane * (1/d) - o * (1/d); components below 1e-18 become +-1e-18 so that no inf - inf
+                    // arises (the boxes are padded by far more than this moves a plane's t)
+                    bi = mk<float>(rcp_fast(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), rcp_fast(fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                                   rcp_fast(fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+                    oi = mk<float>(o.x * bi.x, o.y * bi.y, o.z * bi.z);
+                    const uint32_t sx = __float_as_uint(d.x) >> 31, sy = __float_as_uint(d.y) >> 31, sz = __float_as_uint(d.z) >> 31;
+                    selNx = 0x7650u | sx; selFx = 0x7651u ^ sx;              // word 0 of a child: lo.x hi.x lo.y hi.y
+                    selNy = 0x7652u | sy; selFy = 0x7653u ^ sy;
+                    selNz = 0x7650u | sz; selFz = 0x7651u ^ sz;              // word 1: lo.z hi.z
+                    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+                    sp = 0; cur = 0; has = true;
+                    if (sub == 0) my_traced++;
+                }
+                pool_next += take;
+            }
+        }
+        const bool at_inner = has && (uint32_t)cur < (uint32_t)WIDE_EMPTY, at_leaf = has && cur < 0;
+        const uint32_t inner = __ballot_sync(0xffffffffu, at_inner) & RAY_LANE0, leafy = __ballot_sync(0xffffffffu, at_leaf) & RAY_LANE0;
+        if ((inner | leafy) == 0) {
+            if (__ballot_sync(0xffffffffu, has) == 0 && exhausted) break;
+        } else if (inner && ((uint32_t)__popc(inner) >= p.descend_min || !leafy)) {
+            // ---- node phase (rays that are not at an inner node decode the root, which hits L1, and discard the result)
+            const WideNode* nd = p.wide + (at_inner ? cur : 0);
+            float4 h0, h1;
+            ldg256(reinterpret_cast<const float4*>(nd), h0, h1);
+            uint32_t qw[2 * CPL];
+            int32_t lk[CPL];
+            wide_load_children<LPR>(nd, sub, qw, lk);
+            const float Ax = h0.w * bi.x, Ay = h1.x * bi.y, Az = h1.y * bi.z;
+            const float Bx = fmaf(-8388608.f, Ax, fmaf(h0.x, bi.x, -oi.x)), By = fmaf(-8388608.f, Ay, fmaf(h0.y, bi.y, -oi.y)),
+                        Bz = fmaf(-8388608.f, Az, fmaf(h0.z, bi.z, -oi.z));
+            float tn[CPL];
+            uint32_t key[CPL];
+            uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                const uint32_t w0 = qw[2 * c], w1 = qw[2 * c + 1];
+                const float n = fmaxf(max3f(fmaf(u8m(w0, selNx), Ax, Bx), fmaf(u8m(w0, selNy), Ay, By), fmaf(u8m(w1, selNz), Az, Bz)), 0.f);
+                const float f = fminf(min3f(fmaf(u8m(w0, selFx), Ax, Bx), fmaf(u8m(w0, selFy), Ay, By), fmaf(u8m(w1, selFz), Az, Bz)), best.t) * slack;
+                tn[c] = n;
+                // entry distance with the slot in its low 3 bits: unique per child, ordered by distance
+                key[c] = (at_inner && n <= f) ? ((__float_as_uint(n) & ~7u) | (sub * CPL + c)) : 0xFFFFFFFFu;
+                kmin = min(kmin, key[c]);
+            }
+#pragma unroll
+            for (int x = 1; x < LPR; x <<= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, x));
+            // the link of the nearest hit child, from the lane that decoded it
+            int32_t next = lk[0];
+#pragma unroll
+            for (int c = 1; c < CPL; c++) next = (kmin & (CPL - 1)) == (uint32_t)c ? lk[c] : next;
+            if (LPR > 1) next = __shfl_sync(0xffffffffu, next, gshift | ((kmin & 7u) / CPL));
+            // every other hit child goes on this lane's own stack
+            if (sp + CPL <= CAP) {
+                // the common case: all of them fit the shared-memory part (predicated stores, no branches)
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const bool push = key[c] != 0xFFFFFFFFu && key[c] != kmin;
+                    if (push) sts64(sbase + sp * 256u, (uint32_t)lk[c], __float_as_uint(tn[c]));
+                    sp += push ? 1u : 0u;
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < CPL; c++) {
+                    if (key[c] != 0xFFFFFFFFu && key[c] != kmin) {
+                        if (sp < CAP) sts64(sbase + sp * 256u, (uint32_t)lk[c], __float_as_uint(tn[c]));
+                        else spill[sp - CAP] = make_uint2((uint32_t)lk[c], __float_as_uint(tn[c]));
+                        sp++;
+                    }
+                }
+            }
+            if (at_inner) cur = kmin == 0xFFFFFFFFu ? WIDE_EMPTY : next;
+        } else {
+            // ---- leaf phase: the ray's lanes test the leaf's primitives side by side
+            Hit<float> cand = best;
+            if (at_leaf) {
+                const uint32_t code = (uint32_t)(~cur), first = code >> 4, cnt = (code & 15u) + 1u;
+                const V3<float> inv = mk<float>(1.f / d.x, 1.f / d.y, 1.f / d.z);   // as the 2-wide path: +-inf for zero components (Plane.cu:55)
+                for (uint32_t k = sub; k < cnt; k += LPR) test_bslot(sc, first + k, o, d, inv, self, onSurf, cand);
+            }
+#pragma unroll
+            for (int x = 1; x < LPR; x <<= 1) {
+                const float ot = __shfl_xor_sync(0xffffffffu, cand.t, x);
+                const uint32_t oo = __shfl_xor_sync(0xffffffffu, cand.obj, x), os = __shfl_xor_sync(0xffffffffu, cand.slot, x);
+                const bool better = ot < cand.t || (ot == cand.t && oo < cand.obj);       // Renderer.cu:235: lowest object index wins ties
+                cand.t = better ? ot : cand.t; cand.obj = better ? oo : cand.obj; cand.slot = better ? os : cand.slot;
+            }
+            if (at_leaf) { best = cand; cur = WIDE_EMPTY; }
+        }
+        // ---- pop phase: a ray without a current node takes, of its lanes' stack tops, the one entered first; entries
+        // behind the nearest hit so far are dropped
+        for (;;) {
+            const bool want = has && cur == WIDE_EMPTY;
+            if (!__any_sync(0xffffffffu, want)) break;
+            uint2 e = make_uint2((uint32_t)WIDE_EMPTY, 0xFFFFFFFFu);
+            if (want && sp > 0) e = sp <= CAP ? lds64(sbase + (sp - 1u) * 256u) : spill[sp - 1u - CAP];
+            uint32_t k = (want && sp > 0) ? ((e.y & ~(uint32_t)(LPR - 1)) | sub) : 0xFFFFFFFFu;
+            const uint32_t mine_k = k;
+#pragma unroll
+            for (int x = 1; x < LPR; x <<= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, x));
+            const int32_t link = LPR > 1 ? __shfl_sync(0xffffffffu, (int32_t)e.x, gshift | (k & (LPR - 1))) : (int32_t)e.x;
+            if (want) {
+                if (k == 0xFFFFFFFFu) {
+                    // nothing pending: the ray is finished
+                    if (sub == 0) __stcs(p.hits + idx, make_uint2(__float_as_uint(best.t), best.slot));
+                    has = false;
+                } else {
+                    if (mine_k == k) sp--;
+                    if (__uint_as_float(k & ~(uint32_t)(LPR - 1)) <= best.t * slack) cur = link;
+                }
+            }
+        }
+    }
+    my_traced = __reduce_add_sync(0xffffffffu, my_traced);
+    if (lane == 0 && my_traced) atomicAdd(p.traced, (unsigned long long)my_traced);
 }
 
 // fp32 contributions are exact in fixed point without going through fp64: v * 2^k is exact in fp32.

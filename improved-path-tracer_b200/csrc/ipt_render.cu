@@ -79,6 +79,10 @@ struct ipt_ctx {
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
     float4* bslot = nullptr;         // fp32 BVH leaf records (2 x float4 per slot), built when the scene has a BVH
+    WideNode* wide = nullptr;        // the 8-wide quantised tree derived from the 2-wide one (ipt_wide.h), fp32 traversal
+    uint32_t n_wide = 0, wide_stack_need = 0, wide_depth = 0;
+    uint2* wide_spill = nullptr;     // stack entries beyond the shared-memory part, per resident ray of k_extend_wide
+    size_t wide_spill_bytes = 0;
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
     FastHeader fast_hd = {};
@@ -167,7 +171,8 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
 static void free_scene(ipt_ctx* c)
 {
     cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob); cudaFree(c->bslot);
-    c->bslot = nullptr;
+    cudaFree(c->wide);
+    c->bslot = nullptr; c->wide = nullptr; c->n_wide = 0;
     c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr; c->fast_blob = nullptr; c->fast_words = 0;
     std::memset(c->scene_bytes, 0, sizeof(c->scene_bytes));
     c->have_scene = false;
@@ -179,6 +184,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
+    cudaFree(c->wide_spill);
     cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->fast_hint); cudaFree(c->lights); cudaFree(c->frame);
     cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
@@ -392,7 +398,30 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
           }
         });
     }
-    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4};
+    // The 2-wide tree must be emitted parents first (children at higher indices: what host/bvh.cpp does; no cycles) and no
+    // deeper than the traversal stacks of the generic kernels (ipt_device.cuh: int stack[64]).
+    WideTree wt;
+    if (bvh) {
+        std::vector<uint8_t> depth(s->n_bvh_nodes, 0);
+        uint32_t deepest = 1;
+        depth[0] = 1;
+        for (uint32_t i = 0; i < s->n_bvh_nodes; i++)
+            for (int k = 0; k < 2; k++) {
+                const int32_t ch = s->bvh_nodes[i].child[k];
+                if (ch < 0) continue;
+                if ((uint32_t)ch <= i) { set_err("ipt_ctx_set_scene: BVH nodes must be ordered parents first (child index > parent index)"); return IPT_ERR_BAD_ARGUMENT; }
+                depth[ch] = (uint8_t)std::min(255, depth[i] + 1);
+                deepest = std::max<uint32_t>(deepest, depth[ch]);
+            }
+        if (deepest > 60) { set_err("ipt_ctx_set_scene: BVH deeper than 60 levels (traversal stacks hold 64 entries)"); return IPT_ERR_BAD_ARGUMENT; }
+        // the 8-wide quantised form the fp32 traversal walks (ipt_wide.h); IPT_BVH2=1 keeps the 2-wide traversal (A/B runs)
+        if (!std::getenv("IPT_BVH2")) {
+            const uint32_t leaf_max = std::getenv("IPT_WIDE_LEAF") ? (uint32_t)std::atoi(std::getenv("IPT_WIDE_LEAF")) : 8u;
+            if (const char* e = wide_collapse(s->bvh_nodes, s->n_bvh_nodes, n, leaf_max, wt)) { set_err(std::string("ipt_ctx_set_scene: ") + e); return IPT_ERR_BAD_ARGUMENT; }
+            if (wt.stack_need > 256) wt.nodes.clear();   // absurdly skewed tree: the 2-wide traversal handles it
+        }
+    }
+    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode)};
     if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom64) {
         free_scene(c);
         CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
@@ -401,6 +430,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
         if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
         if (!bs.empty()) CK(cudaMalloc(&c->bslot, bs.size() * 4));
+        if (!wt.nodes.empty()) CK(cudaMalloc(&c->wide, wt.nodes.size() * sizeof(WideNode)));
         std::memcpy(c->scene_bytes, want, sizeof(want));
     }
     c->have_scene = false;
@@ -411,6 +441,11 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
     if (!bs.empty()) CK(cudaMemcpyAsync(c->bslot, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!wt.nodes.empty()) CK(cudaMemcpyAsync(c->wide, wt.nodes.data(), wt.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
+    c->n_wide = (uint32_t)wt.nodes.size(); c->wide_stack_need = wt.stack_need; c->wide_depth = wt.depth;
+    if (std::getenv("IPT_VERBOSE") && bvh)
+        std::fprintf(stderr, "[ipt] 8-wide tree: %zu nodes (%.2f children per node), depth %u, stack need <= %u, from %u 2-wide nodes\n", wt.nodes.size(),
+                     wt.nodes.empty() ? 0.0 : wt.sum_children / wt.nodes.size(), wt.depth, wt.stack_need, s->n_bvh_nodes);
     c->fast_words = 0;
     if (!blob.empty()) {
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -422,7 +457,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total + blob.size() * 4 + bs.size() * 4;
+    c->last.h2d_bytes = total + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode);
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -511,9 +546,35 @@ static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_ca
 }
 
 // One batch of the split pipeline (fp32, BVH): raygen, then per bounce k_extend_bvh and k_bounce<MODE_SHADE>.
+// k_extend_wide<LPR>: launch by the number of lanes that walk a ray together (IPT_WIDE_LPR = 1 | 2 | 4, A/B knob)
+static int wide_lpr()
+{
+    const char* e = std::getenv("IPT_WIDE_LPR");
+    const int x = e ? std::atoi(e) : 2;
+    return (x == 1 || x == 4) ? x : 2;
+}
+static size_t wide_smem_bytes() { return wide_lpr() == 4 ? WideCfg<4>::SMEM : (wide_lpr() == 2 ? WideCfg<2>::SMEM : WideCfg<1>::SMEM); }
+static void (*wide_kernel())(const KParams<float>) { return wide_lpr() == 4 ? k_extend_wide<4> : (wide_lpr() == 2 ? k_extend_wide<2> : k_extend_wide<1>); }
+
 static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth, uint32_t cap, size_t smem_top, int* grids, uint64_t* launches)
 {
     auto shade = k_bounce<float, MODE_SHADE, false, false>;
+    if (kp.wide && grids[2] == 0) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_kernel(), BLOCK_THREADS, wide_smem_bytes()));
+        if (per_sm < 1) { set_err("k_extend_wide does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
+        grids[2] = per_sm * c->sm_count;
+        // stack entries beyond the shared-memory part: one area per resident ray
+        // stack entries beyond a lane's shared-memory part: no lane can hold more than the whole tree asks of a ray
+        kp.wide_spill_cap = std::max(1u, c->wide_stack_need);
+        const size_t need = (size_t)grids[2] * BLOCK_THREADS * kp.wide_spill_cap * sizeof(uint2);
+        if (need > c->wide_spill_bytes) {
+            cudaFree(c->wide_spill); c->wide_spill = nullptr; c->wide_spill_bytes = 0;
+            CK(cudaMalloc(&c->wide_spill, need));
+            c->wide_spill_bytes = need;
+        }
+        kp.wide_spill = c->wide_spill;
+    }
     if (grids[0] == 0) {
         CK(cudaFuncSetAttribute(k_extend_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_top));
         int per_sm = 0;
@@ -531,7 +592,8 @@ static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth
         kp.depth = d;
         kp.qin = Queue{c->q[d & 1], cap};
         kp.qout = Queue{c->q[(d + 1) & 1], cap};
-        k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
+        if (kp.wide) wide_kernel()<<<grids[2], BLOCK_THREADS, wide_smem_bytes(), c->stream>>>(kp);
+        else k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
         shade<<<grids[1], BLOCK_THREADS, 0, c->stream>>>(kp);
         *launches += 2;
     }
@@ -714,8 +776,11 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         c->hits_bytes = (size_t)cap * 8;
     }
     kp.hits = c->hits;
-    kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : 12u;
-    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
+    // 8-wide traversal (the default when the scene has a BVH): thresholds count rays of a warp (8), not lanes
+    kp.wide = (use_split && !std::getenv("IPT_BVH2")) ? c->wide : nullptr;
+    const uint32_t wide_rays = 32u / (uint32_t)wide_lpr();
+    kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : (kp.wide ? wide_rays * 5u / 8u : 12u);
+    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : (kp.wide ? wide_rays / 4u : 8u);
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
@@ -735,7 +800,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 16, c->stream));   // [0] casts, [1] queue records moved
     CK(cudaEventRecord(c->ev0, c->stream));
-    int grid_first = 0, grid_next = 0, split_grids[2] = {0, 0};
+    int grid_first = 0, grid_next = 0, split_grids[3] = {0, 0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
     const bool pass_times = std::getenv("IPT_PASS_TIMES") != nullptr && !use_split;
     struct PassDiag {                 // released on every return path
