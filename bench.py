@@ -202,6 +202,286 @@ def cpu_baseline(wl, seconds_budget=20.0):
         return {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
 
+class Comm:
+    """torch.distributed (NCCL) as plumbing only: barrier, max / sum over ranks, the one-off handle broadcast."""
+
+    def __init__(self, rank, local, world):
+        self.rank, self.local, self.world, self.dist, self.torch = rank, local, world, None, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.dist, self.torch = dist, torch
+            self.token = torch.zeros(1, device="cuda")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.all_reduce(self.token)
+            self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allmax(self, x):
+        return self._red(x, None if self.dist is None else self.dist.ReduceOp.MAX)
+
+    def allsum(self, x):
+        return self._red(x, None if self.dist is None else self.dist.ReduceOp.SUM)
+
+    def per_rank(self, x):
+        if self.dist is None:
+            return [x]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = x
+        self.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def bcast_obj(self, obj):
+        if self.dist is None:
+            return obj
+        box = [obj if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def frame_key(name, W, H, depth, spp, seed, fp64):
+    return f"{name}|{W}x{H}|d{depth}|s{spp}|seed{seed}|{'f64' if fp64 else 'f32'}"
+
+
+def committed_hash(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "frame_hashes.json"))).get(key)
+    except Exception:
+        return None
+
+
+def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=False):
+    """One workload: `warmup` untimed + `steps` timed device-resident renders, then `steps` end-to-end renders through
+    host buffers, then the frame check.  Every rank calls this; rank 0 gets the line (a dict), the others None."""
+    import hashlib
+    import numpy as np
+    import pyipt
+    rank, local, world = comm.rank, comm.local, comm.world
+    seed = 123456
+    hs = pyipt.HostScene.load(scene_file(wl["scene"]), width=wl["width"], height=wl["height"], leaf_size=args.leaf)
+    W, H = hs.width, hs.height
+    ctx = pyipt.Context(local)
+    ctx.set_scene(hs)
+    flags = pyipt.FLAG_FP64 if fp64 else 0
+    gather = "single GPU"
+    if world > 1:
+        # rank 0's frame is the gather target of every rank: its CUDA IPC handle goes round once
+        handle = comm.bcast_obj(ctx.export_frame() if rank == 0 else None)
+        if rank != 0:
+            ctx.set_gather_target_ipc(handle)
+        gather = "tiles stored into rank 0's frame over NVLink peer access (CUDA IPC), no collective"
+
+    def step(r=rank, w=world):
+        return ctx.render(wl["spp"], wl["depth"], seed=seed, flags=flags, rank=r, world=w, batch=args.batch)
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    comm.barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms, bounces, samples, launches, qbytes = 0.0, 0, 0, 0, 0
+    work = {"node_steps": 0, "leaf_steps": 0, "sphere_tests": 0, "rect_tests": 0}
+    for _ in range(steps):
+        st = step()
+        dev_ms += st["render_ms"]; bounces += st["traced_bounces"]; samples += st["samples"]; launches += st["kernel_launches"]
+        qbytes += st["queue_bytes"]
+        for k in work:
+            work[k] += st.get(k, 0)
+    comm.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.result()
+    ms_dev = comm.allmax(dev_ms) / steps                   # CUDA events on the rendering stream, max over ranks
+    per_rank_ms = comm.per_rank(dev_ms / steps)
+    per_rank_bounces = comm.per_rank(bounces / steps)
+    ms_wall = comm.allmax(t_wall * 1e3) / steps
+    tot_samples = comm.allsum(samples) / steps
+    tot_bounces = comm.allsum(bounces) / steps
+    tot_launches = int(comm.allsum(launches))
+    active_pixels = comm.allsum(st["active_pixels"])
+    my_bounces_per_step = bounces / steps
+
+    # ---- end to end through host buffers: scene upload from the host + kernels + gather + frame download, every step
+    out_dtype = np.float64 if fp64 else np.float32
+    pinned = pyipt.PinnedArray((H, W, 3), out_dtype) if rank == 0 else None   # the caller's frame buffer, page-locked
+    frame = pinned.array if pinned else None
+    comm.barrier()
+    t0 = time.perf_counter()
+    phase = [0.0, 0.0, 0.0, 0.0]                         # this rank's wall time in set_scene / render / barrier / download
+    e2e_events_ms = 0.0
+    for _ in range(steps):
+        ta = time.perf_counter()
+        ctx.set_scene(hs)
+        tb = time.perf_counter()
+        st = step()
+        tc = time.perf_counter()
+        comm.barrier()
+        td = time.perf_counter()
+        if rank == 0:
+            ctx.download(out=frame)
+        te = time.perf_counter()
+        e2e_events_ms += st["render_ms"] / steps
+        for k, v in enumerate((tb - ta, tc - tb, td - tc, te - td)):
+            phase[k] += v * 1e3 / steps
+    comm.barrier()
+    e2e_ms = comm.allmax((time.perf_counter() - t0) * 1e3) / steps
+    h2d = int(st["h2d_bytes"])                            # counted by the library from the buffers it copied (last ipt_ctx_set_scene)
+    d2h = int(H * W * 3 * np.dtype(out_dtype).itemsize)
+
+    # ---- the frame that came back (RenderController.cu:58-60: what is returned is what was rendered).  Its hash must be the
+    # same for every N (fixed-point accumulation: the frame does not depend on the schedule) and equal the committed one,
+    # which tests/test_gpu_parity.py::test_committed_frame_hashes ties to the oracle; at N > 1 rank 0 also renders the
+    # whole frame alone once and compares it with the gathered frame bit for bit.
+    check = None
+    if rank == 0:
+        sha = hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest()
+        key = frame_key(name, W, H, wl["depth"], wl["spp"], seed, fp64)
+        want = committed_hash(key)
+        check = {"key": key, "sha256": sha, "committed": want, "matches_committed": None if want is None else (want == sha),
+                 "nonzero_pixels": int(np.count_nonzero(frame.any(axis=2))), "mean": float(frame.mean(dtype=np.float64))}
+        if world > 1 and not args.no_rerender:
+            gathered = frame.copy()
+            step(0, 1)
+            ctx.download(out=frame)
+            check["n1_rerender_identical"] = bool(np.array_equal(gathered, frame))
+            check["n1_rerender_differing_pixels"] = int(np.count_nonzero((gathered != frame).any(axis=2)))
+    comm.barrier()
+
+    line = None
+    if rank == 0:
+        sm_count = 148
+        clk = (clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
+        # per-GPU figures of rank 0 (the kernels are the same on every rank)
+        r0_ms = dev_ms / steps
+        is_bvh = bool(hs.view.contents.n_bvh_nodes)
+        if is_bvh:
+            # SURVEY.md §8d with a BVH: 19 per sphere test + 31 per rectangle test + 18 per box test + 60 per bounce, with the
+            # tests COUNTED on the device during the timed renders (ipt_stats); an 8-wide node step decodes 8 child boxes
+            n_b = max(1.0, float(bounces))
+            flops_per_bounce = (19.0 * work["sphere_tests"] + 31.0 * work["rect_tests"] + 18.0 * 8.0 * work["node_steps"]) / n_b + 60.0
+            flops_note = (f"counted on the device: {work['node_steps'] / n_b:.2f} node steps (8 boxes each), {work['leaf_steps'] / n_b:.2f} leaf steps, "
+                          f"{work['sphere_tests'] / n_b:.2f} sphere + {work['rect_tests'] / n_b:.2f} rectangle tests per cast")
+        else:
+            flops_per_bounce, flops_note = float(wl["flops"]), "19 S + 31 R + 60 (brute force, SURVEY.md §8d)"
+        ach_fp32 = my_bounces_per_step * flops_per_bounce / (r0_ms * 1e-3) / 1e12
+        # HBM: the ray-queue bytes this design moves (records written + read back, counted on the device); a pass that
+        # advances rays k bounces in registers moves 96/k bytes per bounce
+        my_qbytes_per_step = qbytes / steps
+        ach_hbm = my_qbytes_per_step / (r0_ms * 1e-3) / 1e9
+        bytes_per_bounce = my_qbytes_per_step / max(1.0, my_bounces_per_step)
+        tr = {}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(name, {})
+        except Exception:
+            pass
+        # measured DRAM bytes of the dominant kernel per launch (one ncu --set full capture, profiles/dram_traffic.json)
+        traffic = tr.get("dram_bytes_per_launch")
+        wi = tr.get("warp_instructions_per_bounce")
+        kernel = tr.get("kernel", "k_extend_wide + k_bounce<MODE_SHADE>" if is_bvh else "k_bounce_fast")
+        roof_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_fp32 / fp32_peak,
+                     "traffic": traffic, "peak_source": "148 SM x 128 lanes x 2 x max SM clock (no measured fp32 figure in MEASURED_PEAKS.json)",
+                     "frac_at_observed_clock": ach_fp32 / (sm_count * FP32_LANES_PER_SM * 2 * clk * 1e6 / 1e12),
+                     "algorithmic_flops_per_bounce": flops_per_bounce, "flops_model": flops_note, "kernel": kernel}
+        roof_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak,
+                    "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_bounce": bytes_per_bounce,
+                    "one_bounce_per_pass_equivalent_gbs": my_bounces_per_step * BYTES_PER_BOUNCE / (r0_ms * 1e-3) / 1e9,
+                    "kernel": kernel + "; achieved = ray-queue bytes written + read (ipt_stats.queue_bytes) / sum of launch durations; "
+                              "traffic = measured DRAM bytes of one launch of the dominant kernel (ncu, profiles/dram_traffic.json)"}
+        binding = roof_hbm if roof_hbm["frac"] >= roof_fp32["frac"] else roof_fp32
+        if fp64:
+            # fp64 parity kernels: same algorithmic flops, against the fp64 pipe (64 lanes per SM x 2 x clock on B200)
+            fp64_peak = sm_count * 64 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
+            binding = dict(roof_fp32, bound="fp64", peak=fp64_peak, frac=ach_fp32 / fp64_peak, peak_source="148 SM x 64 fp64 lanes x 2 x max SM clock (computed)")
+            binding.pop("frac_at_observed_clock")
+        # what actually limits the typed-list kernel: warp-instruction issue slots (4 schedulers per SM, one per clock)
+        roof_issue = None
+        if wi and not fp64:
+            issue_peak = sm_count * 4 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e9
+            ach_issue = my_bounces_per_step * wi / (r0_ms * 1e-3) / 1e9
+            roof_issue = {"bound": "issue", "achieved": ach_issue, "peak": issue_peak, "unit": "G warp-inst/s", "frac": ach_issue / issue_peak,
+                          "warp_instructions_per_bounce": wi, "source": "instruction count of the ncu capture in profiles/ (smsp__inst_executed.sum / rays / bounces)"}
+        traced_samples = active_pixels * wl["spp"]
+        line = {
+            "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
+            "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
+            "traced_msamples_per_s": traced_samples / (ms_dev * 1e-3) / 1e6,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev, "ms_per_step_wall": ms_wall,
+            "ms_per_step_per_rank": per_rank_ms, "traced_bounces_per_rank": [int(b) for b in per_rank_bounces],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if fp64 else "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": name, "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],
+                       "samples_per_step": int(tot_samples), "traced_samples_per_step": int(traced_samples),
+                       "traced_bounces_per_step": int(tot_bounces),
+                       "pixels_with_camera_rays": int(active_pixels), "pixels": W * H,
+                       "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
+                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
+            "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "gbounces_per_s": tot_bounces / (e2e_ms * 1e-3) / 1e9,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "result": "fp64 frame" if fp64 else "fp32 frame", "rank0_kernel_ms_events": e2e_events_ms,
+                    "rank0_ms": {"set_scene": phase[0], "render_call": phase[1], "wait_for_ranks": phase[2], "download": phase[3]}},
+            "gpu_launches": tot_launches,
+            "frame_sha256": check["sha256"], "frame_check": check,
+            "clocks": clocks,
+            "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
+        }
+        if fp64:
+            line.pop("roofline_fp32")
+        if roof_issue:
+            line["roofline_issue"] = roof_issue
+        if with_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        frame = None
+        pinned.close()
+    ctx.close()
+    hs.close()
+    return line
+
+
+def compact(line):
+    """A per_config entry: the figures the grading contract asks for per scene, without the long descriptions."""
+    r = line["roofline"]
+    return {"name": line["config"]["name"], "workload": line["config"]["workload"], "dtype": line["dtype"], "frame": line["config"]["frame"],
+            "spp": line["config"]["spp"], "max_depth": line["config"]["max_depth"], "steps": line["steps"], "warmup": line["warmup"],
+            "msamples_per_s": line["value"], "gbounces_per_s": line["gbounces_per_s"], "traced_msamples_per_s": line["traced_msamples_per_s"],
+            "ms_per_step": line["ms_per_step"], "ms_per_step_per_rank": line["ms_per_step_per_rank"],
+            "e2e_msamples_per_s": line["e2e"]["value"], "e2e_gbounces_per_s": line["e2e"]["gbounces_per_s"], "e2e_ms_per_step": line["e2e"]["ms_per_step"],
+            "e2e_rank0_ms": line["e2e"]["rank0_ms"], "e2e_rank0_kernel_ms_events": line["e2e"]["rank0_kernel_ms_events"],
+            "h2d_bytes_per_step": line["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": line["e2e"]["d2h_bytes_per_step"],
+            "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
+            "roofline_fp32_frac": line.get("roofline_fp32", {}).get("frac"), "roofline_hbm_frac": line["roofline_hbm"]["frac"],
+            "flops_per_bounce": line.get("roofline_fp32", r).get("algorithmic_flops_per_bounce"),
+            "gpu_launches": line["gpu_launches"], "frame_sha256": line["frame_sha256"],
+            "frame_check": {k: line["frame_check"].get(k) for k in ("matches_committed", "n1_rerender_identical") if k in line["frame_check"]},
+            "sm_mhz": line["clocks"]["sm_mhz"], "throttle_reasons": line["clocks"]["reasons"]}
+
+
+# per_config of the default run: every BASELINE.json config next to the headline one (reduced spp where stated)
+PER_CONFIG = [("spheres", {}), ("mirrors", {}), ("maze", {}), ("spheres4k_x3", {"spp": 64}), ("synthetic1m", {"spp": 64})]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,8 +495,10 @@ def main():
     ap.add_argument("--leaf", type=int, default=4, help="primitives per BVH leaf (A/B knob; BVH scenes only)")
     ap.add_argument("--fp64", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="only the headline workload (the default run adds every BASELINE config as per_config)")
+    ap.add_argument("--no-rerender", action="store_true", help="N > 1: skip rank 0's single-GPU re-render that the gathered frame is compared with")
     ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
-    ap.add_argument("--ref-stride", type=int, default=4, help="reference arm: 1/stride of the reference's 484 thread cells are rendered per step")
+    ap.add_argument("--ref-stride", type=int, default=1, help="reference arm: 1/stride of the reference's 484 thread cells are rendered per step (1 = the whole frame)")
     ap.add_argument("--ref-spp", type=int, default=4)
     ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: host threads (0 = all cores)")
     args = ap.parse_args()
@@ -224,203 +506,50 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = dict(WORKLOADS[args.workload])
-    if args.spp:
-        wl["spp"] = args.spp
-        wl["desc"] += f" [spp overridden to {args.spp}]"
-    if args.depth:
-        wl["depth"] = args.depth
-        wl["desc"] += f" [depth overridden to {args.depth}]"
 
+    def workload(name, spp=0, depth=0):
+        wl = dict(WORKLOADS[name])
+        if spp:
+            wl["spp"] = spp
+            wl["desc"] += f" [spp overridden to {spp}]"
+        if depth:
+            wl["depth"] = depth
+            wl["desc"] += f" [depth overridden to {depth}]"
+        return wl
+
+    wl = workload(args.workload, args.spp, args.depth)
     if args.impl == "reference":
         run_reference(args, wl, rank)
         return
 
-    import numpy as np
     import pyipt
 
     if args.dry_run:
         dry_run(args, wl, rank, world, pyipt)
         return
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        token = torch.zeros(1, device="cuda")
-
-    def barrier():
-        if dist is not None:
-            dist.all_reduce(token)
-            torch.cuda.synchronize()
-
-    def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     if pyipt.lib().ipt_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device — there is no CPU path to time (use --impl reference for the CPU baseline)")
 
-    hs = pyipt.HostScene.load(scene_file(wl["scene"]), width=wl["width"], height=wl["height"], leaf_size=args.leaf)
-    W, H = hs.width, hs.height
-    ctx = pyipt.Context(local)
-    ctx.set_scene(hs)
-    flags = pyipt.FLAG_FP64 if args.fp64 else 0
-    gather = "single GPU"
-    if world > 1:
-        # rank 0's fp32 frame is the gather target of every rank: its CUDA IPC handle goes round once
-        handle = [ctx.export_frame() if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        if rank != 0:
-            ctx.set_gather_target_ipc(handle[0])
-        gather = "tiles stored into rank 0's frame over NVLink peer access (CUDA IPC), no collective"
-
-    def step():
-        return ctx.render(wl["spp"], wl["depth"], seed=123456, flags=flags, rank=rank, world=world, batch=args.batch)
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(physical_gpu_index(local))
-    sampler.start()
-    barrier()
-    t_wall0 = time.perf_counter()
-    dev_ms, bounces, samples, launches, qbytes = 0.0, 0, 0, 0, 0
-    for _ in range(args.steps):
-        st = step()
-        dev_ms += st["render_ms"]; bounces += st["traced_bounces"]; samples += st["samples"]; launches += st["kernel_launches"]
-        qbytes += st["queue_bytes"]
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.result()
-    ms_dev = allmax(dev_ms) / args.steps                 # CUDA events on the rendering stream, max over ranks
-    per_rank_ms = [dev_ms / args.steps]
-    if dist is not None:
-        t = torch.zeros(world, dtype=torch.float64, device="cuda")
-        t[rank] = dev_ms / args.steps
-        dist.all_reduce(t)
-        per_rank_ms = [float(x) for x in t.tolist()]
-    ms_wall = allmax(t_wall * 1e3) / args.steps
-    tot_samples = allsum(samples) / args.steps
-    tot_bounces = allsum(bounces) / args.steps
-    tot_launches = int(allsum(launches))
-    allsum_active = allsum(st["active_pixels"])
-    my_bounces_per_step = bounces / args.steps
-
-    # ---- end to end through host buffers: upload from pinned memory + kernels + gather + download, every step
-    pinned = pyipt.PinnedArray((H, W, 3), np.float32) if rank == 0 else None   # the caller's frame buffer, page-locked
-    frame = pinned.array if pinned else None
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    phase = [0.0, 0.0, 0.0, 0.0]                        # this rank's wall time in set_scene / render / barrier / download
-    for _ in range(args.steps):
-        ta = time.perf_counter()
-        ctx.set_scene(hs)
-        tb = time.perf_counter()
-        st = step()
-        tc = time.perf_counter()
-        barrier()
-        td = time.perf_counter()
-        if rank == 0:
-            ctx.download(out=frame)
-        te = time.perf_counter()
-        for k, v in enumerate((tb - ta, tc - tb, td - tc, te - td)):
-            phase[k] += v * 1e3 / args.steps
-    barrier()
-    e2e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
-    h2d = int(ctx_last(pyipt, ctx, "h2d"))
-    d2h = int(H * W * 3 * 4)
-
-    if rank == 0:
-        sm_count = 148
-        clk = (clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
-        # per-GPU figures of rank 0 (the kernels are the same on every rank)
-        r0_ms = dev_ms / args.steps
-        ach_fp32 = my_bounces_per_step * wl["flops"] / (r0_ms * 1e-3) / 1e12
-        # HBM: the ray-queue bytes this design moves (records written + read back, counted on the device); a pass that
-        # advances rays k bounces in registers moves 96/k bytes per bounce
-        my_qbytes_per_step = qbytes / args.steps
-        ach_hbm = my_qbytes_per_step / (r0_ms * 1e-3) / 1e9
-        bytes_per_bounce = my_qbytes_per_step / max(1.0, my_bounces_per_step)
-        traffic = wi = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-            traffic = tr.get(args.workload, {}).get("dram_bytes_per_queue_byte")
-            wi = tr.get(args.workload, {}).get("warp_instructions_per_bounce")
-        except Exception:
-            pass
-        roof_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_fp32 / fp32_peak,
-                     "traffic": None, "peak_source": "148 SM x 128 lanes x 2 x max SM clock (no measured fp32 figure in MEASURED_PEAKS.json)",
-                     "frac_at_observed_clock": ach_fp32 / (sm_count * FP32_LANES_PER_SM * 2 * clk * 1e6 / 1e12),
-                     "algorithmic_flops_per_bounce": wl["flops"]}
-        roof_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak,
-                    "traffic": None if traffic is None else traffic * my_qbytes_per_step / max(1, launches / args.steps),
-                    "peak_source": hbm_src, "algorithmic_bytes_per_bounce": bytes_per_bounce,
-                    "one_bounce_per_pass_equivalent_gbs": my_bounces_per_step * BYTES_PER_BOUNCE / (r0_ms * 1e-3) / 1e9,
-                    "kernel": ("k_extend_bvh + k_bounce<MODE_SHADE>" if wl["scene"] == "synthetic1m" else "k_bounce_fast") +
-                              "; achieved = ray-queue bytes written + read (ipt_stats.queue_bytes) / sum of launch durations; "
-                              "traffic = measured DRAM bytes (ncu) per queue byte x queue bytes per launch"}
-        binding = roof_hbm if roof_hbm["frac"] >= roof_fp32["frac"] else roof_fp32
-        # what actually limits the typed-list kernel: warp-instruction issue slots (4 schedulers per SM, one per clock)
-        roof_issue = None
-        if wi:
-            issue_peak = sm_count * 4 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e9
-            ach_issue = my_bounces_per_step * wi / (r0_ms * 1e-3) / 1e9
-            roof_issue = {"bound": "issue", "achieved": ach_issue, "peak": issue_peak, "unit": "G warp-inst/s", "frac": ach_issue / issue_peak,
-                          "warp_instructions_per_bounce": wi, "source": "instruction count of the ncu capture in profiles/ (smsp__inst_executed.sum / rays / bounces)"}
-        line = {
-            "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
-            "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "ms_per_step_wall": ms_wall,
-            "ms_per_step_per_rank": per_rank_ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "frame": [W, H], "spp": wl["spp"], "max_depth": wl["depth"],
-                       "samples_per_step": int(tot_samples), "traced_bounces_per_step": int(tot_bounces),
-                       "pixels_with_camera_rays": int(allsum_active), "pixels": W * H,
-                       "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
-                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
-            "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms,
-                    "rank0_ms": {"set_scene": phase[0], "render_call": phase[1], "wait_for_ranks": phase[2], "download": phase[3]}},
-            "gpu_launches": tot_launches,
-            "clocks": clocks,
-            "roofline": binding, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm,
-        }
-        if roof_issue:
-            line["roofline_issue"] = roof_issue
-        if not wl["flops"]:
-            line["roofline"] = roof_hbm
-            line.pop("roofline_fp32")
-        if world == 1 and not args.no_cpu_baseline and wl["scene"] != "synthetic1m":
-            line["cpu_baseline"] = cpu_baseline(wl)
+    comm = Comm(rank, local, world)
+    line = measure(args, args.workload, wl, comm, args.steps, args.warmup, fp64=args.fp64,
+                   with_cpu_baseline=(world == 1 and not args.no_cpu_baseline and wl["scene"] != "synthetic1m"))
+    # the default run also answers "bounces/s per scene" (test_automation.py:18-20: the reference's matrix is per scene) and gives
+    # the reference's own precision a number: every other BASELINE config, and the headline workload in fp64 at reduced spp
+    default_run = args.workload == "spheres4k" and not (args.spp or args.depth or args.fp64 or args.batch)
+    if default_run and not args.no_per_config:
+        per = []
+        for name, over in PER_CONFIG:
+            sub = measure(args, name, workload(name, **over), comm, 3, 2)
+            if sub:
+                per.append(compact(sub))
+        sub = measure(args, "spheres4k", workload("spheres4k", spp=16), comm, 2, 1, fp64=True)
+        if sub:
+            per.append(compact(sub))
+        if line:
+            line["per_config"] = per
+    if line:
         print(json.dumps(line))
-        frame = None
-        pinned.close()
-    ctx.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    comm.close()
 
 
 def shard(pyipt, W, H, tile_w, tile_h, rank, world):
@@ -456,13 +585,6 @@ def dry_run(args, wl, rank, world, pyipt):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def ctx_last(pyipt, ctx, what):
-    # bytes uploaded by the last ipt_ctx_set_scene: geometry (fp64+fp32), materials, slot ids, BVH nodes
-    v = ctx.scene.view.contents
-    n = v.n_objects
-    return n * (16 * 8 + 16 * 4 + 8 * 8 + 8 * 4) + ((n + 3) // 4) * 16 + v.n_bvh_nodes * 64
 
 
 if __name__ == "__main__":

@@ -347,11 +347,12 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
 //      general rectangle        a = {-, -, -, -}         b = {kind 4, obj|RECT, -, -}          -> generic 64-B slot
 //  Ties in t across primitives are resolved by object index explicitly (traversal order is arbitrary).
 __device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t slot, const V3<float>& o, const V3<float>& d,
-                                           const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best)
+                                           const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best, uint32_t& n_sphere_tests)
 {
     float4 a, b;
     ldg256(sc.bslot + 2 * (size_t)slot, a, b);
     const uint32_t kind = __float_as_uint(b.x), obj = __float_as_uint(b.y);
+    n_sphere_tests += kind == 0 ? 1u : 0u;          // work counters of ipt_stats (the flops model of bench.py)
     float t;
     bool hit;
     if (kind == 0) {
@@ -396,6 +397,7 @@ __device__ __forceinline__ Hit<float> nearest_bvh_f32(const SceneView<float>& sc
     int stack[64];
     int sp = 0;
     int node = 0;
+    uint32_t n_sph = 0;                                  // the fused kernel does not report work counters
     const float slack = 1.0000004f;
     for (;;) {
         while (node >= 0) {
@@ -428,7 +430,7 @@ __device__ __forceinline__ Hit<float> nearest_bvh_f32(const SceneView<float>& sc
         // leaf: ~node = first_slot * 16 + (count - 1)
         const uint32_t code = (uint32_t)(~node);
         const uint32_t first = code >> 4, cnt = (code & 15u) + 1u;
-        for (uint32_t s = first; s < first + cnt; s++) test_bslot(sc, s, o, d, inv, self, onSurf, best);
+        for (uint32_t s = first; s < first + cnt; s++) test_bslot(sc, s, o, d, inv, self, onSurf, best, n_sph);
         if (sp == 0) return best;
         node = stack[--sp];
     }

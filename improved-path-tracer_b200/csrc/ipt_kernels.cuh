@@ -71,9 +71,10 @@ template <typename R> struct KParams {
     uint32_t pass, n_passes;    // k_bounce_fast: index of this launch in its batch (0 and 1 are depth 0 and 1), launches per batch
     uint32_t* fast_hint;        // k_bounce_fast: bounces per pass the previous batch settled on (device word, 0 = none yet)
     FastHeader fast_hd;
-    const WideNode* wide;       // k_extend_wide: the 8-wide quantised tree (ipt_wide.h), null = 2-wide traversal (k_extend_bvh)
-    uint2* wide_spill;          // k_extend_wide: stack entries beyond WIDE_SMEM_STACK, wide_spill_cap per resident ray
+    const WideNode* wide;       // k_extend_cw: the 8-wide quantised tree (ipt_wide.h), null = 2-wide traversal (k_extend_bvh)
+    uint2* wide_spill;          // k_extend_cw: stack entries beyond CW_STACK, wide_spill_cap per resident lane
     uint32_t wide_spill_cap;
+    uint32_t leaf_min;          // k_extend_cw: lanes with a primitive to test that make a primitive step worth a warp instruction
 };
 
 // Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
@@ -402,6 +403,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
     if (lane == 0 && my_traced) atomicAdd(p.traced, my_traced);
 }
 
+// Work counters of the traversal kernels (ipt_stats.node_steps ...): warp sums, one atomic per counter and warp.
+// stats[] = {casts, queue records, node steps, box tests, leaf steps, sphere tests, rectangle tests}
+__device__ __forceinline__ void add_work(unsigned long long* stats, uint32_t nodes, uint32_t boxes, uint32_t leaves, uint32_t sph, uint32_t rect)
+{
+    nodes = __reduce_add_sync(0xffffffffu, nodes); boxes = __reduce_add_sync(0xffffffffu, boxes); leaves = __reduce_add_sync(0xffffffffu, leaves);
+    sph = __reduce_add_sync(0xffffffffu, sph); rect = __reduce_add_sync(0xffffffffu, rect);
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(stats + 2, (unsigned long long)nodes); atomicAdd(stats + 3, (unsigned long long)boxes); atomicAdd(stats + 4, (unsigned long long)leaves);
+        atomicAdd(stats + 5, (unsigned long long)sph); atomicAdd(stats + 6, (unsigned long long)rect);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- split pipeline (BVH, fp32)
 // Stage 1 of the split wavefront step used for BVH scenes: camera rays -> queue (compacted, one atomic per warp).
 template <typename R>
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
     const uint32_t n_in = p.counters[CNT + p.depth];
     uint32_t* work = p.counters + WORK_EXTEND + p.depth;
     unsigned long long my_traced = 0;
+    uint32_t w_nodes = 0, w_leaves = 0, w_prims = 0, w_sph = 0;   // work counters of ipt_stats (per lane)
 
     int stack[64];
     int sp = 0, node = 0;
@@ -506,6 +520,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
                 const float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t)) * slack;
                 const bool h0 = n0 <= f0, h1 = n1 <= f1;
                 const int c0 = __float_as_int(e.x), c1 = __float_as_int(e.y);
+                w_nodes++;
                 if (h0 && h1) {
                     const bool swap = n1 < n0;
                     stack[sp++] = swap ? c0 : c1;
@@ -525,9 +540,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
         if (at_leaf) {
             const uint32_t code = (uint32_t)(~node);
             s_cur = code >> 4; s_end = s_cur + (code & 15u) + 1u;
+            w_leaves++; w_prims += s_end - s_cur;
         }
         while (__any_sync(0xffffffffu, s_cur < s_end)) {
-            if (s_cur < s_end) { test_bslot(sc, s_cur, o, d, inv, self, onSurf, best); s_cur++; }
+            if (s_cur < s_end) { test_bslot(sc, s_cur, o, d, inv, self, onSurf, best, w_sph); s_cur++; }
         }
         if (at_leaf) {
             if (sp == 0) done = true;
@@ -539,37 +555,32 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
         }
     }
     if (my_traced) atomicAdd(p.traced, my_traced);
+    add_work(p.traced, w_nodes, 2u * w_nodes, w_leaves, w_sph, w_prims - w_sph);
 }
 
 // ---------------------------------------------------------------------------------------------- 8-wide traversal
-// Stage 2 of the split pipeline over the 8-wide quantised tree (ipt_wide.h).  LPR lanes (1, 2 or 4) walk one ray
-// together, each decoding 8 / LPR children of the node, so a warp holds 32 / LPR rays.  What the capture of the 2-wide
-// k_extend_bvh asked for (profiles/r02_ncu_extend_v7.txt: L1 wavefronts 86 %, L1 hit rate 3 %, 15 of 32 lanes
-// active, 391 warp instructions per ray, 53 node visits of 64 bytes per ray):
-//  * a third of the steps (13.5 node + 5.4 leaf steps per ray on the 1M-primitive scene, tools/wide_stats.cpp), and the
-//    lanes of a ray read ONE 128-byte node line per step: header by a broadcast 256-bit load, child boxes and links by
-//    one vector load each;
-//  * byte -> plane distance in two instructions: PRMT drops the byte into the mantissa of 2^23, and
+// Stage 2 of the split pipeline over the 8-wide quantised tree (ipt_wide.h): one ray per lane, persistent warps with
+// lane-level refill as in k_extend_bvh.  What the capture of the 2-wide kernel asked for
+// (profiles/r02_ncu_extend_v7.txt: L1 wavefronts 86 %, hit rate 3 %, 17 of 32 lanes, 455 warp instructions per ray, 53
+// node visits of 64 bytes per ray) and what a first 8-wide kernel taught (profiles/r02_ncu_wide_v1.txt: 2-4 lanes per
+// ray, a stack entry with its entry distance per hit child, a pop loop that culls by distance - 2.2x the instructions of
+// the 2-wide kernel, 1.1 against 1.65 Gbounces/s):
+//  * a node step reads 96 bytes of ONE line with three 256-bit loads and tests eight quantised child boxes; byte ->
+//    plane distance in two instructions: PRMT drops the byte into the mantissa of 2^23 and
 //    t = (2^23 + q) * A + (B - 2^23 A) with A = scale / d, B = (origin - o) / d per node and axis (the half step this
-//    can be off by is inside the builder's one-step padding); near / far byte chosen by the ray's direction signs, so
-//    the slab interval is two FMNMX3 and two FMNMX per child;
-//  * the nearest hit child (by entry distance) is entered at once, every other hit child is pushed - with its entry
-//    distance - on the PRIVATE stack of the lane that decoded it (no ranks, no cross-lane positions); a pop takes, of
-//    the lanes' tops, the one with the smallest entry distance and drops it if that lies behind the nearest hit so
-//    far.  On the CPU model this visits the same number of nodes as a single stack in the builder's per-octant order;
-//  * stacks live in shared memory ([entry][lane], conflict-free for equal depths), deeper entries spill to global
-//    memory (per lane, sized from the tree: WideTree::stack_need);
-//  * a leaf's primitives (<= 16) are tested LPR at a time by the same typed 32-byte records and the same arithmetic
-//    as the 2-wide path (test_bslot), reduced over the ray's lanes with the reference's tie rule (Renderer.cu:235):
-//    frames are bit-identical with the 2-wide traversal;
-//  * everything that steers a ray is identical in its lanes; node and leaf steps are warp-synchronous phases chosen by
-//    majority (descend_min), rays come from a warp-private chunk of the queue (one atomic per 64 rays).
-static constexpr uint32_t WIDE_CHUNK = 64;
-template <int LPR> struct WideCfg {
-    static constexpr int CPL = 8 / LPR;                               // children per lane
-    static constexpr uint32_t CAP = LPR == 4 ? 8 : (LPR == 2 ? 12 : 16);   // stack entries per lane in shared memory
-    static constexpr uint32_t SMEM = (BLOCK_THREADS / 32) * CAP * 32 * 8;
-};
+//    can be off by is inside the builder's one-step padding); near / far byte chosen by PRMT selectors that depend only
+//    on the ray's direction signs;
+//  * no per-child stack entries and no distance sort (Ylitie, Karras, Laine 2017): the hit inner children of a node are
+//    ONE 64-bit entry {child_base | imask, hit bits}; the bits are permuted by the ray's octant (a 2 KB table in shared
+//    memory) so that "highest bit first" is roughly front to back; a child index is child_base + popc(imask below slot);
+//  * the hit leaf children become a bit mask over the node's (consecutive) primitive slots, tested before the walk goes
+//    on: one primitive per lane and iteration, by the same typed records and arithmetic as the 2-wide path (test_bslot)
+//    and the reference's tie rule (Renderer.cu:235) - frames are bit-identical with the 2-wide traversal;
+//  * stacks live in shared memory ([entry][lane], conflict-free), one entry per level: 12 entries, deeper ones spill;
+//  * node steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (descend_min,
+//    leaf_min) or nobody wants the other.
+static constexpr uint32_t CW_STACK = 12;                 // stack entries per lane in shared memory
+static constexpr uint32_t CW_SMEM = 2048 + BLOCK_THREADS * CW_STACK * 8;
 
 __device__ __forceinline__ float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
@@ -578,85 +589,60 @@ __device__ __forceinline__ float u8m(uint32_t w, uint32_t sel) { uint32_t r; asm
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; }
 
-template <int LPR> __device__ __forceinline__ void wide_load_children(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk);
-template <> __device__ __forceinline__ void wide_load_children<4>(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk)
-{
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(nd->q) + sub);
-    const int2 l = __ldg(reinterpret_cast<const int2*>(nd->link) + sub);
-    qw[0] = q.x; qw[1] = q.y; qw[2] = q.z; qw[3] = q.w; lk[0] = l.x; lk[1] = l.y;
-}
-template <> __device__ __forceinline__ void wide_load_children<2>(const WideNode* nd, uint32_t sub, uint32_t* qw, int32_t* lk)
-{
-    float4 a, b;
-    ldg256(reinterpret_cast<const float4*>(nd->q) + 2 * sub, a, b);
-    const int4 l = __ldg(reinterpret_cast<const int4*>(nd->link) + sub);
-    qw[0] = __float_as_uint(a.x); qw[1] = __float_as_uint(a.y); qw[2] = __float_as_uint(a.z); qw[3] = __float_as_uint(a.w);
-    qw[4] = __float_as_uint(b.x); qw[5] = __float_as_uint(b.y); qw[6] = __float_as_uint(b.z); qw[7] = __float_as_uint(b.w);
-    lk[0] = l.x; lk[1] = l.y; lk[2] = l.z; lk[3] = l.w;
-}
-template <> __device__ __forceinline__ void wide_load_children<1>(const WideNode* nd, uint32_t, uint32_t* qw, int32_t* lk)
-{
-    float4 a, b, c, e, f, g;
-    ldg256(reinterpret_cast<const float4*>(nd->q), a, b);
-    ldg256(reinterpret_cast<const float4*>(nd->q) + 2, c, e);
-    ldg256(reinterpret_cast<const float4*>(nd->link), f, g);
-    const float4 v[4] = {a, b, c, e};
-#pragma unroll
-    for (int i = 0; i < 4; i++) { qw[4 * i] = __float_as_uint(v[i].x); qw[4 * i + 1] = __float_as_uint(v[i].y); qw[4 * i + 2] = __float_as_uint(v[i].z); qw[4 * i + 3] = __float_as_uint(v[i].w); }
-    lk[0] = __float_as_int(f.x); lk[1] = __float_as_int(f.y); lk[2] = __float_as_int(f.z); lk[3] = __float_as_int(f.w);
-    lk[4] = __float_as_int(g.x); lk[5] = __float_as_int(g.y); lk[6] = __float_as_int(g.z); lk[7] = __float_as_int(g.w);
-}
-
-#ifndef IPT_WIDE_CTAS
-#define IPT_WIDE_CTAS 4
+#ifndef IPT_CW_CTAS
+#define IPT_CW_CTAS 4
 #endif
-template <int LPR>
-__global__ void __launch_bounds__(BLOCK_THREADS, IPT_WIDE_CTAS) k_extend_wide(const __grid_constant__ KParams<float> p)
+__global__ void __launch_bounds__(BLOCK_THREADS, IPT_CW_CTAS) k_extend_cw(const __grid_constant__ KParams<float> p)
 {
-    constexpr int CPL = WideCfg<LPR>::CPL;
-    constexpr uint32_t CAP = WideCfg<LPR>::CAP;
-    constexpr uint32_t RAY_LANE0 = LPR == 4 ? 0x11111111u : (LPR == 2 ? 0x55555555u : 0xFFFFFFFFu);   // first lane of every ray
-    constexpr uint32_t N_RAYS = 32 / LPR;
     extern __shared__ uint4 smem[];
     const SceneView<float> sc = p.sc;
-    const uint32_t lane = threadIdx.x & 31u, sub = lane & (LPR - 1), gshift = lane & ~(uint32_t)(LPR - 1);
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    // octant table: lut[oct * 256 + m] = the hit bits m (bit s = slot s) with slot s moved to bit 7 - (s ^ oct)
+    uint8_t* lut = reinterpret_cast<uint8_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) {
+        const uint32_t oct = i >> 8, m = i & 255u;
+        uint32_t r = 0;
+        for (uint32_t sl = 0; sl < 8; sl++) r |= ((m >> sl) & 1u) << (7u - (sl ^ oct));
+        lut[i] = (uint8_t)r;
+    }
+    __syncthreads();
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(smem);
     // this lane's stack: entry e at sbase + e * 256 (32 lanes x 8 bytes per entry row of the warp)
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + ((threadIdx.x >> 5) * CAP * 32u + lane) * 8u;
+    const uint32_t sbase = lut_base + 2048u + ((threadIdx.x >> 5) * CW_STACK * 32u + lane) * 8u;
     uint2* spill = p.wide_spill + ((size_t)blockIdx.x * BLOCK_THREADS + threadIdx.x) * p.wide_spill_cap;
     const uint32_t n_in = p.counters[CNT + p.depth];
     uint32_t* work = p.counters + WORK_EXTEND + p.depth;
     const float slack = 1.0000004f, tiny = 1e-18f;
 
-    uint32_t pool_next = 0, pool_end = 0;                                    // warp-uniform: the warp's chunk of the queue
     bool exhausted = false;
     uint32_t my_traced = 0;
-
-    // per ray (identical in its lanes), except sp: the depth of this lane's own stack
+    uint32_t w_nodes = 0, w_leaves = 0, w_prims = 0, w_sph = 0;            // work counters of ipt_stats
     bool has = false;
     uint32_t idx = 0, self = NO_OBJECT, sp = 0;
     bool onSurf = false;
-    int32_t cur = WIDE_EMPTY;
     V3<float> o = mk<float>(0, 0, 0), d = o, bi = o, oi = o;
-    uint32_t selNx = 0, selFx = 0, selNy = 0, selFy = 0, selNz = 0, selFz = 0;
+    uint32_t selNx = 0, selFx = 0, selNy = 0, selFy = 0, selNz = 0, selFz = 0, lut_oct = 0, octx = 0;
+    uint32_t g_base = 0, g_hits = 0;                                         // node group: child_base | imask << 24, permuted hit bits
+    uint32_t p_base = 0, p_valid = 0, p_hits = 0;                            // primitive group: first slot, the node's pmask, bits to test
     Hit<float> best;
     best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
 
     for (;;) {
-        // ---- refill: idle rays take the next indices of the warp's chunk
-        const uint32_t idle = __ballot_sync(0xffffffffu, !has) & RAY_LANE0;
-        if (!exhausted && (idle == RAY_LANE0 || (uint32_t)__popc(idle) >= p.refill_min)) {
-            if (pool_next >= pool_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work, WIDE_CHUNK);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                pool_next = base; pool_end = min(base + WIDE_CHUNK, n_in);
-                exhausted = base >= n_in;
-            }
-            if (!exhausted) {
-                const uint32_t take = min((uint32_t)__popc(idle), pool_end - pool_next);
-                const uint32_t rank = __popc(idle & ((1u << gshift) - 1u));
-                if (!has && rank < take) {
-                    idx = pool_next + rank;
+        // ---- a ray with nothing left to visit is finished
+        if (has && p_hits == 0 && g_hits == 0 && sp == 0) {
+            __stcs(p.hits + idx, make_uint2(__float_as_uint(best.t), best.slot));
+            has = false;
+        }
+        // ---- refill: idle lanes claim the next rays of the queue with one warp-aggregated atomic
+        const uint32_t idle = __ballot_sync(0xffffffffu, !has);
+        if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= p.refill_min)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (uint32_t)__popc(idle) >= n_in;
+            if (!has) {
+                idx = base + __popc(idle & lt_mask);
+                if (idx < n_in) {
                     const uint4 a = __ldcs(p.qin.base + idx), b = __ldcs(p.qin.base + p.qin.capacity + idx), c = __ldcs(p.qin.base + 2u * p.qin.capacity + idx);
                     o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                     d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
@@ -670,111 +656,85 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_WIDE_CTAS) k_extend_wide(co
                     selNx = 0x7650u | sx; selFx = 0x7651u ^ sx;              // word 0 of a child: lo.x hi.x lo.y hi.y
                     selNy = 0x7652u | sy; selFy = 0x7653u ^ sy;
                     selNz = 0x7650u | sz; selFz = 0x7651u ^ sz;              // word 1: lo.z hi.z
+                    const uint32_t oct = sx | (sy << 1) | (sz << 2);
+                    lut_oct = lut_base + oct * 256u; octx = oct ^ 7u;
                     best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
-                    sp = 0; cur = 0; has = true;
-                    if (sub == 0) my_traced++;
+                    // the root: "slot 0 of a node whose only inner child is node 0"
+                    g_base = 1u << 24; g_hits = 1u << octx; p_hits = 0; sp = 0; has = true;
+                    my_traced++;
                 }
-                pool_next += take;
             }
         }
-        const bool at_inner = has && (uint32_t)cur < (uint32_t)WIDE_EMPTY, at_leaf = has && cur < 0;
-        const uint32_t inner = __ballot_sync(0xffffffffu, at_inner) & RAY_LANE0, leafy = __ballot_sync(0xffffffffu, at_leaf) & RAY_LANE0;
-        if ((inner | leafy) == 0) {
-            if (__ballot_sync(0xffffffffu, has) == 0 && exhausted) break;
-        } else if (inner && ((uint32_t)__popc(inner) >= p.descend_min || !leafy)) {
-            // ---- node phase (rays that are not at an inner node decode the root, which hits L1, and discard the result)
-            const WideNode* nd = p.wide + (at_inner ? cur : 0);
-            float4 h0, h1;
-            ldg256(reinterpret_cast<const float4*>(nd), h0, h1);
-            uint32_t qw[2 * CPL];
-            int32_t lk[CPL];
-            wide_load_children<LPR>(nd, sub, qw, lk);
-            const float Ax = h0.w * bi.x, Ay = h1.x * bi.y, Az = h1.y * bi.z;
-            const float Bx = fmaf(-8388608.f, Ax, fmaf(h0.x, bi.x, -oi.x)), By = fmaf(-8388608.f, Ay, fmaf(h0.y, bi.y, -oi.y)),
-                        Bz = fmaf(-8388608.f, Az, fmaf(h0.z, bi.z, -oi.z));
-            float tn[CPL];
-            uint32_t key[CPL];
-            uint32_t kmin = 0xFFFFFFFFu;
-#pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                const uint32_t w0 = qw[2 * c], w1 = qw[2 * c + 1];
-                const float n = fmaxf(max3f(fmaf(u8m(w0, selNx), Ax, Bx), fmaf(u8m(w0, selNy), Ay, By), fmaf(u8m(w1, selNz), Az, Bz)), 0.f);
-                const float f = fminf(min3f(fmaf(u8m(w0, selFx), Ax, Bx), fmaf(u8m(w0, selFy), Ay, By), fmaf(u8m(w1, selFz), Az, Bz)), best.t) * slack;
-                tn[c] = n;
-                // entry distance with the slot in its low 3 bits: unique per child, ordered by distance
-                key[c] = (at_inner && n <= f) ? ((__float_as_uint(n) & ~7u) | (sub * CPL + c)) : 0xFFFFFFFFu;
-                kmin = min(kmin, key[c]);
-            }
-#pragma unroll
-            for (int x = 1; x < LPR; x <<= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, x));
-            // the link of the nearest hit child, from the lane that decoded it
-            int32_t next = lk[0];
-#pragma unroll
-            for (int c = 1; c < CPL; c++) next = (kmin & (CPL - 1)) == (uint32_t)c ? lk[c] : next;
-            if (LPR > 1) next = __shfl_sync(0xffffffffu, next, gshift | ((kmin & 7u) / CPL));
-            // every other hit child goes on this lane's own stack
-            if (sp + CPL <= CAP) {
-                // the common case: all of them fit the shared-memory part (predicated stores, no branches)
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    const bool push = key[c] != 0xFFFFFFFFu && key[c] != kmin;
-                    if (push) sts64(sbase + sp * 256u, (uint32_t)lk[c], __float_as_uint(tn[c]));
-                    sp += push ? 1u : 0u;
-                }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < CPL; c++) {
-                    if (key[c] != 0xFFFFFFFFu && key[c] != kmin) {
-                        if (sp < CAP) sts64(sbase + sp * 256u, (uint32_t)lk[c], __float_as_uint(tn[c]));
-                        else spill[sp - CAP] = make_uint2((uint32_t)lk[c], __float_as_uint(tn[c]));
-                        sp++;
-                    }
-                }
-            }
-            if (at_inner) cur = kmin == 0xFFFFFFFFu ? WIDE_EMPTY : next;
-        } else {
-            // ---- leaf phase: the ray's lanes test the leaf's primitives side by side
-            Hit<float> cand = best;
-            if (at_leaf) {
-                const uint32_t code = (uint32_t)(~cur), first = code >> 4, cnt = (code & 15u) + 1u;
+        const bool want_prim = has && p_hits != 0, want_node = has && p_hits == 0 && (g_hits != 0 || sp != 0);
+        const uint32_t m_prim = __ballot_sync(0xffffffffu, want_prim), m_node = __ballot_sync(0xffffffffu, want_node);
+        if ((m_prim | m_node) == 0) {
+            if (exhausted && __ballot_sync(0xffffffffu, has) == 0) break;
+            continue;
+        }
+        // ---- primitive step: one primitive per lane
+        if (m_prim && ((uint32_t)__popc(m_prim) >= p.leaf_min || m_node == 0 || (uint32_t)__popc(m_node) < p.descend_min)) {
+            if (want_prim) {
+                const uint32_t bit = __ffs(p_hits) - 1u;
+                const uint32_t slot = p_base + __popc(p_valid & ((1u << bit) - 1u));
+                p_hits &= p_hits - 1u;
                 const V3<float> inv = mk<float>(1.f / d.x, 1.f / d.y, 1.f / d.z);   // as the 2-wide path: +-inf for zero components (Plane.cu:55)
-                for (uint32_t k = sub; k < cnt; k += LPR) test_bslot(sc, first + k, o, d, inv, self, onSurf, cand);
+                test_bslot(sc, slot, o, d, inv, self, onSurf, best, w_sph);
+                w_prims++;
             }
-#pragma unroll
-            for (int x = 1; x < LPR; x <<= 1) {
-                const float ot = __shfl_xor_sync(0xffffffffu, cand.t, x);
-                const uint32_t oo = __shfl_xor_sync(0xffffffffu, cand.obj, x), os = __shfl_xor_sync(0xffffffffu, cand.slot, x);
-                const bool better = ot < cand.t || (ot == cand.t && oo < cand.obj);       // Renderer.cu:235: lowest object index wins ties
-                cand.t = better ? ot : cand.t; cand.obj = better ? oo : cand.obj; cand.slot = better ? os : cand.slot;
-            }
-            if (at_leaf) { best = cand; cur = WIDE_EMPTY; }
         }
-        // ---- pop phase: a ray without a current node takes, of its lanes' stack tops, the one entered first; entries
-        // behind the nearest hit so far are dropped
-        for (;;) {
-            const bool want = has && cur == WIDE_EMPTY;
-            if (!__any_sync(0xffffffffu, want)) break;
-            uint2 e = make_uint2((uint32_t)WIDE_EMPTY, 0xFFFFFFFFu);
-            if (want && sp > 0) e = sp <= CAP ? lds64(sbase + (sp - 1u) * 256u) : spill[sp - 1u - CAP];
-            uint32_t k = (want && sp > 0) ? ((e.y & ~(uint32_t)(LPR - 1)) | sub) : 0xFFFFFFFFu;
-            const uint32_t mine_k = k;
-#pragma unroll
-            for (int x = 1; x < LPR; x <<= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, x));
-            const int32_t link = LPR > 1 ? __shfl_sync(0xffffffffu, (int32_t)e.x, gshift | (k & (LPR - 1))) : (int32_t)e.x;
-            if (want) {
-                if (k == 0xFFFFFFFFu) {
-                    // nothing pending: the ray is finished
-                    if (sub == 0) __stcs(p.hits + idx, make_uint2(__float_as_uint(best.t), best.slot));
-                    has = false;
-                } else {
-                    if (mine_k == k) sp--;
-                    if (__uint_as_float(k & ~(uint32_t)(LPR - 1)) <= best.t * slack) cur = link;
+        // ---- node step
+        if (m_node && ((uint32_t)__popc(m_node) >= p.descend_min || m_prim == 0)) {
+            if (want_node) {
+                if (g_hits == 0) {   // the group is used up: the next one comes from the stack
+                    sp--;
+                    const uint2 e = sp < CW_STACK ? lds64(sbase + sp * 256u) : spill[sp - CW_STACK];
+                    g_base = e.x; g_hits = e.y;
                 }
+                const uint32_t qb = 31u - (uint32_t)__clz(g_hits), slot = qb ^ octx;
+                g_hits &= ~(1u << qb);
+                const uint32_t node = (g_base & 0xFFFFFFu) + (uint32_t)__popc((g_base >> 24) & ((1u << slot) - 1u));
+                if (g_hits) {        // the siblings still to visit wait on the stack
+                    if (sp < CW_STACK) sts64(sbase + sp * 256u, g_base, g_hits);
+                    else spill[sp - CW_STACK] = make_uint2(g_base, g_hits);
+                    sp++;
+                }
+                const float4* nd = reinterpret_cast<const float4*>(p.wide + node);
+                float4 h0, h1, c0, c1, c2, c3;
+                ldg256(nd, h0, h1); ldg256(nd + 2, c0, c1); ldg256(nd + 4, c2, c3);
+                const float Ax = h0.w * bi.x, Ay = h1.x * bi.y, Az = h1.y * bi.z;
+                const float Bx = fmaf(-8388608.f, Ax, fmaf(h0.x, bi.x, -oi.x)), By = fmaf(-8388608.f, Ay, fmaf(h0.y, bi.y, -oi.y)),
+                            Bz = fmaf(-8388608.f, Az, fmaf(h0.z, bi.z, -oi.z));
+                const float tmax = best.t * slack;
+                const uint32_t valid = __float_as_uint(h1.w);
+                const uint32_t qw[16] = {__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c0.w),
+                                         __float_as_uint(c1.x), __float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c1.w),
+                                         __float_as_uint(c2.x), __float_as_uint(c2.y), __float_as_uint(c2.z), __float_as_uint(c2.w),
+                                         __float_as_uint(c3.x), __float_as_uint(c3.y), __float_as_uint(c3.z), __float_as_uint(c3.w)};
+                uint32_t hit8 = 0, prims = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const uint32_t w0 = qw[2 * c], w1 = qw[2 * c + 1];
+                    const float n = fmaxf(max3f(fmaf(u8m(w0, selNx), Ax, Bx), fmaf(u8m(w0, selNy), Ay, By), fmaf(u8m(w1, selNz), Az, Bz)), 0.f);
+                    const float f = fminf(min3f(fmaf(u8m(w0, selFx), Ax, Bx), fmaf(u8m(w0, selFy), Ay, By), fmaf(u8m(w1, selFz), Az, Bz)), tmax);
+                    const bool hit = n <= f;
+                    hit8 |= hit ? (1u << c) : 0u;
+                    prims |= hit ? (valid & (0xFu << (4 * c))) : 0u;
+                }
+                uint32_t pb;
+                asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pb) : "r"(qw[1]), "r"(qw[3]));    // spare bytes of children 0 and 1
+                p_base = pb; p_valid = valid; p_hits = prims;
+                g_base = __float_as_uint(h1.z);
+                const uint32_t inner = hit8 & (g_base >> 24);
+                uint32_t gh;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gh) : "r"(lut_oct + inner));
+                g_hits = gh;
+                w_nodes++; w_leaves += (uint32_t)__popc(hit8 & ~(g_base >> 24));
             }
         }
     }
     my_traced = __reduce_add_sync(0xffffffffu, my_traced);
     if (lane == 0 && my_traced) atomicAdd(p.traced, (unsigned long long)my_traced);
+    add_work(p.traced, w_nodes, 8u * w_nodes, w_leaves, w_sph, w_prims - w_sph);
 }
 
 // fp32 contributions are exact in fixed point without going through fp64: v * 2^k is exact in fp32.

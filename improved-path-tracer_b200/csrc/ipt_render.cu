@@ -20,12 +20,19 @@
 using namespace ipt;
 
 // ------------------------------------------------------------------------------------------------ errors
-static thread_local std::string g_err;
-static std::string g_err_shared;   // last error of any thread (ipt_render uses worker threads)
+// The text of the most recent failure: of this thread if it has one that is at least as recent as any other thread's
+// (ipt_render runs one worker thread per GPU; their messages must reach the caller's thread), under a lock.
+static std::mutex g_err_lock;
+static uint64_t g_err_clock = 0;                 // orders the messages of all threads
+static std::string g_err_shared;                 // most recent message of any thread
+static uint64_t g_err_shared_at = 0;
+static thread_local std::string g_err;           // most recent message of this thread
+static thread_local uint64_t g_err_at = 0;
 static void set_err(const std::string& s)
 {
-    g_err = s;
-    g_err_shared = s;
+    std::lock_guard<std::mutex> lock(g_err_lock);
+    g_err = s; g_err_at = ++g_err_clock;
+    g_err_shared = s; g_err_shared_at = g_err_at;
 }
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -37,7 +44,19 @@ static void set_err(const std::string& s)
     } while (0)
 
 extern "C" int ipt_abi_version(void) { return IPT_ABI_VERSION; }
-extern "C" const char* ipt_last_error(void) { return g_err.empty() ? g_err_shared.c_str() : g_err.c_str(); }
+
+// Progress of a render (Renderer.cu:105-107 prints "\rRendering %.2f%%" per finished pixel row from the device): the share of
+// wavefront batches that have FINISHED on the device, reported from the host thread that renders rank 0's tiles.
+static std::atomic<ipt_progress_fn> g_progress_fn{nullptr};
+static std::atomic<void*> g_progress_user{nullptr};
+extern "C" void ipt_set_progress(ipt_progress_fn fn, void* user) { g_progress_user = user; g_progress_fn = fn; }
+extern "C" const char* ipt_last_error(void)
+{
+    static thread_local std::string copy;        // stays valid until this thread asks again
+    std::lock_guard<std::mutex> lock(g_err_lock);
+    copy = g_err_at >= g_err_shared_at ? g_err : g_err_shared;
+    return copy.c_str();
+}
 
 extern "C" int ipt_device_count(void)
 {
@@ -76,6 +95,10 @@ struct ipt_ctx {
     double scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};   // bounding box of everything a ray can hit
     bool scene_box_valid = false;
     void *geom32 = nullptr, *geom64 = nullptr, *mat32 = nullptr, *mat64 = nullptr;
+    // The fp64 copy of the scene is packed with the fp32 one but crosses PCIe only when an fp64 render or trace asks for
+    // it (upload_fp64): it stays in the pinned staging buffer until then.
+    bool fp64_pending = false;
+    size_t fp64_geom_bytes = 0, fp64_mat_off = 0, fp64_mat_bytes = 0;
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
     float4* bslot = nullptr;         // fp32 BVH leaf records (2 x float4 per slot), built when the scene has a BVH
@@ -158,7 +181,7 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 16) != cudaSuccess ||
+        cudaMalloc(&c->counters, N_COUNTERS * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c->traced, 64) != cudaSuccess ||
         cudaMalloc(&c->fast_hint, 4) != cudaSuccess || cudaMemset(c->fast_hint, 0, 4) != cudaSuccess) {
         set_err(std::string("ipt_ctx_create: ") + cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -277,6 +300,38 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     cudaEvent_t e0 = c->ev0, e1 = c->ev1;
     CK(cudaEventRecord(e0, c->stream));
     const uint32_t n = s->n_objects, ns = s->n_spheres;
+    // The 2-wide tree must be emitted parents first (children at higher indices: what host/bvh.cpp does; no cycles) and no
+    // deeper than the traversal stacks of the generic kernels (ipt_device.cuh: int stack[64]).
+    WideTree wt;
+    if (bvh) {
+        std::vector<uint8_t> depth(s->n_bvh_nodes, 0);
+        uint32_t deepest = 1;
+        depth[0] = 1;
+        for (uint32_t i = 0; i < s->n_bvh_nodes; i++)
+            for (int k = 0; k < 2; k++) {
+                const int32_t ch = s->bvh_nodes[i].child[k];
+                if (ch < 0) continue;
+                if ((uint32_t)ch <= i) { set_err("ipt_ctx_set_scene: BVH nodes must be ordered parents first (child index > parent index)"); return IPT_ERR_BAD_ARGUMENT; }
+                depth[ch] = (uint8_t)std::min(255, depth[i] + 1);
+                deepest = std::max<uint32_t>(deepest, depth[ch]);
+            }
+        if (deepest > 60) { set_err("ipt_ctx_set_scene: BVH deeper than 60 levels (traversal stacks hold 64 entries)"); return IPT_ERR_BAD_ARGUMENT; }
+        // IPT_BVH8=1 (A/B runs): the 8-wide quantised form of the tree (ipt_wide.h) for k_extend_cw.  Measured on the
+        // 1M-primitive scene it loses to the 2-wide traversal, 1.2 against 1.6 Gbounces/s (profiles/README.md, round 2), so
+        // the 2-wide tree is what the fp32 pipeline walks by default.
+        if (std::getenv("IPT_BVH8")) {
+            const uint32_t leaf_max = std::getenv("IPT_WIDE_LEAF") ? (uint32_t)std::atoi(std::getenv("IPT_WIDE_LEAF")) : 4u;
+            if (const char* e = wide_collapse(s->bvh_nodes, s->n_bvh_nodes, n, leaf_max, wt)) {
+                // a tree this form cannot express (leaves of more than 4 primitives) is walked 2-wide; a broken one is refused
+                if (std::strncmp(e, "unsupported", 11) != 0) { set_err(std::string("ipt_ctx_set_scene: ") + e); return IPT_ERR_BAD_ARGUMENT; }
+                wt = WideTree();
+            }
+        }
+    }
+    // One slot order for everything on the device: the 8-wide tree's when there is one (ipt_wide.h: whole leaves move, the
+    // leaves of the 2-wide tree stay consecutive ranges), else the caller's.
+    const uint32_t* slot_perm = wt.perm.empty() ? nullptr : wt.perm.data();
+    const uint32_t* slot_inv = wt.inv.empty() ? nullptr : wt.inv.data();
     const size_t slot_pad = ((size_t)n + 3) / 4 * 4;
     const size_t b_geom64 = (size_t)n * 16 * 8, b_geom32 = (size_t)n * 16 * 4, b_mat64 = (size_t)n * 8 * 8, b_mat32 = (size_t)n * 8 * 4;
     const size_t b_slot = slot_pad * 4, b_nodes = (size_t)s->n_bvh_nodes * 64;
@@ -294,7 +349,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     std::atomic<const char*> bad{nullptr};              // first inconsistency a packing thread found
     parallel_ranges(n, [&](size_t lo_, size_t hi_) {
       for (size_t slot = lo_; slot < hi_; slot++) {
-        uint32_t prim = bvh ? s->bvh_slot_prim[slot] : (slot < ns ? (uint32_t)slot : (RECT_BIT | ((uint32_t)slot - ns)));
+        uint32_t prim = bvh ? s->bvh_slot_prim[slot_perm ? slot_perm[slot] : slot] : (slot < ns ? (uint32_t)slot : (RECT_BIT | ((uint32_t)slot - ns)));
         const bool rect = (prim & RECT_BIT) != 0;
         const uint32_t idx = prim & ~RECT_BIT;
         if ((rect && idx >= s->n_rects) || (!rect && idx >= ns)) { bad = "ipt_ctx_set_scene: bad BVH slot"; return; }
@@ -351,7 +406,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
             } else {
                 const uint32_t first = (uint32_t)(~b.child[k]), cnt = b.count[k];
                 if (cnt < 1 || cnt > 16 || (size_t)first + cnt > n || first >= (1u << 27)) { bad = "ipt_ctx_set_scene: bad BVH leaf"; return; }
-                ch[k] = ~(int32_t)((first << 4) | (cnt - 1));
+                ch[k] = ~(int32_t)(((slot_inv ? slot_inv[first] : first) << 4) | (cnt - 1));
             }
         }
         std::memcpy(o + 12, ch, 8);
@@ -375,7 +430,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         };
         parallel_ranges(n, [&](size_t lo_, size_t hi_) {
           for (size_t slot = lo_; slot < hi_; slot++) {
-            const uint32_t prim = s->bvh_slot_prim[slot], idx = prim & ~RECT_BIT;
+            const uint32_t prim = s->bvh_slot_prim[slot_perm ? slot_perm[slot] : slot], idx = prim & ~RECT_BIT;
             float* o8 = &bs[slot * 8];
             uint32_t kind, obj;
             if (!(prim & RECT_BIT)) {
@@ -398,34 +453,11 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
           }
         });
     }
-    // The 2-wide tree must be emitted parents first (children at higher indices: what host/bvh.cpp does; no cycles) and no
-    // deeper than the traversal stacks of the generic kernels (ipt_device.cuh: int stack[64]).
-    WideTree wt;
-    if (bvh) {
-        std::vector<uint8_t> depth(s->n_bvh_nodes, 0);
-        uint32_t deepest = 1;
-        depth[0] = 1;
-        for (uint32_t i = 0; i < s->n_bvh_nodes; i++)
-            for (int k = 0; k < 2; k++) {
-                const int32_t ch = s->bvh_nodes[i].child[k];
-                if (ch < 0) continue;
-                if ((uint32_t)ch <= i) { set_err("ipt_ctx_set_scene: BVH nodes must be ordered parents first (child index > parent index)"); return IPT_ERR_BAD_ARGUMENT; }
-                depth[ch] = (uint8_t)std::min(255, depth[i] + 1);
-                deepest = std::max<uint32_t>(deepest, depth[ch]);
-            }
-        if (deepest > 60) { set_err("ipt_ctx_set_scene: BVH deeper than 60 levels (traversal stacks hold 64 entries)"); return IPT_ERR_BAD_ARGUMENT; }
-        // the 8-wide quantised form the fp32 traversal walks (ipt_wide.h); IPT_BVH2=1 keeps the 2-wide traversal (A/B runs)
-        if (!std::getenv("IPT_BVH2")) {
-            const uint32_t leaf_max = std::getenv("IPT_WIDE_LEAF") ? (uint32_t)std::atoi(std::getenv("IPT_WIDE_LEAF")) : 8u;
-            if (const char* e = wide_collapse(s->bvh_nodes, s->n_bvh_nodes, n, leaf_max, wt)) { set_err(std::string("ipt_ctx_set_scene: ") + e); return IPT_ERR_BAD_ARGUMENT; }
-            if (wt.stack_need > 256) wt.nodes.clear();   // absurdly skewed tree: the 2-wide traversal handles it
-        }
-    }
     const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode)};
-    if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom64) {
+    if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom32) {
         free_scene(c);
-        CK(cudaMalloc(&c->geom64, b_geom64)); CK(cudaMalloc(&c->geom32, b_geom32));
-        CK(cudaMalloc(&c->mat64, b_mat64)); CK(cudaMalloc(&c->mat32, b_mat32));
+        CK(cudaMalloc(&c->geom32, b_geom32));
+        CK(cudaMalloc(&c->mat32, b_mat32));
         CK(cudaMalloc(&c->slot_obj, b_slot));
         if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
         if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
@@ -434,9 +466,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         std::memcpy(c->scene_bytes, want, sizeof(want));
     }
     c->have_scene = false;
-    CK(cudaMemcpyAsync(c->geom64, g64, b_geom64, cudaMemcpyHostToDevice, c->stream));
+    c->fp64_pending = true; c->fp64_geom_bytes = b_geom64; c->fp64_mat_off = b_geom64 + b_geom32; c->fp64_mat_bytes = b_mat64;
     CK(cudaMemcpyAsync(c->geom32, g32, b_geom32, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->mat64, m64, b_mat64, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
@@ -457,7 +488,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode);
+    c->last.h2d_bytes = total - b_geom64 - b_mat64 + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode);
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -546,27 +577,17 @@ static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_ca
 }
 
 // One batch of the split pipeline (fp32, BVH): raygen, then per bounce k_extend_bvh and k_bounce<MODE_SHADE>.
-// k_extend_wide<LPR>: launch by the number of lanes that walk a ray together (IPT_WIDE_LPR = 1 | 2 | 4, A/B knob)
-static int wide_lpr()
-{
-    const char* e = std::getenv("IPT_WIDE_LPR");
-    const int x = e ? std::atoi(e) : 2;
-    return (x == 1 || x == 4) ? x : 2;
-}
-static size_t wide_smem_bytes() { return wide_lpr() == 4 ? WideCfg<4>::SMEM : (wide_lpr() == 2 ? WideCfg<2>::SMEM : WideCfg<1>::SMEM); }
-static void (*wide_kernel())(const KParams<float>) { return wide_lpr() == 4 ? k_extend_wide<4> : (wide_lpr() == 2 ? k_extend_wide<2> : k_extend_wide<1>); }
-
-static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth, uint32_t cap, size_t smem_top, int* grids, uint64_t* launches)
+// Grids of the split pipeline's kernels (once per render) and, for k_extend_cw, the spill area of its stacks.
+static int prepare_extend(ipt_ctx* c, KParams<float>& kp, size_t smem_top, int* grids)
 {
     auto shade = k_bounce<float, MODE_SHADE, false, false>;
     if (kp.wide && grids[2] == 0) {
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_kernel(), BLOCK_THREADS, wide_smem_bytes()));
-        if (per_sm < 1) { set_err("k_extend_wide does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_cw, BLOCK_THREADS, CW_SMEM));
+        if (per_sm < 1) { set_err("k_extend_cw does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
         grids[2] = per_sm * c->sm_count;
-        // stack entries beyond the shared-memory part: one area per resident ray
-        // stack entries beyond a lane's shared-memory part: no lane can hold more than the whole tree asks of a ray
-        kp.wide_spill_cap = std::max(1u, c->wide_stack_need);
+        // stack entries beyond a lane's shared-memory part: a ray has at most one entry pending per level of the tree
+        kp.wide_spill_cap = std::max(1u, c->wide_depth);
         const size_t need = (size_t)grids[2] * BLOCK_THREADS * kp.wide_spill_cap * sizeof(uint2);
         if (need > c->wide_spill_bytes) {
             cudaFree(c->wide_spill); c->wide_spill = nullptr; c->wide_spill_bytes = 0;
@@ -584,6 +605,14 @@ static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade, BLOCK_THREADS, 0));
         grids[1] = std::max(per_sm, 1) * c->sm_count;
     }
+    return IPT_OK;
+}
+
+static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth, uint32_t cap, size_t smem_top, int* grids, uint64_t* launches)
+{
+    auto shade = k_bounce<float, MODE_SHADE, false, false>;
+    int rc_prep = prepare_extend(c, kp, smem_top, grids);
+    if (rc_prep) return rc_prep;
     kp.depth = 0;
     kp.qout = Queue{c->q[0], cap};
     k_raygen<float><<<c->sm_count * 8, BLOCK_THREADS, 0, c->stream>>>(kp);
@@ -592,7 +621,7 @@ static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth
         kp.depth = d;
         kp.qin = Queue{c->q[d & 1], cap};
         kp.qout = Queue{c->q[(d + 1) & 1], cap};
-        if (kp.wide) wide_kernel()<<<grids[2], BLOCK_THREADS, wide_smem_bytes(), c->stream>>>(kp);
+        if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
         else k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
         shade<<<grids[1], BLOCK_THREADS, 0, c->stream>>>(kp);
         *launches += 2;
@@ -691,9 +720,23 @@ static int build_active_microtiles(ipt_ctx* c, uint32_t tile_w, uint32_t tile_h,
     return IPT_OK;
 }
 
+// fp64 copy of the scene: from the staging buffer of the last ipt_ctx_set_scene to the device, on first use.
+static int upload_fp64(ipt_ctx* c)
+{
+    if (!c->fp64_pending) return IPT_OK;
+    if (!c->geom64) { CK(cudaMalloc(&c->geom64, c->fp64_geom_bytes)); CK(cudaMalloc(&c->mat64, c->fp64_mat_bytes)); }
+    const char* pin = (const char*)c->pinned;
+    CK(cudaMemcpyAsync(c->geom64, pin, c->fp64_geom_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->mat64, pin + c->fp64_mat_off, c->fp64_mat_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->last.h2d_bytes += c->fp64_geom_bytes + c->fp64_mat_bytes;
+    c->fp64_pending = false;
+    return IPT_OK;
+}
+
 template <typename R>
 static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint32_t tile_h, uint32_t tiles_x, ipt_stats* st)
 {
+    if (sizeof(R) == 8) { int rc64 = upload_fp64(c); if (rc64) return rc64; }
     const bool bvh = c->n_nodes > 0;
     KParams<R> kp;
     std::memset(&kp, 0, sizeof(kp));
@@ -728,6 +771,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         const double mc = std::max(1.0, c->max_color);
         double bound = std::max(c->max_emission, 1e-30) * 2.0 * (prm.max_depth + 1.0) * std::pow(mc, (double)prm.max_depth);
         bound *= (double)prm.samples;
+        // next-event estimation adds, per diffuse hit, up to lobe (0.433) x 1/q (2 pi) x n_lights x E of explicit light
+        if (nee) bound *= std::max(1.0, 2.7 * (double)c->n_lights);
         const int bits = 62 - (int)std::ceil(std::log2(bound));
         // below 2^-30 resolution the quantisation would show in dim pixels: use fp64 atomics instead (not bit-reproducible)
         if (!std::isfinite(bound) || bits < 30) float_accum = true;
@@ -750,7 +795,9 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     const bool defer = prm.max_depth >= 130;
     const size_t ray_bytes = (size_t)16 * (QPlanes<R>::N + (defer ? QPlanes<R>::ACC : 0));
     // a sample has at most two live rays; + room for the dead tails of the fast kernel's per-warp output blocks
-    auto cap_of = [](uint64_t b) { return (uint32_t)(2 * b) + (1u << 20); };
+    // (at most OUT_BLOCK - 1 dead slots per resident warp of k_bounce_fast, whatever its launch configuration: 64 warps per SM)
+    const uint32_t tail_slack = (uint32_t)c->sm_count * 64u * OUT_BLOCK;
+    auto cap_of = [tail_slack](uint64_t b) { return (uint32_t)(2 * b) + tail_slack; };
     {   // the default batch shrinks on devices (or in processes) where two queues of that size do not fit comfortably
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t)0; }
@@ -776,11 +823,11 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         c->hits_bytes = (size_t)cap * 8;
     }
     kp.hits = c->hits;
-    // 8-wide traversal (the default when the scene has a BVH): thresholds count rays of a warp (8), not lanes
-    kp.wide = (use_split && !std::getenv("IPT_BVH2")) ? c->wide : nullptr;
-    const uint32_t wide_rays = 32u / (uint32_t)wide_lpr();
-    kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : (kp.wide ? wide_rays * 5u / 8u : 12u);
-    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : (kp.wide ? wide_rays / 4u : 8u);
+    // 8-wide traversal: only with IPT_BVH8=1 at ipt_ctx_set_scene time (and leaves of at most 4 primitives)
+    kp.wide = use_split ? c->wide : nullptr;
+    kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : 12u;
+    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
+    kp.leaf_min = std::getenv("IPT_LEAF_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_LEAF_MIN")) : 8u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
@@ -798,7 +845,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.fast_hint = c->fast_hint;
     const int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
-    CK(cudaMemsetAsync(c->traced, 0, 16, c->stream));   // [0] casts, [1] queue records moved
+    CK(cudaMemsetAsync(c->traced, 0, 64, c->stream));   // [0] casts, [1] queue records moved, [2..6] traversal work (add_work)
     CK(cudaEventRecord(c->ev0, c->stream));
     int grid_first = 0, grid_next = 0, split_grids[3] = {0, 0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
@@ -813,6 +860,20 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     if (pass_times && std::getenv("IPT_PASS_CLOCKS")) CK(cudaMallocManaged(&clock_probe, 4096 * sizeof(float)));
     uint64_t launches = 0, batches = 0;
     const uint64_t groups_per_batch = B / 32;
+    // progress (ipt_set_progress): an event after (at most 200 of) the batches; the host reports how many have finished
+    const ipt_progress_fn progress = prm.rank == 0 ? g_progress_fn.load() : nullptr;
+    struct BatchEvents {
+        std::vector<cudaEvent_t> ev; size_t done = 0;
+        ~BatchEvents() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    } marks;
+    const uint64_t n_batches_total = groups_per_batch ? (total_groups + groups_per_batch - 1) / groups_per_batch : 0;
+    const uint64_t mark_every = std::max<uint64_t>(1, (n_batches_total + 199) / 200);
+    auto report = [&]() {
+        while (marks.done < marks.ev.size() && cudaEventQuery(marks.ev[marks.done]) == cudaSuccess) marks.done++;
+        cudaGetLastError();   // cudaErrorNotReady is not an error
+        const double total_marks = (double)((n_batches_total + mark_every - 1) / mark_every);
+        progress(total_marks > 0 ? std::min(1.0, (double)marks.done / total_marks) : 1.0, g_progress_user.load());
+    };
     // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
     // rectangle and the frame stays black.  Kept: such frames are resolved from zeroed accumulators without tracing.
     const bool tiny = c->W <= 22 && c->H <= 22;
@@ -827,6 +888,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             k_batch_stats<<<1, 32, 0, c->stream>>>(c->counters, c->traced);
             launches++;
             batches++;
+            if (progress && batches % mark_every == 0) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); CK(cudaEventRecord(e, c->stream));
+                marks.ev.push_back(e);
+                report();
+            }
             continue;
         }
         const uint32_t n_passes = passes_per_batch;
@@ -868,6 +935,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         k_batch_stats<<<1, 32, 0, c->stream>>>(c->counters, c->traced);
         launches++;
         batches++;
+        if (progress && batches % mark_every == 0) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); CK(cudaEventRecord(e, c->stream));
+            marks.ev.push_back(e);
+            report();
+        }
     }
     if (pass_times) { cudaEvent_t e; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, c->stream)); pass_events.push_back(e); }
     // resolve (and gather: dst may be a peer GPU's frame)
@@ -880,6 +953,10 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     launches++;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());
+    if (progress) {   // wait for the device while reporting the batches it finishes (20 reports a second)
+        while (cudaEventQuery(c->ev1) == cudaErrorNotReady) { report(); std::this_thread::sleep_for(std::chrono::milliseconds(50)); }
+        cudaGetLastError();
+    }
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -908,8 +985,10 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             std::fprintf(stderr, "\n");
         }
     }
-    unsigned long long traced[2] = {0, 0};
-    CK(cudaMemcpy(traced, c->traced, 16, cudaMemcpyDeviceToHost));
+    unsigned long long traced[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpy(traced, c->traced, 64, cudaMemcpyDeviceToHost));
+    c->last.node_steps = traced[2]; c->last.box_tests = traced[3]; c->last.leaf_steps = traced[4];
+    c->last.sphere_tests = traced[5]; c->last.rect_tests = traced[6];
     const size_t record_bytes = (sizeof(R) == 4 ? 48 : 96) + (defer ? (sizeof(R) == 4 ? 16 : 32) : 0);
     c->last.queue_bytes = traced[1] * record_bytes;
     c->last.render_ms = ms; c->last.traced_bounces = traced[0]; c->last.kernel_launches = launches; c->last.batches = batches;
@@ -1130,8 +1209,11 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
         *stats = sts[0];
         stats->samples = 0; stats->traced_bounces = 0; stats->kernel_launches = 0; stats->batches = 0; stats->render_ms = 0;
         stats->queue_bytes = 0;
+        stats->node_steps = stats->box_tests = stats->leaf_steps = stats->sphere_tests = stats->rect_tests = 0;
         for (int g = 0; g < n_gpus; g++) {
             stats->queue_bytes += sts[g].queue_bytes;
+            stats->node_steps += sts[g].node_steps; stats->box_tests += sts[g].box_tests; stats->leaf_steps += sts[g].leaf_steps;
+            stats->sphere_tests += sts[g].sphere_tests; stats->rect_tests += sts[g].rect_tests;
             stats->samples += sts[g].samples; stats->traced_bounces += sts[g].traced_bounces;
             stats->kernel_launches += sts[g].kernel_launches; stats->batches += sts[g].batches;
             if (g > 0) stats->active_pixels += sts[g].active_pixels;
@@ -1163,10 +1245,64 @@ extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_
     if (!c || !c->have_scene || !rays || !out_obj || !out_t) { set_err("ipt_ctx_trace: bad argument"); return IPT_ERR_BAD_ARGUMENT; }
     if (n == 0) return IPT_OK;
     CK(cudaSetDevice(c->device));
-    double* d_rays = nullptr; int32_t* d_obj = nullptr; double* d_t = nullptr;
+    struct Temps {                  // released on every return path
+        double* rays = nullptr; int32_t* obj = nullptr; double* t = nullptr;
+        ~Temps() { cudaFree(rays); cudaFree(obj); cudaFree(t); }
+    } tmp;
+    double*& d_rays = tmp.rays; int32_t*& d_obj = tmp.obj; double*& d_t = tmp.t;
+    if (flags & IPT_FLAG_FP64) { int rc64 = upload_fp64(c); if (rc64) return rc64; }
     CK(cudaMalloc(&d_rays, (size_t)n * 48)); CK(cudaMalloc(&d_obj, (size_t)n * 4)); CK(cudaMalloc(&d_t, (size_t)n * 8));
     CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
     const bool bvh = c->n_nodes > 0, f64 = (flags & IPT_FLAG_FP64) != 0;
+    if (!f64 && bvh && c->bslot && !std::getenv("IPT_GENERIC_KERNEL") && !std::getenv("IPT_FUSED_BVH")) {
+        // fp32 + BVH: through the traversal kernel of the split pipeline itself (k_extend_bvh, or k_extend_cw with IPT_BVH8), fed
+        // with a one-pass ray queue - what a render runs, not a restatement of it
+        struct Q {
+            uint4* rays = nullptr; uint2* hits = nullptr;
+            ~Q() { cudaFree(rays); cudaFree(hits); }
+        } q;
+        CK(cudaMalloc(&q.rays, (size_t)n * 48)); CK(cudaMalloc(&q.hits, (size_t)n * 8));
+        std::vector<uint4> rec((size_t)n * 3);
+        auto fb = [](double x) { const float f = (float)x; uint32_t u; std::memcpy(&u, &f, 4); return u; };
+        for (uint32_t i = 0; i < n; i++) {
+            const double* r = rays + 6 * (size_t)i;
+            rec[i] = make_uint4(fb(r[0]), fb(r[1]), fb(r[2]), fb(r[3]));
+            rec[(size_t)n + i] = make_uint4(fb(r[4]), fb(r[5]), 0u, 0u);
+            rec[2 * (size_t)n + i] = make_uint4(0u, 0u, 0u, NO_OBJECT);       // no flags, starts on no object
+        }
+        CK(cudaMemcpyAsync(q.rays, rec.data(), rec.size() * 16, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->counters, 0, N_COUNTERS * sizeof(uint32_t), c->stream));
+        CK(cudaMemcpyAsync(c->counters + CNT, &n, 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->traced, 0, 64, c->stream));
+        KParams<float> kp;
+        std::memset(&kp, 0, sizeof(kp));
+        kp.sc.geom = (const R4<float>*)c->geom32; kp.sc.mat = (const R4<float>*)c->mat32; kp.sc.slot_obj = c->slot_obj;
+        kp.sc.n_slots = c->n_slots; kp.sc.n_spheres = c->n_spheres; kp.sc.n_objects = c->n_objects;
+        kp.sc.nodes = c->nodes; kp.sc.n_nodes = c->n_nodes; kp.sc.bslot = c->bslot;
+        kp.counters = c->counters; kp.traced = c->traced; kp.hits = q.hits; kp.depth = 0;
+        kp.qin = Queue{q.rays, n};
+        kp.wide = c->wide;
+        kp.descend_min = 12; kp.refill_min = 8; kp.leaf_min = 8;
+        const size_t smem_top = (size_t)std::min<uint32_t>(c->n_nodes, BVH_TOP_NODES) * 64;
+        int grids[3] = {0, 0, 0};
+        int rc = prepare_extend(c, kp, smem_top, grids);
+        if (rc) return rc;
+        if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
+        else k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
+        CK(cudaGetLastError());
+        std::vector<uint2> hits(n);
+        std::vector<uint32_t> slot_obj(c->n_slots);
+        CK(cudaMemcpyAsync(hits.data(), q.hits, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(slot_obj.data(), c->slot_obj, (size_t)c->n_slots * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint32_t i = 0; i < n; i++) {
+            float t; std::memcpy(&t, &hits[i].x, 4);
+            const bool hit = hits[i].y != NO_OBJECT && hits[i].y < c->n_slots;
+            out_obj[i] = hit ? (int32_t)(slot_obj[hits[i].y] & ~RECT_BIT) : -1;
+            out_t[i] = hit ? (double)t : 0.0;
+        }
+        return IPT_OK;
+    }
     const size_t esz = f64 ? 32 : 16;
     const size_t smem = bvh ? (size_t)std::min<uint32_t>(c->n_nodes, BVH_TOP_NODES) * 64 : (size_t)c->n_slots * 4 * esz + ((size_t)c->n_slots + 3) / 4 * 16;
     const int grid = c->sm_count * 2;
@@ -1190,6 +1326,5 @@ extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_
     CK(cudaMemcpyAsync(out_obj, d_obj, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(out_t, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_rays); cudaFree(d_obj); cudaFree(d_t);
     return IPT_OK;
 }

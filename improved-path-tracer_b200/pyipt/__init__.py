@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "ipt_abi_version", "ipt_device_count", "ipt_device_name", "ipt_last_error", "ipt_render", "ipt_render_rgb8", "ipt_render_objects",
     "ipt_ctx_create", "ipt_ctx_destroy", "ipt_ctx_set_scene", "ipt_ctx_render", "ipt_ctx_download", "ipt_ctx_download_rgb8",
     "ipt_ctx_export_frame", "ipt_ctx_set_gather_target_ipc", "ipt_ctx_set_gather_target", "ipt_tile_owner",
-    "ipt_ctx_trace", "ipt_alloc_pinned", "ipt_free_pinned",
+    "ipt_ctx_trace", "ipt_alloc_pinned", "ipt_free_pinned", "ipt_set_progress",
 ]
 HOST_SYMBOLS = [
     "ipt_host_load_scene", "ipt_host_from_objects", "ipt_host_free_scene", "ipt_host_scene_view", "ipt_host_set_size",
@@ -64,7 +64,9 @@ class Stats(ctypes.Structure):
                 ("batches", ctypes.c_uint64), ("render_ms", ctypes.c_double), ("upload_ms", ctypes.c_double),
                 ("download_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("per_gpu_render_ms", ctypes.c_double * 8), ("per_gpu_bounces", ctypes.c_uint64 * 8),
-                ("active_pixels", ctypes.c_uint64), ("queue_bytes", ctypes.c_uint64)]
+                ("active_pixels", ctypes.c_uint64), ("queue_bytes", ctypes.c_uint64),
+                ("node_steps", ctypes.c_uint64), ("box_tests", ctypes.c_uint64), ("leaf_steps", ctypes.c_uint64),
+                ("sphere_tests", ctypes.c_uint64), ("rect_tests", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.startswith("per_gpu") else getattr(self, k)) for k, _ in self._fields_}
@@ -117,6 +119,8 @@ def lib():
     L.ipt_tile_owner.argtypes = [u32, u32, u32, u32]
     L.ipt_tile_owner.restype = u32
     L.ipt_ctx_trace.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.ipt_set_progress.argtypes = [vp, vp]
+    L.ipt_set_progress.restype = None
     L.ipt_host_load_scene.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     L.ipt_host_load_scene.restype = vp
     L.ipt_host_from_objects.argtypes = [vp, u32, u32, u32, vp]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IPT_ABI_VERSION 2
+#define IPT_ABI_VERSION 3
 
 typedef enum ipt_status {
     IPT_OK = 0,
@@ -131,6 +131,13 @@ typedef struct ipt_stats {
                                     for every sample and no ray is generated for them (they still count in `samples`)  */
     uint64_t queue_bytes;        /* ray-queue bytes written + read back by the wavefront passes (records x record size): the
                                     traffic the design sends through HBM, counted on the device                         */
+    /* Traversal work of BVH scenes in fp32 (the split pipeline), counted on the device; 0 for the brute-force scenes, whose
+     * work per cast is fixed (every primitive).  bench.py turns these into the algorithmic flops of SURVEY.md §8d. */
+    uint64_t node_steps;         /* inner nodes visited                                                */
+    uint64_t box_tests;          /* child boxes tested (2 per node of the 2-wide tree, 8 per node of the 8-wide tree) */
+    uint64_t leaf_steps;         /* leaves visited                                                     */
+    uint64_t sphere_tests;       /* Sphere::intersect evaluations (Sphere.cu:25-39)                    */
+    uint64_t rect_tests;         /* Plane::intersect evaluations (Plane.cu:47-100)                     */
 } ipt_stats;
 
 /* -- device probe (CudaUtils.cu:8-23) ------------------------------------------------------------------- */
@@ -138,6 +145,14 @@ int ipt_abi_version(void);
 int ipt_device_count(void);
 const char* ipt_device_name(int device);
 const char* ipt_last_error(void);
+
+/* -- progress ------------------------------------------------------------------------------------------------
+ * The reference prints "\rRendering %.2f%%" from the device after every pixel row (Renderer.cu:105-107).  Here a
+ * process-wide hook is called from the host thread that renders rank 0's tiles with the fraction (0..1) of wavefront
+ * batches the device has finished: while batches are enqueued and, about 20 times a second, while the call waits for the
+ * device.  NULL (the default) switches it off.  The hook must not call back into this library. */
+typedef void (*ipt_progress_fn)(double fraction_done, void* user);
+void ipt_set_progress(ipt_progress_fn fn, void* user);
 
 /* -- page-locked host buffers ---------------------------------------------------------------------------
  * Optional: every entry point accepts any host pointer.  A frame buffer obtained here is copied at full PCIe

@@ -151,6 +151,10 @@ def ref():
         L.ref_scatter.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_ulonglong, dp]
         L.ref_scatter.restype = None
         L.ref_xorwow_kat.argtypes = [ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+        if hasattr(L, "ref_scene_objects"):
+            L.ref_scene_objects.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+            L.ref_scene_objects.restype = ctypes.c_int
         _ref = L
     return _ref
 
@@ -177,6 +181,20 @@ def nearest_hit(scene, rays):
     t = np.zeros(n, dtype=np.float64)
     lib().or_nearest_hit(ctypes.byref(cs), rays.ctypes.data, n, idx.ctypes.data, t.ctypes.data)
     return idx, t
+
+
+def ref_scene_objects(path):
+    """The reference's own in-memory scene, byte for byte: (objects bytes [n*144], camera bytes [72], W, H, n) as
+    SceneData::getObjectsData() / getCamera() hold them (what RenderContoller::start() uploads)."""
+    path = scene_path(path) if not os.path.isfile(path) else path
+    W, H = ctypes.c_int(), ctypes.c_int()
+    n = ref().ref_scene_objects(os.fsencode(path), None, 0, None, ctypes.byref(W), ctypes.byref(H))
+    if n < 0:
+        raise RuntimeError(f"reference SceneData could not load {path}")
+    objs = ctypes.create_string_buffer(144 * n)
+    cam = ctypes.create_string_buffer(72)
+    ref().ref_scene_objects(os.fsencode(path), objs, n, cam, ctypes.byref(W), ctypes.byref(H))
+    return objs.raw, cam.raw, W.value, H.value, n
 
 
 def ref_render(path, samples, depth, width=0, height=0, cell_begin=0, cell_end=-1, nthreads=None):

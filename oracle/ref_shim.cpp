@@ -128,6 +128,24 @@ int ref_scene_dims(const char* path, int* W, int* H, int* nObjects)
     return 0;
 }
 
+// The reference's OWN in-memory scene, byte for byte: the storage of SceneData::getObjectsData() (std::vector<ObjectData>,
+// ObjectData.hpp:15-31) and getCamera() (Camera.hpp:8-16) - what RenderContoller::start() uploads
+// (RenderController.cu:47-50) and what ipt_render_objects() takes.  Returns the number of objects, or -1; copies at
+// most max_objects records of 144 bytes into out_objects and 72 bytes into out_camera.
+static_assert(sizeof(ObjectData) == 144, "ObjectData layout changed: include/ipt_abi.h (ipt_render_objects) assumes 144 bytes");
+static_assert(sizeof(Camera) == 72, "Camera layout changed: include/ipt_abi.h assumes 9 doubles");
+int ref_scene_objects(const char* path, void* out_objects, int max_objects, void* out_camera, int* W, int* H)
+{
+    Loaded l = load(path, 0, 0);
+    if (!l.ok) return -1;
+    const int n = (int)l.objs.size();
+    if (out_objects) std::memcpy(out_objects, l.objs.data(), sizeof(ObjectData) * (size_t)(n < max_objects ? n : max_objects));
+    if (out_camera) std::memcpy(out_camera, &l.cam, sizeof(Camera));
+    if (W) *W = (int)l.W;
+    if (H) *H = (int)l.H;
+    return n;
+}
+
 // Number of "CUDA threads" (cells) the reference launches: min(H,22) blocks x min(W,22) threads
 // (RenderController.cu:53-56).
 int ref_num_cells(int W, int H)

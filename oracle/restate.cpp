@@ -474,12 +474,20 @@ int or_render(const or_scene* scene, uint32_t samples, uint32_t max_depth, int r
 void or_nearest_hit(const or_scene* scene, const double* rays, uint32_t n_rays, int32_t* out_index, double* out_t)
 {
     const Ctx c = make_ctx(scene, 1, 3);
-    for (uint32_t i = 0; i < n_rays; i++) {
-        const RayT r{V(rays + 6 * i), V(rays + 6 * i + 3)};
-        const Hit h = nearest(c, r);
-        out_index[i] = h.index;
-        out_t[i] = h.t;
-    }
+    // rays are independent: spread over the host cores (the scan of a million-primitive scene takes ~10 ms per ray)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t nt = std::max(1u, std::min<uint32_t>(hw ? hw : 1u, n_rays / 16u + 1u));
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nt; t++)
+        pool.emplace_back([&, t] {
+            for (uint32_t i = t; i < n_rays; i += nt) {
+                const RayT r{V(rays + 6 * i), V(rays + 6 * i + 3)};
+                const Hit h = nearest(c, r);
+                out_index[i] = h.index;
+                out_t[i] = h.t;
+            }
+        });
+    for (auto& th : pool) th.join();
 }
 
 double or_sphere_intersect(double radius, const double* c, const double* o, const double* d)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pyipt):
     L = pyipt.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ipt_abi_version() == 2
+    assert L.ipt_abi_version() == 3
 
 
 def test_no_torch_and_no_oracle_in_the_product():
@@ -341,3 +341,23 @@ def test_bvh_traversal_equals_linear_scan_on_cpu(tmp_path):
     for leaf in (1, 4, 16):
         r = subprocess.run([exe, path, str(leaf), "3000", "check"], capture_output=True, text=True)
         assert r.returncode == 0 and "check: 0 of 3000" in r.stdout, r.stdout + r.stderr
+
+
+def test_wide_tree_equals_linear_scan_on_cpu(tmp_path):
+    """tools/wide_stats.cpp in check mode: the 8-wide quantised tree of csrc/ipt_wide.h (SAH-optimal collapse and the first,
+    greedy one), walked the way k_extend_cw walks it - fp32 arithmetic on the quantised planes, implicit child and primitive
+    addressing, octant-ordered hit masks - finds exactly the nearest distance of a scan over every primitive; the explicit
+    links of every visited node agree with the implicit addressing; a 2-wide tree with leaves above 4 primitives is refused."""
+    import subprocess, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scene_util import synthetic_scene, write_scene
+    exe = str(tmp_path / "wide_stats")
+    pkg = os.path.join(ROOT, "improved-path-tracer_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "wide_stats.cpp"),
+                    "-L" + pkg, "-lipt_b200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    path = write_scene(tmp_path / "syn6000.json", synthetic_scene(6000, seed=11, general_rects=True))
+    for leaf2, leaf_max, extra in ((4, 4, []), (1, 1, []), (2, 4, []), (4, 2, ["greedy"])):
+        r = subprocess.run([exe, path, str(leaf2), str(leaf_max), "3000", "check"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0 and "check: 0 of 3000" in r.stdout and " 0 link mismatches" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe, path, "8", "4", "10"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unsupported" in r.stderr

@@ -1,10 +1,12 @@
-// wide_stats — development tool (CPU only): the 8-wide quantised tree of csrc/ipt_wide.h walked the way k_extend_wide
-// walks it (fp32 slab arithmetic on the quantised planes, nearest hit child first, the others pushed with their entry
-// distance and culled when popped), against the linear scan of Renderer.cu:227-243.
+// wide_stats — development and test tool (CPU only): the 8-wide quantised tree of csrc/ipt_wide.h walked the way
+// k_extend_cw walks it (fp32 slab arithmetic on the quantised planes; one stack entry per node holding the hit inner
+// children as a bit mask, visited in increasing slot ^ octant; the hit leaf children as a bit mask over the node's
+// consecutive primitive slots; implicit child and primitive addressing), against the linear scan of Renderer.cu:227-243.
 //   g++ -O2 -std=c++17 -Iinclude tools/wide_stats.cpp -Limproved-path-tracer_b200 -lipt_b200 -Wl,-rpath,$PWD/improved-path-tracer_b200 -o /tmp/wide_stats
-//   /tmp/wide_stats scene.json [leaf2=4] [leaf_max=8] [rays=20000] [check] [sorted]
-// Prints node steps, leaf steps, pops and primitive tests per ray and the deepest stack seen; with `check` every ray is
-// also tested against every primitive and the nearest distance must agree exactly (exit 1 otherwise).
+//   /tmp/wide_stats scene.json [leaf2=4] [leaf_max=4] [rays=20000] [check] [greedy] [cnode=4]
+// Prints node steps, leaf children entered and primitive tests per ray and the deepest stack seen; with `check` every ray
+// is also tested against every primitive and the nearest distance must agree exactly (exit 1 otherwise).  The links of a
+// node (WideNode::link) are cross-checked against the implicit addressing on every step.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -42,30 +44,34 @@ static double hit_prim(const ipt_scene* s, uint32_t prim, const Ray& r, double b
 
 int main(int argc, char** argv)
 {
-    if (argc < 2) { std::fprintf(stderr, "usage: wide_stats scene.json [leaf2] [leaf_max] [rays] [check] [sorted]\n"); return 2; }
-    const uint32_t leaf2 = argc > 2 ? (uint32_t)std::atoi(argv[2]) : 4, leaf_max = argc > 3 ? (uint32_t)std::atoi(argv[3]) : 8;
+    if (argc < 2) { std::fprintf(stderr, "usage: wide_stats scene.json [leaf2] [leaf_max] [rays] [check]\n"); return 2; }
+    const uint32_t leaf2 = argc > 2 ? (uint32_t)std::atoi(argv[2]) : 4, leaf_max = argc > 3 ? (uint32_t)std::atoi(argv[3]) : 4;
     const int n_rays = argc > 4 ? std::atoi(argv[4]) : 20000;
-    bool check = false, sorted = false, octant = false, stat = false; int multi = 0;
-    for (int i = 5; i < argc; i++) { check = check || std::string(argv[i]) == "check"; sorted = sorted || std::string(argv[i]) == "sorted"; octant = octant || std::string(argv[i]) == "octant"; stat = stat || std::string(argv[i]) == "static"; if (std::string(argv[i]).rfind("multi", 0) == 0) multi = std::atoi(argv[i] + 5); }
+    bool check = false, greedy = false;
+    double c_node = 4.0;
+    for (int i = 5; i < argc; i++) {
+        check = check || std::string(argv[i]) == "check"; greedy = greedy || std::string(argv[i]) == "greedy";
+        if (std::string(argv[i]).rfind("cnode=", 0) == 0) c_node = std::atof(argv[i] + 6);
+    }
     char msg[256];
     ipt_host_scene* hs = ipt_host_load_scene(argv[1], msg, sizeof msg);
     if (!hs) { std::fprintf(stderr, "%s\n", msg); return 1; }
     if (ipt_host_build_bvh(hs, leaf2, 0) < 0) { std::fprintf(stderr, "BVH build failed\n"); return 1; }
     const ipt_scene* s = ipt_host_scene_view(hs);
     ipt::WideTree wt;
-    if (const char* e = ipt::wide_collapse(s->bvh_nodes, s->n_bvh_nodes, s->n_bvh_slots, leaf_max, wt)) { std::fprintf(stderr, "%s\n", e); return 1; }
-    std::printf("2-wide: %u nodes (leaf %u)  ->  8-wide: %zu nodes, %.2f children per node, depth %u, stack need <= %u\n", s->n_bvh_nodes, leaf2,
-                wt.nodes.size(), wt.sum_children / wt.nodes.size(), wt.depth, wt.stack_need);
+    if (const char* e = ipt::wide_collapse(s->bvh_nodes, s->n_bvh_nodes, s->n_bvh_slots, leaf_max, wt, greedy, c_node)) { std::fprintf(stderr, "%s\n", e); return 1; }
+    std::printf("2-wide: %u nodes (leaf %u)  ->  8-wide: %zu nodes, %.2f children per node, depth %u\n", s->n_bvh_nodes, leaf2,
+                wt.nodes.size(), wt.sum_children / wt.nodes.size(), wt.depth);
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     std::normal_distribution<double> N(0.0, 1.0);
-    const double lo[3] = {30, -480, 30}, hi[3] = {1250, 680, 690};
-    unsigned long long steps = 0, leaves = 0, prims = 0, pops = 0, culled = 0, wrong = 0, hits = 0, pushes = 0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};   // ray origins: inside the box of the sphere centres
+    for (uint32_t k = 0; k < s->n_spheres; k++) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], s->sphere_cxyzr[4 * (size_t)k + a]); hi[a] = std::max(hi[a], s->sphere_cxyzr[4 * (size_t)k + a]); }
+    if (!s->n_spheres) for (int a = 0; a < 3; a++) { lo[a] = -100; hi[a] = 100; }
+    unsigned long long steps = 0, leaves = 0, prims = 0, wrong = 0, hits = 0, bad_links = 0;
     uint32_t max_sp = 0;
-    struct Entry { int32_t link; float tn; };
-    std::vector<Entry> stack(1024);
-    std::vector<Entry> ms[8];
-    for (auto& v : ms) v.reserve(256);
+    struct Group { uint32_t base_imask, hits; };
+    std::vector<Group> stack(256);
     for (int i = 0; i < n_rays; i++) {
         Ray r;
         double len = 0;
@@ -82,66 +88,60 @@ int main(int argc, char** argv)
             oi[k] = o[k] * bi[k];
             sgn[k] = std::signbit(d) ? 1 : 0;
         }
+        const uint32_t oct = (uint32_t)(sgn[0] | sgn[1] << 1 | sgn[2] << 2), octx = oct ^ 7u;
         double best = 1e20;
         uint32_t sp = 0;
-        int32_t cur = 0;
+        Group g{1u << 24, 1u << octx};     // the root: slot 0 of a node whose only inner child is node 0
         for (;;) {
-            if (cur >= 0) {
-                steps++;
-                const ipt::WideNode& nd = wt.nodes[cur];
-                float A[3], B[3];
-                for (int k = 0; k < 3; k++) { A[k] = nd.scale[k] * bi[k]; B[k] = std::fmaf(-8388608.f, A[k], std::fmaf(nd.origin[k], bi[k], -oi[k])); }
-                float tn[8]; bool h[8]; int nh = 0, first = -1;
-                for (int j = 0; j < 8; j++) {
-                    float n = 0.f, f = (float)best;
-                    for (int k = 0; k < 3; k++) {
-                        const float qn = 8388608.f + (float)nd.q[j][2 * k + sgn[k]], qf = 8388608.f + (float)nd.q[j][2 * k + 1 - sgn[k]];
-                        n = std::fmax(n, std::fmaf(qn, A[k], B[k])); f = std::fmin(f, std::fmaf(qf, A[k], B[k]));
-                    }
-                    tn[j] = n; h[j] = n <= f * 1.0000004f;
-                    if (h[j]) { nh++; if (first < 0 || n < tn[first]) first = j; }
+            if (g.hits == 0) {
+                if (sp == 0) break;
+                g = stack[--sp];
+            }
+            uint32_t qb = 31;
+            while (!(g.hits >> qb & 1u)) qb--;
+            const uint32_t slot = qb ^ octx;
+            g.hits &= ~(1u << qb);
+            const uint32_t node = (g.base_imask & 0xFFFFFFu) + (uint32_t)__builtin_popcount((g.base_imask >> 24) & ((1u << slot) - 1u));
+            if (g.hits) { stack[sp++] = g; max_sp = std::max(max_sp, sp); }
+            steps++;
+            const ipt::WideNode& nd = wt.nodes[node];
+            float A[3], B[3];
+            for (int k = 0; k < 3; k++) { A[k] = nd.scale[k] * bi[k]; B[k] = std::fmaf(-8388608.f, A[k], std::fmaf(nd.origin[k], bi[k], -oi[k])); }
+            const float tmax = (float)best * 1.0000004f;
+            uint32_t hit8 = 0, pm = 0;
+            for (int j = 0; j < 8; j++) {
+                float n = 0.f, f = tmax;
+                for (int k = 0; k < 3; k++) {
+                    const float qn = 8388608.f + (float)nd.q[j][2 * k + sgn[k]], qf = 8388608.f + (float)nd.q[j][2 * k + 1 - sgn[k]];
+                    n = std::fmax(n, std::fmaf(qn, A[k], B[k])); f = std::fmin(f, std::fmaf(qf, A[k], B[k]));
                 }
-                if (!nh) cur = ipt::WIDE_EMPTY;
-                else {
-                    int order[8], m = 0;
-                    for (int j = 0; j < 8; j++) if (h[j] && j != first) order[m++] = j;
-                    if (sorted) std::sort(order, order + m, [&](int a, int b) { return tn[a] > tn[b]; });   // farthest first: nearest on top
-                    if (octant) {   // by the child centre along the ray's sign vector (what a per-octant slot order can approximate)
-                        float key[8];
-                        for (int j = 0; j < 8; j++) { key[j] = 0; for (int k = 0; k < 3; k++) key[j] += (sgn[k] ? -1.f : 1.f) * nd.scale[k] * (float)(nd.q[j][2 * k] + nd.q[j][2 * k + 1]); }
-                        std::sort(order, order + m, [&](int a, int b) { return key[a] > key[b]; });
-                    }
-                    if (stat) {     // what the kernel does: increasing (slot ^ octant) from the top of the stack down
-                        const int oct = sgn[0] | sgn[1] << 1 | sgn[2] << 2;
-                        std::sort(order, order + m, [&](int a, int b) { return (a ^ oct) > (b ^ oct); });
-                    }
-                    if (multi) { for (int k = 0; k < m; k++) { ms[order[k] / (8 / multi)].push_back(Entry{nd.link[order[k]], tn[order[k]]}); uint32_t tot = 0, mx = 0; for (int q = 0; q < multi; q++) { tot += ms[q].size(); mx = std::max<uint32_t>(mx, ms[q].size()); } max_sp = std::max(max_sp, mx); } }
-                    else
-                    for (int k = 0; k < m; k++) stack[sp++] = Entry{nd.link[order[k]], tn[order[k]]};
-                    pushes += m;
-                    max_sp = std::max(max_sp, sp);
-                    cur = nd.link[first];
+                if (n <= f) { hit8 |= 1u << j; pm |= nd.pmask & (0xFu << (4 * j)); }
+            }
+            const uint32_t prim_base = (uint32_t)nd.q[0][6] | (uint32_t)nd.q[0][7] << 8 | (uint32_t)nd.q[1][6] << 16 | (uint32_t)nd.q[1][7] << 24;
+            // the links say the same as the implicit addressing
+            for (int j = 0; j < 8; j++) {
+                const bool inner = (nd.base_imask >> (24 + j)) & 1u, leaf = (nd.pmask >> (4 * j)) & 0xFu;
+                if (inner && nd.link[j] != (int32_t)((nd.base_imask & 0xFFFFFFu) + __builtin_popcount((nd.base_imask >> 24) & ((1u << j) - 1u)))) bad_links++;
+                if (leaf) {
+                    const uint32_t code = (uint32_t)~nd.link[j];
+                    if ((code >> 4) != prim_base + (uint32_t)__builtin_popcount(nd.pmask & ((1u << (4 * j)) - 1u)) || (code & 15u) + 1u != (uint32_t)__builtin_popcount(nd.pmask & (0xFu << (4 * j)))) bad_links++;
                 }
-            } else {
-                leaves++;
-                const uint32_t code = (uint32_t)~cur, f = code >> 4, cnt = (code & 15u) + 1u;
-                for (uint32_t k = 0; k < cnt; k++) { prims++; best = hit_prim(s, s->bvh_slot_prim[f + k], r, best); }
-                cur = ipt::WIDE_EMPTY;
+                if (!inner && !leaf && nd.link[j] != ipt::WIDE_EMPTY) bad_links++;
             }
-            while (multi && cur == ipt::WIDE_EMPTY) {
-                int bq = -1;
-                for (int q = 0; q < multi; q++) if (!ms[q].empty() && (bq < 0 || ms[q].back().tn < ms[bq].back().tn)) bq = q;
-                if (bq < 0) break;
-                pops++;
-                const Entry e = ms[bq].back(); ms[bq].pop_back();
-                if ((double)e.tn <= best * 1.0000004) cur = e.link; else culled++;
+            leaves += __builtin_popcount(hit8 & ~(nd.base_imask >> 24));
+            while (pm) {
+                const uint32_t bit = (uint32_t)__builtin_ctz(pm);
+                pm &= pm - 1u;
+                const uint32_t slot_new = prim_base + (uint32_t)__builtin_popcount(nd.pmask & ((1u << bit) - 1u));
+                prims++;
+                best = hit_prim(s, s->bvh_slot_prim[wt.perm[slot_new]], r, best);
             }
-            while (!multi && cur == ipt::WIDE_EMPTY && sp) {
-                pops++;
-                const Entry e = stack[--sp];
-                if ((double)e.tn <= best * 1.0000004) cur = e.link; else culled++;
-            }
-            if (cur == ipt::WIDE_EMPTY) break;
+            // hit inner children, in the order the device's table gives: slot j at bit 7 - (j ^ oct)
+            const uint32_t inner = hit8 & (nd.base_imask >> 24);
+            uint32_t permuted = 0;
+            for (uint32_t j = 0; j < 8; j++) permuted |= ((inner >> j) & 1u) << (7u - (j ^ oct));
+            if (g.hits) { /* already pushed */ }
+            g = Group{nd.base_imask, permuted};
         }
         hits += best < 1e20;
         if (check) {
@@ -151,10 +151,9 @@ int main(int argc, char** argv)
             wrong += lin != best;
         }
     }
-    std::printf("per ray: %.2f node steps, %.2f leaf steps, %.2f primitive tests, %.2f pushes, %.2f pops (%.2f culled); deepest stack %u; %.1f %% hit\n",
-                (double)steps / n_rays, (double)leaves / n_rays, (double)prims / n_rays, (double)pushes / n_rays, (double)pops / n_rays,
-                (double)culled / n_rays, max_sp, 100.0 * hits / n_rays);
+    std::printf("per ray: %.2f node steps, %.2f leaf children entered, %.2f primitive tests; deepest stack %u (tree depth %u); %.1f %% hit; %llu link mismatches\n",
+                (double)steps / n_rays, (double)leaves / n_rays, (double)prims / n_rays, max_sp, wt.depth, 100.0 * hits / n_rays, bad_links);
     if (check) std::printf("check: %llu of %d rays differ from the linear scan\n", wrong, n_rays);
     ipt_host_free_scene(hs);
-    return wrong ? 1 : 0;
+    return (wrong || bad_links) ? 1 : 0;
 }
