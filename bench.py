@@ -188,16 +188,16 @@ def cpu_baseline(wl, seconds_budget=20.0):
         cores = os.cpu_count() or 1
         W, H = wl["width"] or 1280, wl["height"] or 720
         n_cells = O.ref().ref_num_cells(W, H)
-        cells = spread_cells(n_cells, min(n_cells, 4 * cores))
-        spp = 4
+        cells = list(range(n_cells))            # every cell: the same sample of the frame as the reference arm (--ref-stride 1)
+        spp = 2
         ref_scene = scene_file(wl["scene"]) if wl["scene"].endswith("_x3") else wl["scene"]
         dt = O.ref_time_cells(ref_scene, spp, wl["depth"], wl["width"], wl["height"], cells, cores)
         # scale spp so that the sample takes ~seconds_budget, then time that
-        spp = int(max(4, min(256, spp * seconds_budget / max(dt, 1e-3))))
+        spp = int(max(2, min(256, spp * seconds_budget / max(dt, 1e-3))))
         dt = O.ref_time_cells(ref_scene, spp, wl["depth"], wl["width"], wl["height"], cells, cores)
         samples = len(cells) * (W * H / n_cells) * spp
         return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                "sample": f"{len(cells)} of the reference's {n_cells} thread cells (spread over the frame) at {spp} spp, depth {wl['depth']}: {int(samples)} samples in {dt:.1f} s, fp64"}
+                "sample": f"all {n_cells} thread cells of the reference (the whole frame) at {spp} spp, depth {wl['depth']}: {int(samples)} samples in {dt:.1f} s, fp64"}
     except Exception as e:   # the baseline is reported, never required for the GPU number
         return {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -297,10 +297,11 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
     t_wall0 = time.perf_counter()
     dev_ms, bounces, samples, launches, qbytes = 0.0, 0, 0, 0, 0
     work = {"node_steps": 0, "leaf_steps": 0, "sphere_tests": 0, "rect_tests": 0}
+    box_tests = 0
     for _ in range(steps):
         st = step()
         dev_ms += st["render_ms"]; bounces += st["traced_bounces"]; samples += st["samples"]; launches += st["kernel_launches"]
-        qbytes += st["queue_bytes"]
+        qbytes += st["queue_bytes"]; box_tests += st.get("box_tests", 0)
         for k in work:
             work[k] += st.get(k, 0)
     comm.barrier()
@@ -378,12 +379,15 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
         r0_ms = dev_ms / steps
         is_bvh = bool(hs.view.contents.n_bvh_nodes)
         if is_bvh:
-            # SURVEY.md §8d with a BVH: 19 per sphere test + 31 per rectangle test + 18 per box test + 60 per bounce, with the
-            # tests COUNTED on the device during the timed renders (ipt_stats); an 8-wide node step decodes 8 child boxes
+            # SURVEY.md §8d with an acceleration structure: 19 per sphere test + 31 per rectangle test + 18 per box test + 60 per
+            # bounce, with the tests COUNTED on the device during the timed renders (ipt_stats); a cell step of the uniform grid
+            # (no boxes) is charged 12 (three boundary distances, their minimum, one re-evaluated)
             n_b = max(1.0, float(bounces))
-            flops_per_bounce = (19.0 * work["sphere_tests"] + 31.0 * work["rect_tests"] + 18.0 * 8.0 * work["node_steps"]) / n_b + 60.0
-            flops_note = (f"counted on the device: {work['node_steps'] / n_b:.2f} node steps (8 boxes each), {work['leaf_steps'] / n_b:.2f} leaf steps, "
-                          f"{work['sphere_tests'] / n_b:.2f} sphere + {work['rect_tests'] / n_b:.2f} rectangle tests per cast")
+            work["box_tests"] = box_tests
+            grid = box_tests == 0 and work["node_steps"] > 0
+            flops_per_bounce = (19.0 * work["sphere_tests"] + 31.0 * work["rect_tests"] + 18.0 * box_tests + (12.0 * work["node_steps"] if grid else 0.0)) / n_b + 60.0
+            flops_note = (f"counted on the device: {work['node_steps'] / n_b:.2f} {'cell steps (uniform grid)' if grid else 'node steps'}, {box_tests / n_b:.2f} box tests, "
+                          f"{work['leaf_steps'] / n_b:.2f} {'occupied cells' if grid else 'leaf steps'}, {work['sphere_tests'] / n_b:.2f} sphere + {work['rect_tests'] / n_b:.2f} rectangle tests per cast")
         else:
             flops_per_bounce, flops_note = float(wl["flops"]), "19 S + 31 R + 60 (brute force, SURVEY.md §8d)"
         ach_fp32 = my_bounces_per_step * flops_per_bounce / (r0_ms * 1e-3) / 1e12
@@ -400,7 +404,7 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
         # measured DRAM bytes of the dominant kernel per launch (one ncu --set full capture, profiles/dram_traffic.json)
         traffic = tr.get("dram_bytes_per_launch")
         wi = tr.get("warp_instructions_per_bounce")
-        kernel = tr.get("kernel", "k_extend_wide + k_bounce<MODE_SHADE>" if is_bvh else "k_bounce_fast")
+        kernel = tr.get("kernel", ("k_extend_grid" if hs.view.contents.grid_res[0] else "k_extend_bvh") + " + k_bounce<MODE_SHADE>" if is_bvh else "k_bounce_fast")
         roof_fp32 = {"bound": "fp32", "achieved": ach_fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_fp32 / fp32_peak,
                      "traffic": traffic, "peak_source": "148 SM x 128 lanes x 2 x max SM clock (no measured fp32 figure in MEASURED_PEAKS.json)",
                      "frac_at_observed_clock": ach_fp32 / (sm_count * FP32_LANES_PER_SM * 2 * clk * 1e6 / 1e12),
@@ -437,7 +441,7 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
                        "traced_bounces_per_step": int(tot_bounces),
                        "pixels_with_camera_rays": int(active_pixels), "pixels": W * H,
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
-                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-10 keyed by pixel/sample/bounce"},
+                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-7 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "gbounces_per_s": tot_bounces / (e2e_ms * 1e-3) / 1e9,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "result": "fp64 frame" if fp64 else "fp32 frame", "rank0_kernel_ms_events": e2e_events_ms,

@@ -53,24 +53,31 @@ template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
 template <typename R> __device__ __forceinline__ V3<R> normalize(V3<R> a) { return a * rsqrt_(dot(a, a)); }
 
 // ---------------------------------------------------------------------------------------------- RNG
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  One block = the four uniforms one scatter event can use,
+// Philox4x32-7 (Salmon, Moraes, Dror, Shaw, SC'11: Philox4x32 with R rounds; 7 is the smallest R that is Crush-resistant
+// in their Table 2, 10 their default with a safety margin; Random123's known answers exist for both and pin the oracle's
+// copy, tests/test_oracle_pin.py).  Round 1 used 10 rounds: 81 of ~540 warp instructions per 32 rays and bounce
+// (profiles/r01_ncu_spheres4k_final_deep_pass.txt), 7 rounds save 24 of them.  One block = the four uniforms one scatter event can use,
 // addressed by (pixel, sample, lane<<8|depth): no generator state travels with a ray, and the image does not
 // depend on how rays are scheduled, batched, tiled or split over GPUs.  The reference seeds one XORWOW stream per
 // CUDA thread (Renderer.cu:95-97) and walks it through ~1900 pixels, which no parallel schedule can reproduce;
 // parity with it is therefore statistical, and exact against the oracle run on this same counter stream.
-// The ten round keys k + r*W are the same for every thread of a render: the host expands them once into the kernel
+// The round keys k + r*W are the same for every thread of a render: the host expands them once into the kernel
 // parameters (constant bank), so a round is two IMAD.WIDE and two LOP3 with a constant operand.
-struct PhiloxKeys { uint32_t k[20]; };
+#ifndef IPT_PHILOX_ROUNDS
+#define IPT_PHILOX_ROUNDS 7
+#endif
+static constexpr int PHILOX_ROUNDS = IPT_PHILOX_ROUNDS;
+struct PhiloxKeys { uint32_t k[2 * PHILOX_ROUNDS]; };
 __host__ __device__ inline PhiloxKeys philox_expand(uint32_t k0, uint32_t k1)
 {
     PhiloxKeys ks;
-    for (int r = 0; r < 10; r++) { ks.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; ks.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    for (int r = 0; r < PHILOX_ROUNDS; r++) { ks.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; ks.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
     return ks;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks)
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks)
 {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < PHILOX_ROUNDS; r++) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
         c0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks.k[2 * r]; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks.k[2 * r + 1]; c3 = (uint32_t)p0;
     }
@@ -530,6 +537,7 @@ struct FastScene {
     uint32_t ax0_x, ax0_y, ax0_z, n_x, n_y, n_z;
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
+    bool box_uniform;                        // see fast_axis_pair
 };
 __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
@@ -538,12 +546,13 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 // The list sizes come in as kernel parameters (uniform registers / constant bank), not from the blob in shared memory.
 struct FastHeader {
     uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
+    uint32_t box_uniform;   // box room whose two rectangles per axis differ only in their plane coordinate, lower one first
     uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
 };
 __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
     FastHeader h;
-    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj;
+    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_uniform = 0;
     h.off_sphobj = 2 + n_sph;
     h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
     h.off_gen = h.off_axs + 2 * (nx + ny + nz);
@@ -554,7 +563,7 @@ __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, u
 __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen;
+    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_uniform = hd.box_uniform != 0;
     f.sph = reinterpret_cast<const float4*>(blob + 2);
     f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
     f.axs = reinterpret_cast<const float4*>(blob + hd.off_axs);
@@ -614,6 +623,25 @@ __device__ __forceinline__ void fast_axis_fixed(const float4* __restrict__ axs, 
     }
 }
 
+// The two parallel walls of a box room along axis K, for a ray whose origin lies between them (FastHeader::box_uniform: the
+// host has checked that the two records differ only in the plane coordinate and stored the lower wall first).  The wall
+// the ray travels away from has t = (p - o_K) / d_K <= 0 (or -inf / NaN for d_K = 0) and fails `t > 1e-4` in the scan of
+// both, so testing only the wall ahead gives the bit-identical result with half the tests.
+template <int K, int FIRST_REC>
+__device__ __forceinline__ void fast_axis_pair(const float4* __restrict__ axs, const V3<float>& o, const V3<float>& d, float inv_dk, FastHit& best)
+{
+    constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
+    const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
+    const float4 a = axs[2 * FIRST_REC];
+    const float hj = axs[2 * FIRST_REC + 1].x, p_up = axs[2 * (FIRST_REC + 1)].x;
+    const bool up = comp<K>(d) > 0.f;
+    const float t = ((up ? p_up : a.x) - ok) * inv_dk;
+    const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
+    const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
+    best.t = hit ? t : best.t;
+    best.code = hit ? ((((uint32_t)(K + 1) << 28) | (uint32_t)FIRST_REC) + (up ? 1u : 0u)) : best.code;
+}
+
 // Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.  `self` is the hit CODE of
 // the surface the ray starts on (the fast kernel's queues are private to it), NO_OBJECT for camera rays.
 __device__ __forceinline__ void fast_sphere(const float4 sp, uint32_t s, uint32_t self_sphere, const V3<float>& o, const V3<float>& d, FastHit& best)
@@ -648,9 +676,18 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
     if (SHAPE > 0) {
 #pragma unroll
         for (int s = 0; s < SHAPE - 1; s++) fast_sphere(f.sph[s], (uint32_t)s, self_sphere, o, d, best);
-        fast_axis_fixed<0, 0, 2>(f.axs, o, d, rcp_fast(d.x), best);
-        fast_axis_fixed<1, 2, 2>(f.axs, o, d, rcp_fast(d.y), best);
-        fast_axis_fixed<2, 4, 2>(f.axs, o, d, rcp_fast(d.z), best);
+        // origin between the walls of every pair (on a wall counts): only the wall ahead can be hit (fast_axis_pair)
+        const bool between = f.box_uniform && o.x >= f.axs[0].x && o.x <= f.axs[2].x && o.y >= f.axs[4].x && o.y <= f.axs[6].x &&
+                             o.z >= f.axs[8].x && o.z <= f.axs[10].x;
+        if (between) {
+            fast_axis_pair<0, 0>(f.axs, o, d, rcp_fast(d.x), best);
+            fast_axis_pair<1, 2>(f.axs, o, d, rcp_fast(d.y), best);
+            fast_axis_pair<2, 4>(f.axs, o, d, rcp_fast(d.z), best);
+        } else {
+            fast_axis_fixed<0, 0, 2>(f.axs, o, d, rcp_fast(d.x), best);
+            fast_axis_fixed<1, 2, 2>(f.axs, o, d, rcp_fast(d.y), best);
+            fast_axis_fixed<2, 4, 2>(f.axs, o, d, rcp_fast(d.z), best);
+        }
         return best;
     }
 #pragma unroll 2

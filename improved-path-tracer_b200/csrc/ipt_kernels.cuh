@@ -34,7 +34,17 @@ static constexpr int BVH_TOP_NODES = 512; // top of the BVH staged in shared mem
 // (k_bounce_fast claims no work: there [WORK + p] is the depth pass p starts at and [WORK_EXTEND + p] its bounce count)
 static constexpr int MAX_PASSES = 256;
 static constexpr int CNT = 0, WORK = MAX_PASSES, WORK_EXTEND = 2 * MAX_PASSES;   // WORK_EXTEND: claim counter of k_extend_bvh
-static constexpr int N_COUNTERS = 3 * MAX_PASSES;
+static constexpr int CLAIM = 3 * MAX_PASSES;   // k_bounce_fast: next unclaimed ray of pass p (slices of 32 are claimed by warps)
+static constexpr int N_COUNTERS = 4 * MAX_PASSES;
+
+// Uniform grid (ipt_scene::grid_*, host/grid.cpp) as k_extend_grid sees it
+static constexpr uint32_t GRID_MAX_BIG = 64;
+struct GridHeader {
+    uint32_t res[3];
+    uint32_t n_big;
+    float lo[3], hi[3], cs[3], inv_cs[3];
+    uint32_t big[GRID_MAX_BIG];     // slots of the primitives every ray tests
+};
 
 template <typename R> struct KParams {
     SceneView<R> sc;
@@ -75,6 +85,10 @@ template <typename R> struct KParams {
     uint2* wide_spill;          // k_extend_cw: stack entries beyond CW_STACK, wide_spill_cap per resident lane
     uint32_t wide_spill_cap;
     uint32_t leaf_min;          // k_extend_cw: lanes with a primitive to test that make a primitive step worth a warp instruction
+    const uint2* grid_cells;    // k_extend_grid: {first reference, count} per cell, null = walk a tree
+    const uint32_t* grid_refs;  // k_extend_grid: slots, cell by cell
+    GridHeader grid;
+    uint32_t static_slices;     // k_bounce_fast: 1 = slices assigned to warps statically instead of claimed (A/B runs)
 };
 
 // Deterministic accumulation: a contribution is rounded once to a multiple of 1/fixed_scale and added with an
@@ -119,7 +133,7 @@ __device__ __forceinline__ void camera_ray(const KParams<R>& p, uint32_t px, uin
     const R stepZ = (pz < p.H / 2) ? (R)(p.H / 2 - pz) - corr : ((R)p.H / (R)2 - (R)pz - (R)1) + ((corr == (R)0) ? (R)1 : corr);
     r.d = normalize(p.camD + p.camX * stepX * p.fov + p.camZ * stepZ * p.fov);                       // :127
     const uint32_t pixel = pz * p.W + px;
-    const uint4 rnd = philox4x32_10(pixel, sample, NODE_CAMERA, CTR_TAG, p.keys);
+    const uint4 rnd = philox4x32(pixel, sample, NODE_CAMERA, CTR_TAG, p.keys);
     R jx = s24<R>(rnd.x), jz = s24<R>(rnd.y);                                                         // :133-134
     if (p.flags & 0x10u) {   // IPT_FLAG_STRATIFIED (extension): jitter of sample i drawn inside stratum i of an n x n grid
         const uint32_t n = p.strat_n;
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                         if (nthr.x != (R)0 || nthr.y != (R)0 || nthr.z != (R)0 || pending) {
                             const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                             const V3<R> P = r.o + r.d * h.t;                                       // :156,:179,:207
-                            const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
+                            const uint4 rnd = philox4x32(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG, p.keys);
                             const Spawn<R> sp = scatter<R>(isRect, sc.geom[4 * (size_t)h.slot], (int)m0.w, P, r.d, depth, rnd);
                             bool alive = sp.has0;
                             const bool onS = isRect || fabs(dot(r.d, r.d) - (R)1) < (R)1e-3;
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                                 // "diffuse" lobe (AObject.hpp:35-45: cube-normalised, flipped into the hemisphere of N,
                                 // weight = colour) has density 1 / (12 max|w_i|^3) there, which weights the sample.
                                 nee = true;
-                                const uint4 rl = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 2u, p.keys);
+                                const uint4 rl = philox4x32(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 2u, p.keys);
                                 const uint32_t li = min((uint32_t)(u23<R>(rl.x) * (R)sc.n_lights), sc.n_lights - 1u);
                                 const double* L = sc.lights + 8 * (size_t)li;
                                 const V3<R> lc = mk<R>((R)__ldg(L), (R)__ldg(L + 1), (R)__ldg(L + 2));
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bounce(const __grid_constant_
                             }
                             if ((p.flags & 0x8u) && depth >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension, off by default)
                                 const R q = fmin((R)1, fmax((R)0.05, fmax(nthr.x, fmax(nthr.y, nthr.z))));
-                                const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
+                                const uint4 rr = philox4x32(r.pixel, sample, (lane_id << 8) | depth, CTR_TAG + 1u, p.keys);
                                 if (u23<R>(rr.x) >= q) alive = false;
                                 else nthr = nthr * ((R)1 / q);
                             }
@@ -556,6 +570,154 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
     }
     if (my_traced) atomicAdd(p.traced, my_traced);
     add_work(p.traced, w_nodes, 2u * w_nodes, w_leaves, w_sph, w_prims - w_sph);
+}
+
+// ---------------------------------------------------------------------------------------------- grid traversal
+// Stage 2 of the split pipeline over the uniform grid (ipt_scene::grid_*, host/grid.cpp): the nearest hit of
+// Renderer.cu:227-243 for scenes of many small, evenly spread primitives, found by walking the cells the ray passes through
+// (3D-DDA) instead of a hierarchy - on BASELINE config 5 about 13 cell steps and 17 primitive tests per ray against 49 inner
+// nodes (98 box tests) and 18 primitive tests through the 2-wide tree.  One ray per lane, persistent warps with lane-level
+// refill as in k_extend_bvh; primitives are tested by the same typed records and arithmetic (test_bslot) with the reference's
+// tie rule, so frames are bit-identical with the tree traversals.
+//  * a new ray first tests the "big" primitives (walls, large lights: up to 64 slots kept in the kernel parameters), then is
+//    clipped against the grid's box;
+//  * per cell: one 8-byte load {first reference, count}; the references are slots, tested one per lane and iteration;
+//  * a ray ends when the exit distance of the cell it has just finished is not below its nearest hit (a primitive that
+//    overlaps several cells may report a hit beyond the current cell: it stays a candidate and the walk goes on), or when
+//    it leaves the grid;
+//  * the next boundary along an axis is evaluated from the integer cell coordinate, t = i * (cell / d) + (lo - o) / d, not
+//    accumulated: no drift over hundreds of steps; what is left (~1e-4 at |x| ~ 1e3) is covered 40 times by the padding of
+//    the boxes the host filed the primitives under;
+//  * cell steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (descend_min,
+//    leaf_min) or nobody wants the other.
+static constexpr int GRID_BURST = 4;
+__global__ void __launch_bounds__(BLOCK_THREADS, 4) k_extend_grid(const __grid_constant__ KParams<float> p)
+{
+    const SceneView<float> sc = p.sc;
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const uint32_t n_in = p.counters[CNT + p.depth];
+    uint32_t* work = p.counters + WORK_EXTEND + p.depth;
+    const float tiny = 1e-18f;
+    const uint32_t rx = p.grid.res[0], rxy = p.grid.res[0] * p.grid.res[1];
+
+    bool exhausted = false;
+    uint32_t my_traced = 0;
+    uint32_t w_cells = 0, w_prims = 0, w_sph = 0, w_occupied = 0;        // work counters of ipt_stats
+    bool has = false, marching = false;
+    uint32_t idx = 0, self = NO_OBJECT;
+    bool onSurf = false;
+    V3<float> o = mk<float>(0, 0, 0), d = o, inv = o;
+    V3<float> fi = o, tmx = o, A = o, B = o;                              // cell coordinate, next boundary per axis, t = fi * A + B
+    uint32_t cell = 0;
+    uint32_t pr_cur = 0, pr_end = 0;                                      // references of the current cell still to test
+    float t_exit = 0.f;                                                   // where the ray leaves the current cell
+    Hit<float> best;
+    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+
+    for (;;) {
+        if (has && !marching && pr_cur >= pr_end) {                       // finished (or never entered the grid)
+            __stcs(p.hits + idx, make_uint2(__float_as_uint(best.t), best.slot));
+            has = false;
+        }
+        // ---- refill
+        const uint32_t idle = __ballot_sync(0xffffffffu, !has);
+        if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= p.refill_min)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (uint32_t)__popc(idle) >= n_in;
+            if (!has) {
+                idx = base + __popc(idle & lt_mask);
+                if (idx < n_in) {
+                    const uint4 a = __ldcs(p.qin.base + idx), b = __ldcs(p.qin.base + p.qin.capacity + idx), c = __ldcs(p.qin.base + 2u * p.qin.capacity + idx);
+                    o = mk<float>(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+                    d = mk<float>(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+                    onSurf = (c.z & META_ONSURF) != 0; self = c.w;
+                    inv = mk<float>(1.f / d.x, 1.f / d.y, 1.f / d.z);       // primitive tests: +-inf for zero components (Plane.cu:55)
+                    best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+                    has = true; marching = false; pr_cur = pr_end = 0;
+                    my_traced++;
+                    for (uint32_t k = 0; k < p.grid.n_big; k++) { test_bslot(sc, p.grid.big[k], o, d, inv, self, onSurf, best, w_sph); w_prims++; }
+                    // the grid's box: components below 1e-18 become +-1e-18, so no inf - inf arises (as the tree traversals do)
+                    const V3<float> bi = mk<float>(rcp_fast(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), rcp_fast(fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                                                   rcp_fast(fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+                    const float ax = (p.grid.lo[0] - o.x) * bi.x, bx = (p.grid.hi[0] - o.x) * bi.x;
+                    const float ay = (p.grid.lo[1] - o.y) * bi.y, by = (p.grid.hi[1] - o.y) * bi.y;
+                    const float az = (p.grid.lo[2] - o.z) * bi.z, bz = (p.grid.hi[2] - o.z) * bi.z;
+                    const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+                    const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t));
+                    if (t0 <= t1) {
+                        // the cell of the entry point (clamped: an entry point on the far faces rounds to res)
+                        const float ex = fmaf(d.x, t0, o.x), ey = fmaf(d.y, t0, o.y), ez = fmaf(d.z, t0, o.z);
+                        fi.x = fminf(fmaxf(floorf((ex - p.grid.lo[0]) * p.grid.inv_cs[0]), 0.f), (float)(p.grid.res[0] - 1u));
+                        fi.y = fminf(fmaxf(floorf((ey - p.grid.lo[1]) * p.grid.inv_cs[1]), 0.f), (float)(p.grid.res[1] - 1u));
+                        fi.z = fminf(fmaxf(floorf((ez - p.grid.lo[2]) * p.grid.inv_cs[2]), 0.f), (float)(p.grid.res[2] - 1u));
+                        cell = (uint32_t)fi.x + rx * (uint32_t)fi.y + rxy * (uint32_t)fi.z;
+                        // boundary an axis crosses next: the upper face of the cell when the ray goes up, else the lower one
+                        A = mk<float>(p.grid.cs[0] * bi.x, p.grid.cs[1] * bi.y, p.grid.cs[2] * bi.z);
+                        // (by the sign of the CLAMPED direction: a component of +0 walks up, like +1e-18)
+                        B = mk<float>(fmaf(p.grid.lo[0] - o.x, bi.x, bi.x > 0.f ? A.x : 0.f), fmaf(p.grid.lo[1] - o.y, bi.y, bi.y > 0.f ? A.y : 0.f),
+                                      fmaf(p.grid.lo[2] - o.z, bi.z, bi.z > 0.f ? A.z : 0.f));
+                        tmx = mk<float>(fmaf(fi.x, A.x, B.x), fmaf(fi.y, A.y, B.y), fmaf(fi.z, A.z, B.z));
+                        marching = true;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, has) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- cell steps: leave the finished cell (if any) and open the next one.  Up to GRID_BURST steps before the warp looks
+        // at its finished and idle lanes again; the burst ends early when few lanes still march and others hold primitives.
+#pragma unroll 1
+        for (int it = 0; it < GRID_BURST; it++) {
+            const bool want_cell = has && marching && pr_cur >= pr_end;
+            const uint32_t m_cell = __ballot_sync(0xffffffffu, want_cell);
+            if (m_cell == 0) break;
+            if ((uint32_t)__popc(m_cell) < p.descend_min && __any_sync(0xffffffffu, has && pr_cur < pr_end)) break;
+            if (want_cell) {
+                const uint2 ce = __ldg(p.grid_cells + cell);
+                t_exit = fminf(tmx.x, fminf(tmx.y, tmx.z));
+                pr_cur = ce.x; pr_end = ce.x + ce.y;
+                w_cells++; w_occupied += ce.y ? 1u : 0u;
+                // step now: the state is cheaper to keep one cell ahead than to carry "which axis" along
+                const bool sx = tmx.x <= tmx.y && tmx.x <= tmx.z, sy = !sx && tmx.y <= tmx.z;
+                const float a_k = sx ? A.x : (sy ? A.y : A.z);              // its sign is the direction of travel along the axis
+                const float stepf = a_k > 0.f ? 1.f : -1.f;
+                const uint32_t stride = sx ? 1u : (sy ? rx : rxy);
+                const float f = (sx ? fi.x : (sy ? fi.y : fi.z)) + stepf;
+                const float lim = (float)(sx ? p.grid.res[0] : (sy ? p.grid.res[1] : p.grid.res[2]));
+                const bool inside = f >= 0.f && f < lim;
+                const float nt = fmaf(f, a_k, sx ? B.x : (sy ? B.y : B.z));
+                fi.x = sx ? f : fi.x; fi.y = sy ? f : fi.y; fi.z = (!sx && !sy) ? f : fi.z;
+                tmx.x = sx ? nt : tmx.x; tmx.y = sy ? nt : tmx.y; tmx.z = (!sx && !sy) ? nt : tmx.z;
+                cell = a_k > 0.f ? cell + stride : cell - stride;
+                // the walk ends with this cell when the next one lies outside, or (empty cell) when the nearest hit is before its exit
+                if (!inside || (ce.y == 0u && best.t <= t_exit)) marching = false;
+            }
+        }
+        // ---- primitive steps: one reference per lane and step
+#pragma unroll 1
+        for (int it = 0; it < GRID_BURST; it++) {
+            const bool want_prim = has && pr_cur < pr_end;
+            const uint32_t m_prim = __ballot_sync(0xffffffffu, want_prim);
+            if (m_prim == 0) break;
+            // few lanes hold primitives: leave them waiting only if enough lanes march for a cell step to run (progress either way)
+            if ((uint32_t)__popc(m_prim) < p.leaf_min && (uint32_t)__popc(__ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end)) >= p.descend_min) break;
+            if (want_prim) {
+                const uint32_t slot = __ldg(p.grid_refs + pr_cur);
+                pr_cur++;
+                test_bslot(sc, slot, o, d, inv, self, onSurf, best, w_sph);
+                w_prims++;
+                // the cell is done: stop if the nearest hit lies before its exit
+                if (pr_cur >= pr_end && best.t <= t_exit) marching = false;
+            }
+        }
+    }
+    my_traced = __reduce_add_sync(0xffffffffu, my_traced);
+    if (lane == 0 && my_traced) atomicAdd(p.traced, (unsigned long long)my_traced);
+    add_work(p.traced, w_cells, 0u, w_occupied, w_sph, w_prims - w_sph);
 }
 
 // ---------------------------------------------------------------------------------------------- 8-wide traversal
@@ -854,8 +1016,6 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_in = FIRST ? p.n_first : p.counters[CNT + p.pass];
     uint32_t* out_count = p.counters + CNT + p.pass + 1;
-    const uint32_t warp_global = blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5);
-    const uint32_t stride = gridDim.x * BLOCK_THREADS;   // rays per sweep of the whole grid
     uint32_t my_traced = 0;                              // per warp and pass: far below 2^32
     uint32_t blk_base = 0, blk_used = OUT_BLOCK;         // no block reserved yet
 
@@ -875,14 +1035,34 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
         else blk_used += tot;
     };
 
-    uint32_t i = warp_global * 32u + lane;
+    // Slices of 32 rays are claimed from a per-pass counter, two ahead: the slice being computed, the next one (its records
+    // already on their way into shared memory) and the claim for the one after (issued, not yet read).  Static assignment
+    // (slice = warp + k * warps) left the SMs idle at the end of a pass: warps on SMs with slower memory finish late, and
+    // ncu showed 30.5 % achieved against 37.5 % theoretical occupancy (profiles/r01_ncu_spheres4k_final_deep_pass.txt).
+    uint32_t* claim_ctr = p.counters + CLAIM + p.pass;
+    // (p.static_slices, IPT_STATIC_SLICES=1: the static assignment, for A/B runs - no atomics, slice = warp + k * warps)
+    const uint32_t stride = gridDim.x * BLOCK_THREADS;
+    uint32_t static_next = (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) * 32u;
+    auto claim_issue = [&]() {
+        uint32_t v = 0;
+        if (p.static_slices) { v = static_next; static_next = static_next + stride < static_next ? 0xFFFFFFE0u : static_next + stride; }
+        else if (lane == 0) v = atomicAdd(claim_ctr, 32u);
+        return v;
+    };
+    auto prefetch = [&](uint32_t base, int b) {
+        const uint32_t j = base + lane;
+        if (!FIRST && j < n_in)
+            for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + (b * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + j);
+        cp_async_commit();
+    };
+    uint32_t cur = __shfl_sync(0xffffffffu, claim_issue(), 0);
+    uint32_t nxt = __shfl_sync(0xffffffffu, claim_issue(), 0);
+    uint32_t pending = claim_issue();
     int buf = 0;
-    if (!FIRST && i < n_in) {
-        for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + (buf * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + i);
-    }
-    cp_async_commit();
+    prefetch(cur, buf);
 
-    for (; (i & ~31u) < n_in; i += stride) {
+    for (; cur < n_in; cur = nxt, nxt = __shfl_sync(0xffffffffu, pending, 0), pending = claim_issue()) {
+        const uint32_t i = cur + lane;
         bool live = i < n_in;
         Ray<float> r;
         if (FIRST) {
@@ -891,10 +1071,7 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
             if (live) camera_ray(p, px, pz, sample, r);
         } else {
             cp_async_wait_all();
-            const uint32_t nxt = i + stride;
-            if (nxt < n_in && nxt > i)
-                for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + ((buf ^ 1) * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + nxt);
-            cp_async_commit();
+            prefetch(nxt, buf ^ 1);
             if (live) {
                 const uint4 a = stagebuf[(buf * 3 + 0) * BLOCK_THREADS + threadIdx.x], b = stagebuf[(buf * 3 + 1) * BLOCK_THREADS + threadIdx.x],
                             c = stagebuf[(buf * 3 + 2) * BLOCK_THREADS + threadIdx.x];
@@ -927,12 +1104,12 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                     if (go) {
                         const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
-                        const uint4 rnd = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
+                        const uint4 rnd = philox4x32(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
                         const Spawn<float> sp = scatter_fast<(SHAPE > 0)>(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
                         bool alive = sp.has0;
                         if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
-                            const uint4 rr = philox4x32_10(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG + 1u, p.keys);
+                            const uint4 rr = philox4x32(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG + 1u, p.keys);
                             if (u23<float>(rr.x) >= q) alive = false;
                             else nthr = nthr * (1.f / q);
                         }

@@ -102,6 +102,10 @@ struct ipt_ctx {
     uint32_t* slot_obj = nullptr;
     float4* nodes = nullptr;
     float4* bslot = nullptr;         // fp32 BVH leaf records (2 x float4 per slot), built when the scene has a BVH
+    // uniform grid (ipt_scene::grid_*): {first reference, count} per cell, the references (slots), the big primitives' slots
+    uint2* grid_cells = nullptr;
+    uint32_t* grid_refs = nullptr;
+    GridHeader grid_hd = {};
     WideNode* wide = nullptr;        // the 8-wide quantised tree derived from the 2-wide one (ipt_wide.h), fp32 traversal
     uint32_t n_wide = 0, wide_stack_need = 0, wide_depth = 0;
     uint2* wide_spill = nullptr;     // stack entries beyond the shared-memory part, per resident ray of k_extend_wide
@@ -109,7 +113,7 @@ struct ipt_ctx {
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
     FastHeader fast_hd = {};
-    size_t scene_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // sizes of the scene allocations (reused when unchanged)
+    size_t scene_bytes[8] = {0, 0, 0, 0, 0, 0, 0};   // sizes of the scene allocations (reused when unchanged)
     // render state
     uint4* q[2] = {nullptr, nullptr};
     size_t q_bytes = 0;
@@ -194,7 +198,8 @@ extern "C" ipt_ctx* ipt_ctx_create(int device)
 static void free_scene(ipt_ctx* c)
 {
     cudaFree(c->geom32); cudaFree(c->geom64); cudaFree(c->mat32); cudaFree(c->mat64); cudaFree(c->slot_obj); cudaFree(c->nodes); cudaFree(c->fast_blob); cudaFree(c->bslot);
-    cudaFree(c->wide);
+    cudaFree(c->wide); cudaFree(c->grid_cells); cudaFree(c->grid_refs);
+    c->grid_cells = nullptr; c->grid_refs = nullptr; c->grid_hd = GridHeader{};
     c->bslot = nullptr; c->wide = nullptr; c->n_wide = 0;
     c->geom32 = c->geom64 = c->mat32 = c->mat64 = nullptr; c->slot_obj = nullptr; c->nodes = nullptr; c->fast_blob = nullptr; c->fast_words = 0;
     std::memset(c->scene_bytes, 0, sizeof(c->scene_bytes));
@@ -247,6 +252,15 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         r.obj = s->rect_object[j] | RECT_BIT;
         ax[K].push_back(r);
     }
+    // box room whose two walls per axis differ only in their plane coordinate: the lower wall goes first and the kernel tests
+    // only the wall a ray travels towards when its origin lies between the two (fast_axis_pair); IPT_NO_PAIR=1 for A/B runs
+    bool box_uniform = gen.empty() && s->n_spheres <= 4 && !std::getenv("IPT_NO_PAIR");
+    for (int k = 0; k < 3 && box_uniform; k++) {
+        if (ax[k].size() != 2) { box_uniform = false; break; }
+        if (ax[k][1].pk < ax[k][0].pk) std::swap(ax[k][0], ax[k][1]);
+        const AxRect &a = ax[k][0], &b = ax[k][1];
+        box_uniform = a.pk < b.pk && a.cI == b.cI && a.cJ == b.cJ && a.hI == b.hI && a.hJ == b.hJ;
+    }
     // the axis lists are padded to an even length with a record that can never be hit (their device loops step by 2)
     for (int k = 0; k < 3; k++)
         if (ax[k].size() & 1) ax[k].push_back(AxRect{3.0e38f, 0.f, 0.f, -1.f, -1.f, NO_OBJECT});
@@ -257,6 +271,7 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
     auto Ff = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     uint32_t* p = blob.data();
     p[0] = ns; p[1] = (uint32_t)ax[0].size(); p[2] = (uint32_t)ax[1].size(); p[3] = (uint32_t)ax[2].size(); p[4] = ng; p[5] = no;
+    p[6] = box_uniform ? 1u : 0u;
     p += 8;
     for (uint32_t i = 0; i < ns; i++)
         for (int k = 0; k < 4; k++) *p++ = i < ns_real ? F(s->sphere_cxyzr[4 * (size_t)i + k]) : F(k < 3 ? (double)NAN : 0.0);   // pad: NaN centre -> delta is NaN -> never a hit
@@ -336,7 +351,19 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     const size_t b_geom64 = (size_t)n * 16 * 8, b_geom32 = (size_t)n * 16 * 4, b_mat64 = (size_t)n * 8 * 8, b_mat32 = (size_t)n * 8 * 4;
     const size_t b_slot = slot_pad * 4, b_nodes = (size_t)s->n_bvh_nodes * 64;
     const size_t total = b_geom64 + b_geom32 + b_mat64 + b_mat32 + b_slot + b_nodes;
-    int rc = ensure_pinned(c, total);
+    // uniform grid of the caller (ipt_scene::grid_*), checked here: indices in range, cell starts ascending
+    const bool grid = bvh && s->grid_res[0] > 0 && !std::getenv("IPT_NO_GRID");
+    uint64_t grid_n_cells = 0;
+    if (grid) {
+        grid_n_cells = (uint64_t)s->grid_res[0] * s->grid_res[1] * s->grid_res[2];
+        const bool sane = s->grid_res[0] <= 1024 && s->grid_res[1] <= 1024 && s->grid_res[2] <= 1024 && s->grid_res[1] > 0 && s->grid_res[2] > 0 &&
+                          grid_n_cells <= (1ull << 26) && s->grid_cell_start && s->n_grid_big <= GRID_MAX_BIG && (s->n_grid_big == 0 || s->grid_big) &&
+                          (s->n_grid_refs == 0 || s->grid_refs) && s->grid_cell[0] > 0.f && s->grid_cell[1] > 0.f && s->grid_cell[2] > 0.f &&
+                          s->n_grid_refs < (1u << 31);
+        if (!sane) { set_err("ipt_ctx_set_scene: inconsistent grid"); return IPT_ERR_BAD_ARGUMENT; }
+    }
+    const size_t b_cells = grid ? (size_t)grid_n_cells * 8 : 0, b_refs = grid ? ((size_t)s->n_grid_refs + 4) * 4 : 0;
+    int rc = ensure_pinned(c, total + b_cells + b_refs);
     if (rc) return rc;
     char* pin = (char*)c->pinned;
     double* g64 = (double*)pin;
@@ -347,6 +374,25 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     float* nd = (float*)(pin + b_geom64 + b_geom32 + b_mat64 + b_mat32 + b_slot);
     std::memset(so + n, 0xFF, b_slot - (size_t)n * 4);
     std::atomic<const char*> bad{nullptr};              // first inconsistency a packing thread found
+    uint2* gcells = (uint2*)(pin + total);
+    uint32_t* grefs = (uint32_t*)(pin + total + b_cells);
+    if (grid) {
+        parallel_ranges((size_t)grid_n_cells, [&](size_t lo_, size_t hi_) {
+            for (size_t ci = lo_; ci < hi_; ci++) {
+                const uint32_t a = s->grid_cell_start[ci], z = s->grid_cell_start[ci + 1];
+                if (z < a || z > s->n_grid_refs) { bad = "ipt_ctx_set_scene: bad grid cell"; return; }
+                gcells[ci] = make_uint2(a, z - a);
+            }
+        });
+        parallel_ranges(s->n_grid_refs, [&](size_t lo_, size_t hi_) {
+            for (size_t r = lo_; r < hi_; r++) {
+                const uint32_t slot = s->grid_refs[r];
+                if (slot >= n) { bad = "ipt_ctx_set_scene: bad grid reference"; return; }
+                grefs[r] = slot_inv ? slot_inv[slot] : slot;
+            }
+        });
+        for (uint32_t b = 0; b < s->n_grid_big; b++) if (s->grid_big[b] >= n) bad = "ipt_ctx_set_scene: bad grid reference";
+    }
     parallel_ranges(n, [&](size_t lo_, size_t hi_) {
       for (size_t slot = lo_; slot < hi_; slot++) {
         uint32_t prim = bvh ? s->bvh_slot_prim[slot_perm ? slot_perm[slot] : slot] : (slot < ns ? (uint32_t)slot : (RECT_BIT | ((uint32_t)slot - ns)));
@@ -453,7 +499,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
           }
         });
     }
-    const size_t want[7] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode)};
+    const size_t want[8] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode), b_cells + b_refs};
     if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom32) {
         free_scene(c);
         CK(cudaMalloc(&c->geom32, b_geom32));
@@ -463,6 +509,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
         if (!bs.empty()) CK(cudaMalloc(&c->bslot, bs.size() * 4));
         if (!wt.nodes.empty()) CK(cudaMalloc(&c->wide, wt.nodes.size() * sizeof(WideNode)));
+        if (grid) { CK(cudaMalloc(&c->grid_cells, b_cells)); CK(cudaMalloc(&c->grid_refs, b_refs)); }
         std::memcpy(c->scene_bytes, want, sizeof(want));
     }
     c->have_scene = false;
@@ -474,6 +521,20 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     if (!bs.empty()) CK(cudaMemcpyAsync(c->bslot, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, c->stream));
     if (!wt.nodes.empty()) CK(cudaMemcpyAsync(c->wide, wt.nodes.data(), wt.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
     c->n_wide = (uint32_t)wt.nodes.size(); c->wide_stack_need = wt.stack_need; c->wide_depth = wt.depth;
+    c->grid_hd = GridHeader{};
+    if (grid) {
+        CK(cudaMemcpyAsync(c->grid_cells, gcells, b_cells, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->grid_refs, grefs, b_refs, cudaMemcpyHostToDevice, c->stream));
+        GridHeader& g = c->grid_hd;
+        for (int k = 0; k < 3; k++) {
+            g.res[k] = s->grid_res[k]; g.lo[k] = s->grid_lo[k]; g.cs[k] = s->grid_cell[k]; g.inv_cs[k] = 1.f / s->grid_cell[k];
+            g.hi[k] = s->grid_lo[k] + s->grid_cell[k] * (float)s->grid_res[k];
+        }
+        g.n_big = s->n_grid_big;
+        for (uint32_t b = 0; b < s->n_grid_big; b++) g.big[b] = slot_inv ? slot_inv[s->grid_big[b]] : s->grid_big[b];
+        if (std::getenv("IPT_VERBOSE"))
+            std::fprintf(stderr, "[ipt] grid %u x %u x %u, %u references, %u big primitives: %.1f MB\n", g.res[0], g.res[1], g.res[2], s->n_grid_refs, g.n_big, (b_cells + b_refs) / 1e6);
+    }
     if (std::getenv("IPT_VERBOSE") && bvh)
         std::fprintf(stderr, "[ipt] 8-wide tree: %zu nodes (%.2f children per node), depth %u, stack need <= %u, from %u 2-wide nodes\n", wt.nodes.size(),
                      wt.nodes.empty() ? 0.0 : wt.sum_children / wt.nodes.size(), wt.depth, wt.stack_need, s->n_bvh_nodes);
@@ -482,13 +543,14 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->fast_words = (uint32_t)(blob.size() / 4);
         c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
+        c->fast_hd.box_uniform = blob[6];
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total - b_geom64 - b_mat64 + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode);
+    c->last.h2d_bytes = total - b_geom64 - b_mat64 + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode) + b_cells + b_refs;
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -596,6 +658,12 @@ static int prepare_extend(ipt_ctx* c, KParams<float>& kp, size_t smem_top, int* 
         }
         kp.wide_spill = c->wide_spill;
     }
+    if (kp.grid_cells && grids[3] == 0) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_grid, BLOCK_THREADS, 0));
+        if (per_sm < 1) { set_err("k_extend_grid does not fit on an SM"); return IPT_ERR_BAD_ARGUMENT; }
+        grids[3] = per_sm * c->sm_count;
+    }
     if (grids[0] == 0) {
         CK(cudaFuncSetAttribute(k_extend_bvh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_top));
         int per_sm = 0;
@@ -621,7 +689,8 @@ static int launch_split_batch(ipt_ctx* c, KParams<float>& kp, uint32_t max_depth
         kp.depth = d;
         kp.qin = Queue{c->q[d & 1], cap};
         kp.qout = Queue{c->q[(d + 1) & 1], cap};
-        if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
+        if (kp.grid_cells) k_extend_grid<<<grids[3], BLOCK_THREADS, 0, c->stream>>>(kp);
+        else if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
         else k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
         shade<<<grids[1], BLOCK_THREADS, 0, c->stream>>>(kp);
         *launches += 2;
@@ -804,6 +873,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         const size_t avail = free_b / 2 + 2 * c->q_bytes;
         while (!prm.batch_samples && B > (1u << 20) && 2 * (size_t)cap_of(B) * ray_bytes > avail) B = B / 2 / 32 * 32;
     }
+    // equal batches: 3 full ones and a remainder leave the last launches of a render half empty (at 8 GPUs a rank of the 4K
+    // bench has ~3.6 default batches), so the default size is spread evenly over the number of batches it implies
+    if (!prm.batch_samples && total_samples > B) {
+        const uint64_t nb = (total_samples + B - 1) / B;
+        B = std::max<uint64_t>(32, ((total_samples + nb - 1) / nb + 31) / 32 * 32);
+    }
     const uint32_t cap = cap_of(B);
     const size_t q_bytes = (size_t)cap * ray_bytes;
     if (q_bytes > c->q_bytes) {
@@ -825,9 +900,14 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.hits = c->hits;
     // 8-wide traversal: only with IPT_BVH8=1 at ipt_ctx_set_scene time (and leaves of at most 4 primitives)
     kp.wide = use_split ? c->wide : nullptr;
+    // uniform grid: when the host layer built one for the scene (host/grid.cpp) it replaces the tree in the fp32 pipeline
+    kp.grid_cells = use_split ? c->grid_cells : nullptr; kp.grid_refs = c->grid_refs; kp.grid = c->grid_hd;
     kp.descend_min = std::getenv("IPT_DESCEND_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_DESCEND_MIN")) : 12u;
-    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : 8u;
-    kp.leaf_min = std::getenv("IPT_LEAF_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_LEAF_MIN")) : 8u;
+    // (measured on the 1M-primitive scene, profiles/README.md round 2: the grid walk likes 12 / 16, the tree walks 8 / 8)
+    const bool grid_walk = use_split && c->grid_cells != nullptr;
+    kp.refill_min = std::getenv("IPT_REFILL_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_REFILL_MIN")) : (grid_walk ? 12u : 8u);
+    kp.leaf_min = std::getenv("IPT_LEAF_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_LEAF_MIN")) : (grid_walk ? 16u : 8u);
+    kp.static_slices = std::getenv("IPT_STATIC_SLICES") ? 1u : 0u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
     const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
@@ -847,7 +927,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 64, c->stream));   // [0] casts, [1] queue records moved, [2..6] traversal work (add_work)
     CK(cudaEventRecord(c->ev0, c->stream));
-    int grid_first = 0, grid_next = 0, split_grids[3] = {0, 0, 0};
+    int grid_first = 0, grid_next = 0, split_grids[4] = {0, 0, 0, 0};
     // IPT_PASS_TIMES=1 (diagnostic): an event before every pass of the fused pipelines, per-depth sums on stderr
     const bool pass_times = std::getenv("IPT_PASS_TIMES") != nullptr && !use_split;
     struct PassDiag {                 // released on every return path
@@ -958,6 +1038,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         cudaGetLastError();
     }
     CK(cudaStreamSynchronize(c->stream));
+    if (progress) report();
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     if (pass_times && pass_events.size() > 1) {
@@ -1282,12 +1363,14 @@ extern "C" int ipt_ctx_trace(ipt_ctx* c, const double* rays, uint32_t n, uint32_
         kp.counters = c->counters; kp.traced = c->traced; kp.hits = q.hits; kp.depth = 0;
         kp.qin = Queue{q.rays, n};
         kp.wide = c->wide;
-        kp.descend_min = 12; kp.refill_min = 8; kp.leaf_min = 8;
+        kp.grid_cells = c->grid_cells; kp.grid_refs = c->grid_refs; kp.grid = c->grid_hd;
+        kp.descend_min = 12; kp.refill_min = kp.grid_cells ? 12 : 8; kp.leaf_min = kp.grid_cells ? 16 : 8;
         const size_t smem_top = (size_t)std::min<uint32_t>(c->n_nodes, BVH_TOP_NODES) * 64;
-        int grids[3] = {0, 0, 0};
+        int grids[4] = {0, 0, 0, 0};
         int rc = prepare_extend(c, kp, smem_top, grids);
         if (rc) return rc;
-        if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
+        if (kp.grid_cells) k_extend_grid<<<grids[3], BLOCK_THREADS, 0, c->stream>>>(kp);
+        else if (kp.wide) k_extend_cw<<<grids[2], BLOCK_THREADS, CW_SMEM, c->stream>>>(kp);
         else k_extend_bvh<<<grids[0], BLOCK_THREADS, smem_top, c->stream>>>(kp);
         CK(cudaGetLastError());
         std::vector<uint2> hits(n);

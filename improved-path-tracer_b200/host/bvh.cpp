@@ -59,11 +59,16 @@ struct Builder {
     int par_depth = 0;   // levels below this node that may still fork a thread
 
     // Splits [first, first+count) in place; returns the split position, or first when the range becomes a leaf.
-    uint32_t split(uint32_t first, uint32_t count, Box& box)
+    // `level`: depth of the node being split (root = 1).  The traversal stacks hold 64 entries and ipt_ctx_set_scene refuses
+    // trees deeper than 60 levels; SAH on a skewed distribution (a geometric progression of sizes) can peel one primitive
+    // per level, so from level 40 on a range is halved by index (every level halves the count: at most 32 more levels).
+    static constexpr int SAH_MAX_LEVEL = 40;
+    uint32_t split(uint32_t first, uint32_t count, Box& box, int level)
     {
         Box cb;
         for (uint32_t i = first; i < first + count; i++) { box.grow(prims[i].box); cb.grow(prims[i].c); }
         if (count <= leaf_size) return first;
+        if (level >= SAH_MAX_LEVEL) return first + count / 2;
         // binned SAH over the centroid bounds, 16 bins per axis
         constexpr int NB = 16;
         constexpr uint32_t SMALL = 16;
@@ -154,20 +159,20 @@ struct Builder {
         return mid;
     }
 
-    int build(uint32_t first, uint32_t count)
+    int build(uint32_t first, uint32_t count, int level = 1)
     {
         const int id = (int)nodes.size();
         nodes.emplace_back();
         Box box;
-        const uint32_t mid = split(first, count, box);
+        const uint32_t mid = split(first, count, box, level);
         nodes[id].box = box;
         if (mid == first) { nodes[id].first = first; nodes[id].count = count; return id; }
         if (par_depth > 0 && count > 65536) {
             // large subtree: the two halves are independent (disjoint primitive ranges) -> build them on two threads
             // into private node arrays, then splice them in with an index offset
             Builder lb{prims, {}, leaf_size, par_depth - 1}, rb{prims, {}, leaf_size, par_depth - 1};
-            std::thread t([&] { lb.build(first, mid - first); });
-            rb.build(mid, first + count - mid);
+            std::thread t([&] { lb.build(first, mid - first, level + 1); });
+            rb.build(mid, first + count - mid, level + 1);
             t.join();
             auto splice = [&](const std::vector<BNode>& sub) {
                 const int off = (int)nodes.size();
@@ -178,8 +183,8 @@ struct Builder {
             nodes[id].left = l; nodes[id].right = r;
             return id;
         }
-        const int l = build(first, mid - first);
-        const int r = build(mid, first + count - mid);
+        const int l = build(first, mid - first, level + 1);
+        const int r = build(mid, first + count - mid, level + 1);
         nodes[id].left = l; nodes[id].right = r;
         return id;
     }
@@ -203,6 +208,7 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
 {
     if (!s) return -1;
     s->bvh_nodes.clear(); s->bvh_slot_prim.clear();
+    s->grid_cell_start.clear(); s->grid_refs.clear(); s->grid_big.clear();
     const uint32_t ns = (uint32_t)s->sphere_object.size(), nr = (uint32_t)s->rect_object.size(), n = ns + nr;
     if (n <= brute_max) { s->refresh_view(); return 0; }
     const auto T0 = std::chrono::steady_clock::now();
@@ -278,7 +284,9 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         if (l.left >= 0) o.child[0] = index[nd.left]; else { o.child[0] = leaf_code(l); o.count[0] = l.count; }
         if (r.left >= 0) o.child[1] = index[nd.right]; else { o.child[1] = leaf_code(r); o.count[1] = r.count; }
     }
-    s->refresh_view();
     lap("emit");
+    s->build_grid();
+    lap("grid");
+    s->refresh_view();
     return (int)s->bvh_nodes.size();
 }

@@ -14,6 +14,11 @@ struct ipt_host_scene {
     std::vector<double> rect_center, rect_north, rect_east;
     std::vector<ipt_bvh_node> bvh_nodes;
     std::vector<uint32_t> bvh_slot_prim;
+    // uniform grid over the BVH's slots (host/grid.cpp), empty when the scene does not qualify
+    std::vector<uint32_t> grid_cell_start, grid_refs, grid_big;
+    uint32_t grid_res[3] = {0, 0, 0};
+    float grid_lo[3] = {0, 0, 0}, grid_cell[3] = {0, 0, 0};
+    void build_grid();   // host/grid.cpp; called by ipt_host_build_bvh
 
     void add(int type, double radius, const double* north, const double* east, const double* position,
              const double* emission, const double* color, int reflection);

@@ -205,6 +205,12 @@ void ipt_host_scene::refresh_view()
     view.n_bvh_nodes = (uint32_t)bvh_nodes.size(); view.n_bvh_slots = (uint32_t)bvh_slot_prim.size();
     view.bvh_nodes = bvh_nodes.empty() ? nullptr : bvh_nodes.data();
     view.bvh_slot_prim = bvh_slot_prim.empty() ? nullptr : bvh_slot_prim.data();
+    const bool grid = !grid_cell_start.empty() && !bvh_nodes.empty();
+    for (int k = 0; k < 3; k++) { view.grid_res[k] = grid ? grid_res[k] : 0; view.grid_lo[k] = grid_lo[k]; view.grid_cell[k] = grid_cell[k]; }
+    view.n_grid_big = grid ? (uint32_t)grid_big.size() : 0; view.n_grid_refs = grid ? (uint32_t)grid_refs.size() : 0; view.reserved1 = 0;
+    view.grid_cell_start = grid ? grid_cell_start.data() : nullptr;
+    view.grid_refs = grid && !grid_refs.empty() ? grid_refs.data() : nullptr;
+    view.grid_big = grid && !grid_big.empty() ? grid_big.data() : nullptr;
 }
 
 extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, size_t message_len)

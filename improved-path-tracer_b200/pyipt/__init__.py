@@ -49,7 +49,11 @@ class Scene(ctypes.Structure):
                 ("mat_color", ctypes.POINTER(ctypes.c_double)), ("mat_emission", ctypes.POINTER(ctypes.c_double)),
                 ("mat_reflection", ctypes.POINTER(ctypes.c_int32)),
                 ("n_bvh_nodes", ctypes.c_uint32), ("n_bvh_slots", ctypes.c_uint32),
-                ("bvh_nodes", ctypes.POINTER(BvhNode)), ("bvh_slot_prim", ctypes.POINTER(ctypes.c_uint32))]
+                ("bvh_nodes", ctypes.POINTER(BvhNode)), ("bvh_slot_prim", ctypes.POINTER(ctypes.c_uint32)),
+                ("grid_res", ctypes.c_uint32 * 3), ("n_grid_big", ctypes.c_uint32), ("grid_lo", ctypes.c_float * 3),
+                ("grid_cell", ctypes.c_float * 3), ("n_grid_refs", ctypes.c_uint32), ("reserved1", ctypes.c_uint32),
+                ("grid_cell_start", ctypes.POINTER(ctypes.c_uint32)), ("grid_refs", ctypes.POINTER(ctypes.c_uint32)),
+                ("grid_big", ctypes.POINTER(ctypes.c_uint32))]
 
 
 class Params(ctypes.Structure):

@@ -118,7 +118,7 @@ def lib():
         L.or_plane_intersect.restype = ctypes.c_double
         L.or_scatter.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_ulonglong, dp]
         L.or_scatter.restype = None
-        L.or_philox4x32_10.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.or_philox4x32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         for f in (L.or_sym24, L.or_uniform23):
             f.argtypes = [ctypes.c_uint32]
             f.restype = ctypes.c_double
@@ -224,9 +224,10 @@ def ref_time_cells(path, samples, depth, width, height, cells, nthreads=None):
     return time.perf_counter() - t0
 
 
-def philox(counter, key):
+def philox(counter, key, rounds=0):
+    """Philox4x32 with `rounds` rounds (0: the 7 rounds of the counter stream)."""
     c = (ctypes.c_uint32 * 4)(*counter)
     k = (ctypes.c_uint32 * 2)(*key)
     o = (ctypes.c_uint32 * 4)()
-    lib().or_philox4x32_10(c, k, o)
+    lib().or_philox4x32(c, k, rounds, o)
     return tuple(o)

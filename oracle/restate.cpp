@@ -61,11 +61,13 @@ const double VIEWPORT_DISTANCE = 140; // Renderer.cu:28
 const uint32_t BLOCK = 22;            // renderer/Constants.hpp:11
 
 // ------------------------------------------------------------------------------------------------ RNG
-// Philox4x32-10 (Salmon et al., SC'11) — the counter-based generator of the B200 path.
-inline void philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4])
+// Philox4x32-R (Salmon et al., SC'11) — the counter-based generator of the B200 path, which uses R = 7 rounds
+// (OR_PHILOX_ROUNDS; Random123's known answers for R = 7 and R = 10 pin this function, tests/test_oracle_pin.py).
+const int OR_PHILOX_ROUNDS = 7;
+inline void philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4], int rounds = OR_PHILOX_ROUNDS)
 {
     uint32_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], k0 = k[0], k1 = k[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -524,7 +526,7 @@ void or_scatter(int kind, const double* geom, int reflection, const double* P, c
     out[15] = draws;
 }
 
-void or_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out) { philox(counter, key, out); }
+void or_philox4x32(const uint32_t* counter, const uint32_t* key, int rounds, uint32_t* out) { philox(counter, key, out, rounds > 0 ? rounds : OR_PHILOX_ROUNDS); }
 double or_sym24(uint32_t x) { return s24(x); }
 double or_uniform23(uint32_t x) { return u23(x); }
 

@@ -40,7 +40,7 @@ typedef struct or_scene {
 enum {
     OR_RNG_REFERENCE = 0,  /* curand XORWOW, seed 123456, one stream per reference "CUDA thread" (22x22 cells),
                               draws in the reference's order: reproduces oracle/_ref bit for bit            */
-    OR_RNG_COUNTER = 1     /* Philox4x32-10 keyed by (seed), counter = (pixel, sample, lane<<8|depth, tag):
+    OR_RNG_COUNTER = 1     /* Philox4x32-7 keyed by (seed), counter = (pixel, sample, lane<<8|depth, tag):
                               the stream the B200 kernels use, so images can be compared pixel by pixel     */
 };
 
@@ -65,8 +65,9 @@ double or_plane_intersect(const double* north, const double* east, const double*
 void or_scatter(int kind, const double* geom, int reflection, const double* P, const double* incoming, int depth,
                 unsigned long long subsequence, double* out16);
 
-/* Philox4x32-10 block function (counter[4], key[2]) -> out[4]; and the two 32-bit -> real maps of the counter stream. */
-void or_philox4x32_10(const uint32_t* counter, const uint32_t* key, uint32_t* out);
+/* Philox4x32-R block function (counter[4], key[2]) -> out[4], rounds = 0: the 7 rounds the counter stream uses; and the two
+ * 32-bit -> real maps of the counter stream. */
+void or_philox4x32(const uint32_t* counter, const uint32_t* key, int rounds, uint32_t* out);
 double or_sym24(uint32_t x);     /* (-1,1): odd multiple of 2^-24 */
 double or_uniform23(uint32_t x); /* (0,1)  : odd multiple of 2^-24 */
 

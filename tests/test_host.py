@@ -361,3 +361,30 @@ def test_wide_tree_equals_linear_scan_on_cpu(tmp_path):
         assert r.returncode == 0 and "check: 0 of 3000" in r.stdout and " 0 link mismatches" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([exe, path, "8", "4", "10"], capture_output=True, text=True)
     assert r.returncode == 1 and "unsupported" in r.stderr
+
+
+def test_bvh_depth_is_bounded_on_a_skewed_scene(pyipt, tmp_path):
+    """A geometric progression of sizes and positions makes SAH peel one primitive per level; the builder halves ranges by
+    index from level 40 on, so the tree stays below the 60 levels ipt_ctx_set_scene accepts (traversal stacks: 64 entries)."""
+    import json, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scene_util import vec
+    objs = []
+    for i in range(200):
+        x = 1.5 ** i
+        objs.append({"type": "sphere", "radius": 0.01 * x, "position": vec((x, 0.0, 0.0)), "color": vec((.5, .5, .5)), "emission": vec((0, 0, 0)), "reflection": 0})
+    scene = {"width": 64, "height": 36, "camera": {"position": vec((0, -10, 0)), "direction": vec((0, 1, 0)), "orientation": vec((-1, 0, 0))}, "objects": objs}
+    path = tmp_path / "skew.json"
+    path.write_text(json.dumps(scene))
+    hs = pyipt.HostScene.load(str(path), leaf_size=1)
+    a = hs.arrays()
+    nodes = a["bvh_nodes"]
+    assert len(nodes) > 100
+    depth = [0] * len(nodes)
+    depth[0] = 1
+    for i, nd in enumerate(nodes):
+        for k in range(2):
+            if nd.child[k] >= 0:
+                assert nd.child[k] > i                       # parents first: what ipt_ctx_set_scene requires
+                depth[nd.child[k]] = depth[i] + 1
+    assert 40 <= max(depth) <= 60, max(depth)
