@@ -537,7 +537,7 @@ struct FastScene {
     uint32_t ax0_x, ax0_y, ax0_z, n_x, n_y, n_z;
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
-    bool box_uniform;                        // see fast_axis_pair
+    bool box_pairs;                          // see fast_axis_pair
 };
 __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
@@ -546,13 +546,13 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 // The list sizes come in as kernel parameters (uniform registers / constant bank), not from the blob in shared memory.
 struct FastHeader {
     uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
-    uint32_t box_uniform;   // box room whose two rectangles per axis differ only in their plane coordinate, lower one first
+    uint32_t box_pairs;     // box room whose two rectangles per axis are stored lower plane first (fast_axis_pair)
     uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
 };
 __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
     FastHeader h;
-    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_uniform = 0;
+    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_pairs = 0;
     h.off_sphobj = 2 + n_sph;
     h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
     h.off_gen = h.off_axs + 2 * (nx + ny + nz);
@@ -563,7 +563,7 @@ __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, u
 __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_uniform = hd.box_uniform != 0;
+    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0;
     f.sph = reinterpret_cast<const float4*>(blob + 2);
     f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
     f.axs = reinterpret_cast<const float4*>(blob + hd.off_axs);
@@ -623,23 +623,24 @@ __device__ __forceinline__ void fast_axis_fixed(const float4* __restrict__ axs, 
     }
 }
 
-// The two parallel walls of a box room along axis K, for a ray whose origin lies between them (FastHeader::box_uniform: the
-// host has checked that the two records differ only in the plane coordinate and stored the lower wall first).  The wall
-// the ray travels away from has t = (p - o_K) / d_K <= 0 (or -inf / NaN for d_K = 0) and fails `t > 1e-4` in the scan of
-// both, so testing only the wall ahead gives the bit-identical result with half the tests.
+// The two parallel walls of a box room along axis K, for a ray whose origin lies between them (FastHeader::box_pairs: the
+// host has stored the lower wall of every pair first).  The wall the ray travels away from has t = (p - o_K) / d_K <= 0
+// (or -inf / NaN for d_K = 0) and fails `t > 1e-4` in the scan of both, so testing only the wall ahead - its record picked
+// by the sign of d_K - gives the bit-identical result with half the tests.
 template <int K, int FIRST_REC>
 __device__ __forceinline__ void fast_axis_pair(const float4* __restrict__ axs, const V3<float>& o, const V3<float>& d, float inv_dk, FastHit& best)
 {
     constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
     const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
-    const float4 a = axs[2 * FIRST_REC];
-    const float hj = axs[2 * FIRST_REC + 1].x, p_up = axs[2 * (FIRST_REC + 1)].x;
-    const bool up = comp<K>(d) > 0.f;
-    const float t = ((up ? p_up : a.x) - ok) * inv_dk;
+    const uint32_t up = comp<K>(d) > 0.f ? 1u : 0u;
+    const float4* rec = axs + 2 * FIRST_REC + 2 * up;
+    const float4 a = rec[0];
+    const float hj = rec[1].x;
+    const float t = (a.x - ok) * inv_dk;
     const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
     const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
     best.t = hit ? t : best.t;
-    best.code = hit ? ((((uint32_t)(K + 1) << 28) | (uint32_t)FIRST_REC) + (up ? 1u : 0u)) : best.code;
+    best.code = hit ? ((((uint32_t)(K + 1) << 28) | (uint32_t)FIRST_REC) + up) : best.code;
 }
 
 // Renderer.cu:227-243 for the fp32 brute-force layout; self-hit rule as in SelfRule<float>.  `self` is the hit CODE of
@@ -677,7 +678,7 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
 #pragma unroll
         for (int s = 0; s < SHAPE - 1; s++) fast_sphere(f.sph[s], (uint32_t)s, self_sphere, o, d, best);
         // origin between the walls of every pair (on a wall counts): only the wall ahead can be hit (fast_axis_pair)
-        const bool between = f.box_uniform && o.x >= f.axs[0].x && o.x <= f.axs[2].x && o.y >= f.axs[4].x && o.y <= f.axs[6].x &&
+        const bool between = f.box_pairs && o.x >= f.axs[0].x && o.x <= f.axs[2].x && o.y >= f.axs[4].x && o.y <= f.axs[6].x &&
                              o.z >= f.axs[8].x && o.z <= f.axs[10].x;
         if (between) {
             fast_axis_pair<0, 0>(f.axs, o, d, rcp_fast(d.x), best);

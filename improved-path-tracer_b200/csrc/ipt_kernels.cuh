@@ -65,7 +65,8 @@ template <typename R> struct KParams {
     const uint32_t* mt_list;
     uint32_t n_mt;
     // batch
-    uint32_t base_mt, base_sample, n_first;   // pass 0: first micro-tile, first sample, number of sample ids in the batch
+    uint32_t base_mt, mt_count, base_sample, n_first;   // pass 0: the batch = micro-tiles [base_mt, base_mt + mt_count) x samples
+                                                         // from base_sample on; n_first sample ids (32 per micro-tile and sample)
     Queue qin, qout;
     uint32_t* counters;
     unsigned long long* traced; // total nearest-hit queries (stats)
@@ -108,16 +109,19 @@ __device__ __forceinline__ void accumulate(const KParams<R>& p, uint32_t pixel, 
     }
 }
 
-// Sample id -> (pixel, sample).  Ids are ordered micro-tile major: 32 consecutive ids are one 8x4 pixel block at
-// one sample index (a warp's camera rays are neighbours), consecutive groups walk the samples of that block.
+// Sample id -> (pixel, sample).  32 consecutive ids are one 8x4 pixel block at one sample index (a warp's camera rays are
+// neighbours); consecutive groups walk the MICRO-TILES of the batch, then the samples.  (Round 1 walked the samples of a
+// block first: the ~3500 warps in flight then worked on 3-4 blocks, and the emission they found - three 64-bit atomics per
+// hit - went to ~330 addresses; pass 0 of the batches that only see the light ran at 19 % issue utilisation,
+// profiles/r02_ncu_pass0_v2.txt.)
 template <typename R>
 __device__ __forceinline__ bool decode_sample(const KParams<R>& p, uint32_t sid, uint32_t& px, uint32_t& pz, uint32_t& sample)
 {
     const uint32_t g = sid >> 5, l = sid & 31u;
-    const uint32_t s = p.base_sample + g;
-    sample = s % p.spp;
-    const uint32_t mt = p.base_mt + s / p.spp;
-    if (mt >= p.n_mt) return false;
+    const uint32_t q = g / p.mt_count;
+    sample = p.base_sample + q;
+    const uint32_t mt = p.base_mt + (g - q * p.mt_count);
+    if (mt >= p.n_mt || sample >= p.spp) return false;
     const uint32_t xy = p.mt_list[mt];
     px = (xy & 0xFFFFu) * 8u + (l & 7u);
     pz = (xy >> 16) * 4u + (l >> 3);
@@ -1035,18 +1039,21 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
         else blk_used += tot;
     };
 
-    // Slices of 32 rays are claimed from a per-pass counter, two ahead: the slice being computed, the next one (its records
-    // already on their way into shared memory) and the claim for the one after (issued, not yet read).  Static assignment
-    // (slice = warp + k * warps) left the SMs idle at the end of a pass: warps on SMs with slower memory finish late, and
-    // ncu showed 30.5 % achieved against 37.5 % theoretical occupancy (profiles/r01_ncu_spheres4k_final_deep_pass.txt).
+    // Work is claimed from a per-pass counter in chunks of CHUNK slices of 32 rays, one chunk ahead: the chunk being computed,
+    // the next one (claimed, its first records already on their way into shared memory when the current one ends) and the
+    // claim after that (issued, not yet read).  Static assignment (slice = warp + k * warps) left the SMs idle at the end of a
+    // pass - warps on SMs with slower memory finish late; ncu showed 30.5 % achieved against 37.5 % theoretical occupancy
+    // (profiles/r01_ncu_spheres4k_final_deep_pass.txt) - and one claim per slice ran into the ~0.5 G/s a single address takes
+    // in pass 0, whose slices are short (profiles/r02_ncu_pass0_v2.txt: 28 % of the stall samples on the claim).
+    constexpr uint32_t CHUNK = FIRST ? 8u : 2u, CHUNK_RAYS = CHUNK * 32u;
     uint32_t* claim_ctr = p.counters + CLAIM + p.pass;
-    // (p.static_slices, IPT_STATIC_SLICES=1: the static assignment, for A/B runs - no atomics, slice = warp + k * warps)
-    const uint32_t stride = gridDim.x * BLOCK_THREADS;
-    uint32_t static_next = (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) * 32u;
+    // (p.static_slices, IPT_STATIC_SLICES=1: the static assignment, for A/B runs - no atomics)
+    const uint32_t stride = gridDim.x * (BLOCK_THREADS / 32) * CHUNK_RAYS;
+    uint32_t static_next = (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) * CHUNK_RAYS;
     auto claim_issue = [&]() {
         uint32_t v = 0;
-        if (p.static_slices) { v = static_next; static_next = static_next + stride < static_next ? 0xFFFFFFE0u : static_next + stride; }
-        else if (lane == 0) v = atomicAdd(claim_ctr, 32u);
+        if (p.static_slices) { v = static_next; static_next = static_next + stride < static_next ? 0xFFFFFF00u : static_next + stride; }
+        else if (lane == 0) v = atomicAdd(claim_ctr, CHUNK_RAYS);
         return v;
     };
     auto prefetch = [&](uint32_t base, int b) {
@@ -1055,13 +1062,18 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
             for (int pl = 0; pl < 3; pl++) cp_async16(stagebuf + (b * 3 + pl) * BLOCK_THREADS + threadIdx.x, p.qin.base + (size_t)pl * p.qin.capacity + j);
         cp_async_commit();
     };
-    uint32_t cur = __shfl_sync(0xffffffffu, claim_issue(), 0);
-    uint32_t nxt = __shfl_sync(0xffffffffu, claim_issue(), 0);
+    uint32_t chunk = __shfl_sync(0xffffffffu, claim_issue(), 0);
+    uint32_t chunk_next = __shfl_sync(0xffffffffu, claim_issue(), 0);
     uint32_t pending = claim_issue();
+    uint32_t off = 0;
     int buf = 0;
-    prefetch(cur, buf);
+    prefetch(chunk, buf);
 
-    for (; cur < n_in; cur = nxt, nxt = __shfl_sync(0xffffffffu, pending, 0), pending = claim_issue()) {
+    for (;;) {
+        const uint32_t cur = chunk + off;
+        if (cur >= n_in) break;                              // claims only grow: nothing is left for this warp
+        const uint32_t noff = off + 32u;
+        const uint32_t nxt = noff < CHUNK_RAYS ? chunk + noff : chunk_next;
         const uint32_t i = cur + lane;
         bool live = i < n_in;
         Ray<float> r;
@@ -1083,6 +1095,8 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
             }
             buf ^= 1;
         }
+        off = noff;
+        if (off == CHUNK_RAYS) { chunk = chunk_next; chunk_next = __shfl_sync(0xffffffffu, pending, 0); pending = claim_issue(); off = 0; }
         bool has0 = live;
         for (uint32_t k = 0; k < nk; k++) {
             const bool in = has0;

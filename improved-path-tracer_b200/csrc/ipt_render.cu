@@ -214,7 +214,7 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     free_scene(c);
     cudaFree(c->wide_spill);
     cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->hits); cudaFree(c->counters); cudaFree(c->traced); cudaFree(c->fast_hint); cudaFree(c->lights); cudaFree(c->frame);
-    cudaFree(c->out32); cudaFree(c->out64); cudaFree(c->out8); cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
+    cudaFree(c->out32); cudaFree(c->out8);   // out64 lives in out32's allocation cudaFree(c->tile_ids); cudaFree(c->mt_list); cudaFree(c->mt_packed); cudaFree(c->mt_flags);
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -222,6 +222,9 @@ extern "C" void ipt_ctx_destroy(ipt_ctx* c)
     cudaGetLastError();
     delete c;
 }
+
+// the resolved fp64 frame follows the fp32 one in the same allocation, at this offset
+static size_t frame64_offset(size_t px) { return (px * 12 + 255) & ~(size_t)255; }
 
 // fp32 brute-force layout (see FastScene in ipt_device.cuh): spheres, axis-aligned rectangles per normal axis,
 // general rectangles, materials.  Built in fp64 from the flattened scene, rounded once to fp32.
@@ -252,14 +255,13 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         r.obj = s->rect_object[j] | RECT_BIT;
         ax[K].push_back(r);
     }
-    // box room whose two walls per axis differ only in their plane coordinate: the lower wall goes first and the kernel tests
-    // only the wall a ray travels towards when its origin lies between the two (fast_axis_pair); IPT_NO_PAIR=1 for A/B runs
-    bool box_uniform = gen.empty() && s->n_spheres <= 4 && !std::getenv("IPT_NO_PAIR");
-    for (int k = 0; k < 3 && box_uniform; k++) {
-        if (ax[k].size() != 2) { box_uniform = false; break; }
+    // box room (two rectangles per axis, at different plane coordinates): the lower wall of a pair goes first and the kernel
+    // tests only the wall a ray travels towards when its origin lies between the two (fast_axis_pair); IPT_NO_PAIR=1: A/B runs
+    bool box_pairs = gen.empty() && s->n_spheres <= 4 && !std::getenv("IPT_NO_PAIR");
+    for (int k = 0; k < 3 && box_pairs; k++) {
+        if (ax[k].size() != 2) { box_pairs = false; break; }
         if (ax[k][1].pk < ax[k][0].pk) std::swap(ax[k][0], ax[k][1]);
-        const AxRect &a = ax[k][0], &b = ax[k][1];
-        box_uniform = a.pk < b.pk && a.cI == b.cI && a.cJ == b.cJ && a.hI == b.hI && a.hJ == b.hJ;
+        box_pairs = ax[k][0].pk < ax[k][1].pk;
     }
     // the axis lists are padded to an even length with a record that can never be hit (their device loops step by 2)
     for (int k = 0; k < 3; k++)
@@ -271,7 +273,7 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
     auto Ff = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     uint32_t* p = blob.data();
     p[0] = ns; p[1] = (uint32_t)ax[0].size(); p[2] = (uint32_t)ax[1].size(); p[3] = (uint32_t)ax[2].size(); p[4] = ng; p[5] = no;
-    p[6] = box_uniform ? 1u : 0u;
+    p[6] = box_pairs ? 1u : 0u;
     p += 8;
     for (uint32_t i = 0; i < ns; i++)
         for (int k = 0; k < 4; k++) *p++ = i < ns_real ? F(s->sphere_cxyzr[4 * (size_t)i + k]) : F(k < 3 ? (double)NAN : 0.0);   // pad: NaN centre -> delta is NaN -> never a hit
@@ -363,8 +365,17 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         if (!sane) { set_err("ipt_ctx_set_scene: inconsistent grid"); return IPT_ERR_BAD_ARGUMENT; }
     }
     const size_t b_cells = grid ? (size_t)grid_n_cells * 8 : 0, b_refs = grid ? ((size_t)s->n_grid_refs + 4) * 4 : 0;
-    int rc = ensure_pinned(c, total + b_cells + b_refs);
+    const size_t b_bs = bvh ? (size_t)n * 32 : 0;      // typed 32-byte records of the fp32 traversal kernels
+    int rc = ensure_pinned(c, total + b_cells + b_refs + b_bs);
     if (rc) return rc;
+    // IPT_VERBOSE: where the time of an upload goes (host side)
+    const bool verbose_up = std::getenv("IPT_VERBOSE") != nullptr;
+    auto T_up = std::chrono::steady_clock::now();
+    auto lap_up = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (verbose_up && n > 100000) std::fprintf(stderr, "[ipt] set_scene %-26s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - T_up).count());
+        T_up = now;
+    };
     char* pin = (char*)c->pinned;
     double* g64 = (double*)pin;
     float* g32 = (float*)(pin + b_geom64);
@@ -376,6 +387,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     std::atomic<const char*> bad{nullptr};              // first inconsistency a packing thread found
     uint2* gcells = (uint2*)(pin + total);
     uint32_t* grefs = (uint32_t*)(pin + total + b_cells);
+    float* bs = (float*)(pin + total + b_cells + b_refs);
     if (grid) {
         parallel_ranges((size_t)grid_n_cells, [&](size_t lo_, size_t hi_) {
             for (size_t ci = lo_; ci < hi_; ci++) {
@@ -463,9 +475,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     std::vector<uint32_t> blob;
     if (!bvh) { blob = build_fast_blob(s); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
     // fp32 BVH leaf records: typed 32-byte entries in leaf (slot) order
-    std::vector<float> bs;
+    lap_up("pack geometry + tree");
     if (bvh) {
-        bs.assign((size_t)n * 8, 0.f);
         auto axis_of = [](const double* v, int& k, double& sign) {
             k = -1;
             for (int i = 0; i < 3; i++) {
@@ -477,7 +488,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         parallel_ranges(n, [&](size_t lo_, size_t hi_) {
           for (size_t slot = lo_; slot < hi_; slot++) {
             const uint32_t prim = s->bvh_slot_prim[slot_perm ? slot_perm[slot] : slot], idx = prim & ~RECT_BIT;
-            float* o8 = &bs[slot * 8];
+            float* o8 = bs + slot * 8;
+            for (int k = 0; k < 8; k++) o8[k] = 0.f;
             uint32_t kind, obj;
             if (!(prim & RECT_BIT)) {
                 for (int k = 0; k < 4; k++) o8[k] = (float)s->sphere_cxyzr[4 * (size_t)idx + k];
@@ -499,7 +511,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
           }
         });
     }
-    const size_t want[8] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode), b_cells + b_refs};
+    lap_up("typed records");
+    const size_t want[8] = {b_geom64, b_geom32, b_mat64, b_mat32, b_slot, b_nodes, blob.size() * 4 + b_bs + wt.nodes.size() * sizeof(WideNode), b_cells + b_refs};
     if (std::memcmp(want, c->scene_bytes, sizeof(want)) != 0 || !c->geom32) {
         free_scene(c);
         CK(cudaMalloc(&c->geom32, b_geom32));
@@ -507,7 +520,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         CK(cudaMalloc(&c->slot_obj, b_slot));
         if (b_nodes) CK(cudaMalloc(&c->nodes, b_nodes));
         if (!blob.empty()) CK(cudaMalloc(&c->fast_blob, blob.size() * 4));
-        if (!bs.empty()) CK(cudaMalloc(&c->bslot, bs.size() * 4));
+        if (b_bs) CK(cudaMalloc(&c->bslot, b_bs));
         if (!wt.nodes.empty()) CK(cudaMalloc(&c->wide, wt.nodes.size() * sizeof(WideNode)));
         if (grid) { CK(cudaMalloc(&c->grid_cells, b_cells)); CK(cudaMalloc(&c->grid_refs, b_refs)); }
         std::memcpy(c->scene_bytes, want, sizeof(want));
@@ -518,7 +531,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     CK(cudaMemcpyAsync(c->mat32, m32, b_mat32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->slot_obj, so, b_slot, cudaMemcpyHostToDevice, c->stream));
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
-    if (!bs.empty()) CK(cudaMemcpyAsync(c->bslot, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (b_bs) CK(cudaMemcpyAsync(c->bslot, bs, b_bs, cudaMemcpyHostToDevice, c->stream));
     if (!wt.nodes.empty()) CK(cudaMemcpyAsync(c->wide, wt.nodes.data(), wt.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
     c->n_wide = (uint32_t)wt.nodes.size(); c->wide_stack_need = wt.stack_need; c->wide_depth = wt.depth;
     c->grid_hd = GridHeader{};
@@ -543,14 +556,19 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->fast_words = (uint32_t)(blob.size() / 4);
         c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
-        c->fast_hd.box_uniform = blob[6];
+        c->fast_hd.box_pairs = blob[6];
+        if (std::getenv("IPT_VERBOSE"))
+            std::fprintf(stderr, "[ipt] typed lists: %u spheres, %u + %u + %u axis-aligned rectangles, %u general; box-room instantiation %d, wall pairs %s\n", blob[0], blob[1],
+                         blob[2], blob[3], blob[4], fast_shape(blob[0], blob[1], blob[2], blob[3], blob[4]), blob[6] ? "yes" : "no");
     }
     CK(cudaEventRecord(e1, c->stream));
+    lap_up("enqueue copies");
     CK(cudaStreamSynchronize(c->stream));
+    lap_up("wait for copies");
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
-    c->last.h2d_bytes = total - b_geom64 - b_mat64 + blob.size() * 4 + bs.size() * 4 + wt.nodes.size() * sizeof(WideNode) + b_cells + b_refs;
+    c->last.h2d_bytes = total - b_geom64 - b_mat64 + blob.size() * 4 + b_bs + wt.nodes.size() * sizeof(WideNode) + b_cells + b_refs;
     c->W = s->width; c->H = s->height; c->n_slots = n; c->n_spheres = bvh ? 0 : ns; c->n_objects = n; c->n_nodes = s->n_bvh_nodes;
     std::memcpy(c->cam, s->cam_origin, 24); std::memcpy(c->cam + 3, s->cam_dir, 24); std::memcpy(c->cam + 6, s->cam_orient, 24);
     c->max_emission = maxE; c->max_color = maxC;
@@ -609,10 +627,13 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     const size_t px = (size_t)c->W * c->H;
     if (px != c->frame_pixels) {
         if (c->gather32 == c->out32) { c->gather32 = nullptr; c->gather64 = nullptr; }
-        cudaFree(c->frame); cudaFree(c->out32); cudaFree(c->out64);
+        cudaFree(c->frame); cudaFree(c->out32);
         c->frame = nullptr; c->out32 = nullptr; c->out64 = nullptr; c->frame_pixels = 0;
-        CK(cudaMalloc(&c->frame, px * 24)); CK(cudaMalloc(&c->out32, px * 12)); CK(cudaMalloc(&c->out64, px * 24));
-        CK(cudaMemsetAsync(c->out32, 0, px * 12, c->stream)); CK(cudaMemsetAsync(c->out64, 0, px * 24, c->stream));
+        // the resolved fp32 and fp64 frames share ONE allocation (fp64 at frame64_offset): one CUDA IPC handle then gives
+        // another process both, so an fp64 render gathers across processes like an fp32 one
+        CK(cudaMalloc(&c->frame, px * 24)); CK(cudaMalloc(&c->out32, frame64_offset(px) + px * 24));
+        c->out64 = (double*)((char*)c->out32 + frame64_offset(px));
+        CK(cudaMemsetAsync(c->out32, 0, frame64_offset(px) + px * 24, c->stream));
         c->frame_pixels = px;
         if (!c->gather32) { c->gather32 = c->out32; c->gather64 = c->out64; }
     }
@@ -857,7 +878,7 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     // Gbounces/s on the 4K config (fewer launches, shorter tails); HBM capacity is not a constraint at 180 GB
     // ... and allocating 2 x 6 GB costs ~110 ms, which a one-shot render of a few hundred M samples would notice: 16 / 32 Mi there
     const uint64_t total_samples = total_groups * 32;
-    uint64_t B = prm.batch_samples ? prm.batch_samples : (total_samples >= (2ull << 30) ? (1u << 26) : total_samples >= (512ull << 20) ? (1u << 25) : (1u << 24));
+    uint64_t B = prm.batch_samples ? prm.batch_samples : (total_samples >= (1ull << 30) ? (1u << 26) : total_samples >= (512ull << 20) ? (1u << 25) : (1u << 24));
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
     // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
@@ -872,12 +893,6 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t)0; }
         const size_t avail = free_b / 2 + 2 * c->q_bytes;
         while (!prm.batch_samples && B > (1u << 20) && 2 * (size_t)cap_of(B) * ray_bytes > avail) B = B / 2 / 32 * 32;
-    }
-    // equal batches: 3 full ones and a remainder leave the last launches of a render half empty (at 8 GPUs a rank of the 4K
-    // bench has ~3.6 default batches), so the default size is spread evenly over the number of batches it implies
-    if (!prm.batch_samples && total_samples > B) {
-        const uint64_t nb = (total_samples + B - 1) / B;
-        B = std::max<uint64_t>(32, ((total_samples + nb - 1) / nb + 31) / 32 * 32);
     }
     const uint32_t cap = cap_of(B);
     const size_t q_bytes = (size_t)cap * ray_bytes;
@@ -939,14 +954,23 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     float*& clock_probe = diag.mhz;
     if (pass_times && std::getenv("IPT_PASS_CLOCKS")) CK(cudaMallocManaged(&clock_probe, 4096 * sizeof(float)));
     uint64_t launches = 0, batches = 0;
+    // a batch = mt_per_batch micro-tiles x smp_per_batch samples (sample ids walk the micro-tiles first, decode_sample)
     const uint64_t groups_per_batch = B / 32;
+    const uint32_t smp_per_batch = (uint32_t)std::min<uint64_t>(prm.samples, groups_per_batch);
+    uint32_t mt_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(1, total_mt), groups_per_batch / smp_per_batch));
+    // equal shares of the micro-tiles: full batches and a remainder leave the last launches of a render half empty (at 8 GPUs
+    // a rank of the 4K bench has ~3.6 default batches)
+    if (total_mt > mt_per_batch) {
+        const uint64_t nb = (total_mt + mt_per_batch - 1) / mt_per_batch;
+        mt_per_batch = (uint32_t)((total_mt + nb - 1) / nb);
+    }
     // progress (ipt_set_progress): an event after (at most 200 of) the batches; the host reports how many have finished
     const ipt_progress_fn progress = prm.rank == 0 ? g_progress_fn.load() : nullptr;
     struct BatchEvents {
         std::vector<cudaEvent_t> ev; size_t done = 0;
         ~BatchEvents() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
     } marks;
-    const uint64_t n_batches_total = groups_per_batch ? (total_groups + groups_per_batch - 1) / groups_per_batch : 0;
+    const uint64_t n_batches_total = total_mt ? ((total_mt + mt_per_batch - 1) / mt_per_batch) * ((prm.samples + smp_per_batch - 1) / smp_per_batch) : 0;
     const uint64_t mark_every = std::max<uint64_t>(1, (n_batches_total + 199) / 200);
     auto report = [&]() {
         while (marks.done < marks.ev.size() && cudaEventQuery(marks.ev[marks.done]) == cudaSuccess) marks.done++;
@@ -957,10 +981,12 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     // Renderer.cu:36-39: when width and height are both <= BLOCK_SIZE (22) every reference thread gets an empty pixel
     // rectangle and the frame stays black.  Kept: such frames are resolved from zeroed accumulators without tracing.
     const bool tiny = c->W <= 22 && c->H <= 22;
-    for (uint64_t g0 = 0; g0 < total_groups && !tiny; g0 += groups_per_batch) {
-        kp.base_mt = (uint32_t)(g0 / prm.samples);
-        kp.base_sample = (uint32_t)(g0 % prm.samples);
-        kp.n_first = (uint32_t)(std::min<uint64_t>(groups_per_batch, total_groups - g0) * 32);
+    for (uint64_t bi = 0; bi < n_batches_total && !tiny; bi++) {
+        const uint64_t s_blocks = (prm.samples + smp_per_batch - 1) / smp_per_batch;
+        kp.base_mt = (uint32_t)((bi / s_blocks) * mt_per_batch);
+        kp.mt_count = (uint32_t)std::min<uint64_t>(mt_per_batch, total_mt - kp.base_mt);
+        kp.base_sample = (uint32_t)((bi % s_blocks) * smp_per_batch);
+        kp.n_first = kp.mt_count * std::min<uint32_t>(smp_per_batch, prm.samples - kp.base_sample) * 32u;
         CK(cudaMemsetAsync(c->counters, 0, N_COUNTERS * sizeof(uint32_t), c->stream));
         if (use_split) {
             int rc = launch_split_batch(c, (KParams<float>&)kp, prm.max_depth, cap, smem, split_grids, &launches);
@@ -1194,7 +1220,8 @@ extern "C" int ipt_ctx_set_gather_target_ipc(ipt_ctx* c, const void* handle64)
     if (c->ipc_mapped) cudaIpcCloseMemHandle(c->ipc_mapped);
     c->ipc_mapped = p;
     c->gather32 = (float*)p;
-    c->gather64 = nullptr;   // the fp32 frame is what crosses NVLink between processes
+    // the owner's fp64 frame follows its fp32 frame in the same allocation (same scene, hence the same frame size, on both sides)
+    c->gather64 = c->frame_pixels ? (double*)((char*)p + frame64_offset(c->frame_pixels)) : nullptr;
     return IPT_OK;
 }
 

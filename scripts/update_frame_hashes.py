@@ -17,14 +17,14 @@ import bench
 import pyipt
 
 out = {}
-for name, over in [("spheres4k", {})] + bench.PER_CONFIG:
+for name, over, fp64 in [("spheres4k", {}, False)] + [(n, o, False) for n, o in bench.PER_CONFIG] + [("spheres4k", {"spp": 16}, True)]:
     wl = dict(bench.WORKLOADS[name]); wl.update(over)
     hs = pyipt.HostScene.load(bench.scene_file(wl["scene"]), width=wl["width"], height=wl["height"])
     c = pyipt.Context(0); c.set_scene(hs)
-    c.render(wl["spp"], wl["depth"], seed=123456)
-    frame = c.download(want64=False)
+    c.render(wl["spp"], wl["depth"], seed=123456, flags=pyipt.FLAG_FP64 if fp64 else 0)
+    frame = c.download(want64=fp64)
     c.close()
-    key = bench.frame_key(name, hs.width, hs.height, wl["depth"], wl["spp"], 123456, False)
+    key = bench.frame_key(name, hs.width, hs.height, wl["depth"], wl["spp"], 123456, fp64)
     out[key] = hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest()
     print(key, out[key], float(frame.mean()), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

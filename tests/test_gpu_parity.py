@@ -77,7 +77,8 @@ def test_depth_and_frame_edge_cases(pyipt, oracle, depth, spp, W, H):
     img, st = pyipt.render(hs, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
     assert frac_within(img, ref, 1e-9) >= 0.999
     img32, _ = pyipt.render(hs, spp, depth, seed=seed)
-    assert frac_within(img32, ref, 1e-3) >= 0.97
+    print("MEASURED edge_cases:", frac_within(img32, ref, 1e-3))
+    assert frac_within(img32, ref, 1e-3) >= 0.98   # measured on B200 (round 2): 0.988 - 1.0 over the eight cases
 
 
 def test_tiny_frames_are_black_like_the_reference(pyipt, oracle, golden_dir):
@@ -167,7 +168,8 @@ def test_bvh_render_matches_oracle(pyipt, oracle, tmp_path, monkeypatch, n_small
     assert frac_within(img, ref, 1e-9) >= 0.999
     assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-3 * cnt["casts_needed"]
     img32, _ = pyipt.render(hs, spp, depth, seed=seed)
-    assert frac_within(img32, ref, 1e-3) >= 0.97
+    print("MEASURED bvh_render:", frac_within(img32, ref, 1e-3))
+    assert frac_within(img32, ref, 1e-3) >= 0.99   # measured on B200 (round 2): 0.9979 / 0.9996 / 0.9979
     if n_small <= 300:   # same scene, brute force from shared memory (fp64 slots: 128 B per primitive)
         hs2 = pyipt.HostScene.load(path, brute_max=100000)
         img_b, _ = pyipt.render(hs2, spp, depth, seed=seed, flags=pyipt.FLAG_FP64)
@@ -320,7 +322,8 @@ def test_full_size_properties(pyipt, oracle, ctx, name):
     s64 = ctx.render(40, 10, seed=1, flags=pyipt.FLAG_FP64)
     b = ctx.download()
     assert np.isfinite(a).all() and a.min() >= 0
-    assert frac_within(a, b, 1e-3) >= 0.95
+    print("MEASURED full_size_props:", frac_within(a, b, 1e-3))
+    assert frac_within(a, b, 1e-3) >= 0.999   # measured on B200 (round 2): 0.99989 - 0.99992
     assert np.all(np.abs(a.mean(axis=(0, 1)) - b.mean(axis=(0, 1))) <= 1e-3 * b.mean(axis=(0, 1)))
     assert s32["samples"] == s64["samples"] == 1280 * 720 * 40
     assert abs(s32["traced_bounces"] - s64["traced_bounces"]) <= 2e-3 * s64["traced_bounces"]
@@ -443,7 +446,8 @@ def test_int8_fold_quirk_from_depth_130(pyipt, oracle, tmp_path, depth):
         img, st = pyipt.render(hs, spp, depth, seed=depth, flags=pyipt.FLAG_FP64)
         assert frac_within(img, ref, 1e-9) >= 0.995, path
         img32, _ = pyipt.render(hs, spp, depth, seed=depth)
-        assert frac_within(img32, ref, 1e-3) >= 0.95, path
+        print("MEASURED int8_fold:", frac_within(img32, ref, 1e-3))
+        assert frac_within(img32, ref, 1e-3) >= 0.97, path   # measured on B200 (round 2): 0.974 - 0.979 on the leaky scene (long fp32 paths flip where they leave), 1.0 on the closed one
         hs_bvh = pyipt.HostScene.load(str(path), brute_max=4)
         img_b, _ = pyipt.render(hs_bvh, spp, depth, seed=depth, flags=pyipt.FLAG_FP64)
         assert frac_within(img_b, ref, 1e-9) >= 0.995, path
@@ -513,7 +517,8 @@ def test_degenerate_and_unknown_objects(pyipt, oracle, tmp_path):
         assert frac_within(img, ref, 1e-9) >= 0.999, brute_max
         assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 1e-3 * cnt["casts_needed"]
         img32, _ = pyipt.render(hs, 4, 7, seed=21)
-        assert np.isfinite(img32).all() and frac_within(img32, ref, 1e-3) >= 0.97, brute_max
+        print("MEASURED degenerate:", frac_within(img32, ref, 1e-3))
+        assert np.isfinite(img32).all() and frac_within(img32, ref, 1e-3) >= 0.99, brute_max   # measured on B200 (round 2): 1.0
 
 
 def test_large_bvh_scene_hits_and_means(pyipt, oracle, tmp_path, monkeypatch):
@@ -538,7 +543,8 @@ def test_large_bvh_scene_hits_and_means(pyipt, oracle, tmp_path, monkeypatch):
     assert np.mean(gi == oi) >= 0.998
     s64 = c.render(8, 10, seed=3, flags=pyipt.FLAG_FP64); a = c.download()
     s32 = c.render(8, 10, seed=3); b = c.download()
-    assert frac_within(b, a, 1e-3) >= 0.93
+    print("MEASURED large_bvh_100k:", frac_within(b, a, 1e-3))
+    assert frac_within(b, a, 1e-3) >= 0.965   # measured on B200 (round 2): 0.9716: 100k primitives of radius 1-4 at 256x144, a pixel covers several of them and an fp32 rounding picks another one
     assert abs(a.mean() - b.mean()) <= 3e-3 * a.mean()
     assert abs(s32["traced_bounces"] - s64["traced_bounces"]) <= 3e-3 * s64["traced_bounces"]
     c.close()
@@ -832,7 +838,8 @@ def test_config5_statistical_parity_fp32_vs_fp64(pyipt, oracle, million):
         c.render(spp, depth, seed=100 + seed, flags=pyipt.FLAG_FP64); a = c.download()
         c.render(spp, depth, seed=100 + seed); b = c.download()
         if seed == 0:
-            assert frac_within(b, a, 1e-3) >= 0.97
+            print("MEASURED config5_fp32_vs_fp64:", frac_within(b, a, 1e-3))
+            assert frac_within(b, a, 1e-3) >= 0.99   # measured on B200 (round 2): 0.9980
         m64.append(a.mean(axis=(0, 1))); m32.append(b.mean(axis=(0, 1)))
         r64.append(a.reshape(4, H // 4, 4, W // 4, 3).mean(axis=(1, 3)).reshape(-1)); r32.append(b.reshape(4, H // 4, 4, W // 4, 3).mean(axis=(1, 3)).reshape(-1))
     m32, m64, r32, r64 = map(np.array, (m32, m64, r32, r64))
@@ -847,7 +854,7 @@ def test_config5_statistical_parity_fp32_vs_fp64(pyipt, oracle, million):
 
 
 def test_committed_frame_hashes(pyipt, oracle, million):
-    """tests/golden/frame_hashes.json: sha256 of the fp32 frame of every bench workload at the bench's own sizes (what
+    """tests/golden/frame_hashes.json: sha256 of the frame (fp32; fp64 for the fp64 sub-line) of every bench workload at the bench's own sizes (what
     bench.py compares its downloaded frame with at every N).  The same kernels are tied to the oracle per pixel by the tests
     above at sizes the oracle finishes; here the full-size frames must reproduce the committed hashes bit for bit."""
     import hashlib, sys
@@ -855,20 +862,20 @@ def test_committed_frame_hashes(pyipt, oracle, million):
     import bench
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "frame_hashes.json")))
     checked = 0
-    for name, over in [("spheres4k", {})] + bench.PER_CONFIG:
+    for name, over, fp64 in [("spheres4k", {}, False)] + [(n, o, False) for n, o in bench.PER_CONFIG] + [("spheres4k", {"spp": 16}, True)]:
         wl = dict(bench.WORKLOADS[name]); wl.update(over)
         path = million if name == "synthetic1m" else bench.scene_file(wl["scene"])
         hs = pyipt.HostScene.load(path, width=wl["width"], height=wl["height"])
         c = pyipt.Context(0); c.set_scene(hs)
-        c.render(wl["spp"], wl["depth"], seed=123456)
-        frame = c.download(want64=False)
+        c.render(wl["spp"], wl["depth"], seed=123456, flags=pyipt.FLAG_FP64 if fp64 else 0)
+        frame = c.download(want64=fp64)
         c.close()
-        key = bench.frame_key(name, hs.width, hs.height, wl["depth"], wl["spp"], 123456, False)
+        key = bench.frame_key(name, hs.width, hs.height, wl["depth"], wl["spp"], 123456, fp64)
         assert key in want, f"{key} missing from tests/golden/frame_hashes.json (scripts/update_frame_hashes.py writes it)"
         assert hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest() == want[key], key
         assert np.isfinite(frame).all() and frame.mean() > 0
         checked += 1
-    assert checked == 6
+    assert checked == 7
 
 
 def test_torchrun_two_process_gather(pyipt, oracle):
