@@ -1002,6 +1002,13 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 #ifndef IPT_FIRST_CTAS
 #define IPT_FIRST_CTAS 3
 #endif
+// slices of 32 rays a warp claims per atomic: pass 0 (short slices) and the multi-bounce passes
+#ifndef IPT_FIRST_CHUNK
+#define IPT_FIRST_CHUNK 8u
+#endif
+#ifndef IPT_DEEP_CHUNK
+#define IPT_DEEP_CHUNK 2u
+#endif
 template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? IPT_FIRST_CTAS : IPT_FAST_CTAS; };
 
 template <bool FIRST, int SHAPE = 0>
@@ -1045,7 +1052,7 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
     // pass - warps on SMs with slower memory finish late; ncu showed 30.5 % achieved against 37.5 % theoretical occupancy
     // (profiles/r01_ncu_spheres4k_final_deep_pass.txt) - and one claim per slice ran into the ~0.5 G/s a single address takes
     // in pass 0, whose slices are short (profiles/r02_ncu_pass0_v2.txt: 28 % of the stall samples on the claim).
-    constexpr uint32_t CHUNK = FIRST ? 8u : 2u, CHUNK_RAYS = CHUNK * 32u;
+    constexpr uint32_t CHUNK = FIRST ? IPT_FIRST_CHUNK : IPT_DEEP_CHUNK, CHUNK_RAYS = CHUNK * 32u;
     uint32_t* claim_ctr = p.counters + CLAIM + p.pass;
     // (p.static_slices, IPT_STATIC_SLICES=1: the static assignment, for A/B runs - no atomics)
     const uint32_t stride = gridDim.x * (BLOCK_THREADS / 32) * CHUNK_RAYS;

@@ -888,7 +888,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     // (at most OUT_BLOCK - 1 dead slots per resident warp of k_bounce_fast, whatever its launch configuration: 64 warps per SM)
     const uint32_t tail_slack = (uint32_t)c->sm_count * 64u * OUT_BLOCK;
     auto cap_of = [tail_slack](uint64_t b) { return (uint32_t)(2 * b) + tail_slack; };
-    {   // the default batch shrinks on devices (or in processes) where two queues of that size do not fit comfortably
+    if ((size_t)cap_of(B) * ray_bytes > c->q_bytes) {   // (queues of that size already allocated: nothing to decide, and no driver call)
+        // the default batch shrinks on devices (or in processes) where two queues of that size do not fit comfortably
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t)0; }
         const size_t avail = free_b / 2 + 2 * c->q_bytes;
