@@ -207,7 +207,7 @@ int ipt_ctx_download_rgb8(ipt_ctx* ctx, uint8_t* out_rgb8);                  /* 
 /* Tiles of other ranks: a context can write its finished tiles into another context's frame (same process: pass
  * the context; other process: pass the 64-byte CUDA IPC handle exported by the owner). */
 int ipt_ctx_export_frame(ipt_ctx* ctx, void* handle64);
-int ipt_ctx_set_gather_target_ipc(ipt_ctx* ctx, const void* handle64);
+int ipt_ctx_set_gather_target_ipc(ipt_ctx* ctx, const void* handle64);    /* after ipt_ctx_set_scene (same frame size as the owner) */
 int ipt_ctx_set_gather_target(ipt_ctx* ctx, ipt_ctx* owner);
 /* Owner of a tile under the static interleaved schedule. */
 uint32_t ipt_tile_owner(uint32_t tile_x, uint32_t tile_y, uint32_t tiles_x, uint32_t world);

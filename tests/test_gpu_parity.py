@@ -960,3 +960,25 @@ def test_grid_traversal_is_bit_identical(pyipt, oracle, tmp_path, monkeypatch, w
     if which != "lattice100k":
         oi, ot = oracle.nearest_hit(oracle.Scene.load(path), rays)
         assert np.mean(res[True][2][0] == oi) >= 0.998
+
+
+def test_next_event_with_many_lights_keeps_the_accumulators_in_range(pyipt, oracle, tmp_path):
+    """The next-event extension adds up to ~2.7 x n_lights x E of explicit light per diffuse hit; the fixed-point scale of the
+    frame accumulators accounts for it (a 64-bit accumulator that wrapped would show as a huge or negative pixel).  48 emissive
+    spheres, 4000 spp on a small frame: fixed-point and floating-point accumulation must agree, in fp32 and fp64."""
+    from scene_util import room_objects, vec
+    rng = np.random.default_rng(4)
+    objs = room_objects()
+    for i in range(48):
+        objs.append({"type": "sphere", "radius": float(rng.uniform(10, 25)), "position": vec(rng.uniform([100, -300, 60], [1180, 600, 660])),
+                     "color": vec((0, 0, 0)), "emission": vec((20, 20, 20)), "reflection": 0})
+    for i in range(12):
+        objs.append({"type": "sphere", "radius": 60.0, "position": vec(rng.uniform([150, -200, 100], [1100, 500, 600])),
+                     "color": vec((.7, .7, .7)), "emission": vec((0, 0, 0)), "reflection": 0})
+    scene = {"width": 64, "height": 36, "camera": {"position": vec((640, 0, 360)), "direction": vec((0, 1, 0)), "orientation": vec((-1, 0, 0))}, "objects": objs}
+    hs = pyipt.HostScene.load(write_scene(tmp_path / "lights.json", scene))
+    for fp in (0, pyipt.FLAG_FP64):
+        a, _ = pyipt.render(hs, 4000, 6, seed=5, flags=fp | pyipt.FLAG_NEXT_EVENT)
+        b, _ = pyipt.render(hs, 4000, 6, seed=5, flags=fp | pyipt.FLAG_NEXT_EVENT | pyipt.FLAG_FLOAT_ACCUM)
+        assert np.isfinite(a).all() and a.min() >= 0 and a.max() < 1e4
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-9), float(np.abs(a - b).max())
