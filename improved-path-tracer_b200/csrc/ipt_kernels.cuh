@@ -594,8 +594,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
 //    the boxes the host filed the primitives under;
 //  * cell steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (descend_min,
 //    leaf_min) or nobody wants the other.
-static constexpr int GRID_BURST = 4;
-__global__ void __launch_bounds__(BLOCK_THREADS, 4) k_extend_grid(const __grid_constant__ KParams<float> p)
+#ifndef IPT_GRID_BURST
+#define IPT_GRID_BURST 4
+#endif
+static constexpr int GRID_BURST = IPT_GRID_BURST;
+#ifndef IPT_GRID_CTAS
+#define IPT_GRID_CTAS 4
+#endif
+__global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(const __grid_constant__ KParams<float> p)
 {
     const SceneView<float> sc = p.sc;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;

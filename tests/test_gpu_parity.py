@@ -896,6 +896,12 @@ def test_torchrun_two_process_gather(pyipt, oracle):
     assert b["n_gpus"] == 2 and b["frame_check"]["n1_rerender_identical"] is True
     assert a["frame_sha256"] == b["frame_sha256"]
     assert all(x > 0 for x in b["traced_bounces_per_rank"]) and sum(b["traced_bounces_per_rank"]) == a["traced_bounces_per_rank"][0]
+    # the fp64 frame crosses processes too (it follows the fp32 frame in the exported allocation)
+    f64 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29578", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--fp64", "--spp", "4"] + common, capture_output=True, text=True, timeout=900)
+    assert f64.returncode == 0, f64.stderr[-2000:]
+    c = json.loads([l for l in f64.stdout.splitlines() if l.startswith("{")][-1])
+    assert c["dtype"] == "f64" and c["frame_check"]["n1_rerender_identical"] is True and c["frame_check"]["nonzero_pixels"] > 100000
 
 
 def test_progress_hook_reports_finished_batches(pyipt, oracle, ctx):

@@ -388,3 +388,57 @@ def test_bvh_depth_is_bounded_on_a_skewed_scene(pyipt, tmp_path):
                 assert nd.child[k] > i                       # parents first: what ipt_ctx_set_scene requires
                 depth[nd.child[k]] = depth[i] + 1
     assert 40 <= max(depth) <= 60, max(depth)
+
+
+def test_uniform_grid_files_every_primitive_under_the_cells_it_touches(pyipt, tmp_path):
+    """host/grid.cpp: a lattice of small primitives qualifies for the uniform grid; every small primitive is referenced from
+    every cell its bounding box overlaps (so a ray that walks the cells along its path meets every primitive it can hit), cell
+    lists are sorted and start ascending, the walls and the large light are the 'big' list.  A room of large spheres is
+    rejected (too many references per primitive) and keeps the tree only; IPT_NO_GRID switches the grid off."""
+    import subprocess, sys
+    path = str(tmp_path / "syn20k.json")
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), path, "20000", "64", "36"], check=True)
+    hs = pyipt.HostScene.load(path)
+    v = hs.view.contents
+    res = [v.grid_res[k] for k in range(3)]
+    assert all(r > 1 for r in res) and v.n_bvh_nodes > 0 and v.n_grid_big == 7
+    n_cells = res[0] * res[1] * res[2]
+    start = np.ctypeslib.as_array(v.grid_cell_start, shape=(n_cells + 1,)).astype(np.int64)
+    refs = np.ctypeslib.as_array(v.grid_refs, shape=(v.n_grid_refs,)).astype(np.int64)
+    big = set(int(v.grid_big[i]) for i in range(v.n_grid_big))
+    assert start[0] == 0 and start[-1] == v.n_grid_refs and np.all(np.diff(start) >= 0)
+    assert refs.min() >= 0 and refs.max() < v.n_objects and not (set(refs.tolist()) & big)
+    a = hs.arrays()
+    lo = np.array([v.grid_lo[k] for k in range(3)], dtype=np.float64); cs = np.array([v.grid_cell[k] for k in range(3)], dtype=np.float64)
+    slot_prim = a["bvh_slot_prim"]
+    rng = np.random.default_rng(0)
+    cell_sets = {}
+    for slot in rng.choice(v.n_objects, 400, replace=False):
+        if int(slot) in big:
+            continue
+        prim = int(slot_prim[slot])
+        if prim & 0x80000000:
+            continue                                     # spheres are enough to check the filing rule (boxes from centre and radius)
+        c = a["sphere_cxyzr"][prim]
+        blo, bhi = c[:3] - abs(c[3]), c[:3] + abs(c[3])
+        i0 = np.clip(np.floor((blo - lo) / cs), 0, np.array(res) - 1).astype(int); i1 = np.clip(np.floor((bhi - lo) / cs), 0, np.array(res) - 1).astype(int)
+        for z in range(i0[2], i1[2] + 1):
+            for y in range(i0[1], i1[1] + 1):
+                for x in range(i0[0], i1[0] + 1):
+                    ci = x + res[0] * (y + res[1] * z)
+                    if ci not in cell_sets:
+                        seg = refs[start[ci]:start[ci + 1]]
+                        assert np.all(np.diff(seg) > 0)           # sorted, no duplicates
+                        cell_sets[ci] = set(seg.tolist())
+                    assert int(slot) in cell_sets[ci], (slot, x, y, z)
+    # a room of large spheres: too many references per primitive -> no grid
+    sys.path.insert(0, os.path.dirname(__file__))
+    from scene_util import synthetic_scene, write_scene
+    hs2 = pyipt.HostScene.load(write_scene(tmp_path / "room40k.json", synthetic_scene(40000, 3, width=64, height=36)))
+    assert hs2.view.contents.grid_res[0] == 0 and hs2.view.contents.n_bvh_nodes > 0
+    os.environ["IPT_NO_GRID"] = "1"
+    try:
+        hs3 = pyipt.HostScene.load(path)
+        assert hs3.view.contents.grid_res[0] == 0 and hs3.view.contents.n_bvh_nodes > 0
+    finally:
+        del os.environ["IPT_NO_GRID"]
