@@ -428,6 +428,9 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
             roof_issue = {"bound": "issue", "achieved": ach_issue, "peak": issue_peak, "unit": "G warp-inst/s", "frac": ach_issue / issue_peak,
                           "warp_instructions_per_bounce": wi, "source": "instruction count of the ncu capture in profiles/ (smsp__inst_executed.sum / rays / bounces)"}
         traced_samples = active_pixels * wl["spp"]
+        v = hs.view.contents
+        accel = (f"uniform grid {v.grid_res[0]}x{v.grid_res[1]}x{v.grid_res[2]} ({v.n_grid_refs} references, {v.n_grid_big} big primitives) over a 2-wide BVH of {v.n_bvh_nodes} nodes"
+                 if v.grid_res[0] and not fp64 else f"2-wide BVH of {v.n_bvh_nodes} nodes" if v.n_bvh_nodes else f"none: {v.n_objects} primitives scanned from shared memory")
         line = {
             "metric": "Msamples/s", "value": tot_samples / (ms_dev * 1e-3) / 1e6, "unit": "Msamples/s",
             "gbounces_per_s": tot_bounces / (ms_dev * 1e-3) / 1e9,
@@ -440,8 +443,9 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
                        "samples_per_step": int(tot_samples), "traced_samples_per_step": int(traced_samples),
                        "traced_bounces_per_step": int(tot_bounces),
                        "pixels_with_camera_rays": int(active_pixels), "pixels": W * H,
+                       "acceleration": accel,
                        "parallelism": f"tiles 64x32 interleaved over {world} GPU(s); {gather}",
-                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 6 GB (64 Mi-sample batches, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-7 keyed by pixel/sample/bounce"},
+                       "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 26 GB (batches of a quarter of the frame's samples, 16 Mi to 256 Mi, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-7 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "gbounces_per_s": tot_bounces / (e2e_ms * 1e-3) / 1e9,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "result": "fp64 frame" if fp64 else "fp32 frame", "rank0_kernel_ms_events": e2e_events_ms,

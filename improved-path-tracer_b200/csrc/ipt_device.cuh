@@ -538,6 +538,8 @@ struct FastScene {
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
     bool box_pairs;                          // see fast_axis_pair
+    float blo_x, blo_y, blo_z, bhi_x, bhi_y, bhi_z;   // plane coordinates of the lower / upper wall per axis (kernel parameters:
+                                             // the 'origin between the walls' test compares against the constant bank)
 };
 __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
@@ -547,12 +549,14 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 struct FastHeader {
     uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
     uint32_t box_pairs;     // box room whose two rectangles per axis are stored lower plane first (fast_axis_pair)
+    float box_lo[3], box_hi[3];   // their plane coordinates
     uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
 };
 __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
     FastHeader h;
     h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_pairs = 0;
+    for (int k = 0; k < 3; k++) { h.box_lo[k] = 0.f; h.box_hi[k] = 0.f; }
     h.off_sphobj = 2 + n_sph;
     h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
     h.off_gen = h.off_axs + 2 * (nx + ny + nz);
@@ -564,6 +568,7 @@ __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHead
 {
     FastScene f;
     f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0;
+    f.blo_x = hd.box_lo[0]; f.blo_y = hd.box_lo[1]; f.blo_z = hd.box_lo[2]; f.bhi_x = hd.box_hi[0]; f.bhi_y = hd.box_hi[1]; f.bhi_z = hd.box_hi[2];
     f.sph = reinterpret_cast<const float4*>(blob + 2);
     f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
     f.axs = reinterpret_cast<const float4*>(blob + hd.off_axs);
@@ -678,8 +683,7 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
 #pragma unroll
         for (int s = 0; s < SHAPE - 1; s++) fast_sphere(f.sph[s], (uint32_t)s, self_sphere, o, d, best);
         // origin between the walls of every pair (on a wall counts): only the wall ahead can be hit (fast_axis_pair)
-        const bool between = f.box_pairs && o.x >= f.axs[0].x && o.x <= f.axs[2].x && o.y >= f.axs[4].x && o.y <= f.axs[6].x &&
-                             o.z >= f.axs[8].x && o.z <= f.axs[10].x;
+        const bool between = f.box_pairs && o.x >= f.blo_x && o.x <= f.bhi_x && o.y >= f.blo_y && o.y <= f.bhi_y && o.z >= f.blo_z && o.z <= f.bhi_z;
         if (between) {
             fast_axis_pair<0, 0>(f.axs, o, d, rcp_fast(d.x), best);
             fast_axis_pair<1, 2>(f.axs, o, d, rcp_fast(d.y), best);

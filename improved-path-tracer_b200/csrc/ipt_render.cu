@@ -557,6 +557,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         c->fast_words = (uint32_t)(blob.size() / 4);
         c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
         c->fast_hd.box_pairs = blob[6];
+        if (blob[6]) {   // plane coordinates of the wall pairs: record r of the axis lists starts at word off_axs * 4 + r * 8
+            const uint32_t* ax = blob.data() + (size_t)c->fast_hd.off_axs * 4;
+            for (int k = 0; k < 3; k++) { std::memcpy(&c->fast_hd.box_lo[k], ax + (2 * k) * 8, 4); std::memcpy(&c->fast_hd.box_hi[k], ax + (2 * k + 1) * 8, 4); }
+        }
         if (std::getenv("IPT_VERBOSE"))
             std::fprintf(stderr, "[ipt] typed lists: %u spheres, %u + %u + %u axis-aligned rectangles, %u general; box-room instantiation %d, wall pairs %s\n", blob[0], blob[1],
                          blob[2], blob[3], blob[4], fast_shape(blob[0], blob[1], blob[2], blob[3], blob[4]), blob[6] ? "yes" : "no");
@@ -874,11 +878,17 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     // batches
     const uint64_t total_mt = c->n_mt;   // only the micro-tiles whose camera rays can reach the scene
     const uint64_t total_groups = total_mt * prm.samples;
-    // default batch: 64 Mi camera rays (2 x 6 GB fp32 ray queues) — measured on B200: 4 Mi 27.9, 16 Mi 34.4, 64 Mi 37.3
-    // Gbounces/s on the 4K config (fewer launches, shorter tails); HBM capacity is not a constraint at 180 GB
-    // ... and allocating 2 x 6 GB costs ~110 ms, which a one-shot render of a few hundred M samples would notice: 16 / 32 Mi there
+    // default batch: a quarter of the render, between 16 Mi and 256 Mi camera rays (2 x 26 GB of fp32 ray queues; HBM capacity is
+    // not a constraint at 180 GB) - measured on B200 on the 4K config: 4 Mi 27.9, 16 Mi 34.4, 64 Mi 37.3 Gbounces/s in round 1
+    // (fewer launches, shorter tails), 32 / 64 / 128 / 256 Mi 65.4 / 66.2 / 66.4 / 66.8 in round 2.  A one-shot render
+    // (ipt_render: queues allocated for this call only, ~9 ms per GB) stops at 64 Mi.
     const uint64_t total_samples = total_groups * 32;
-    uint64_t B = prm.batch_samples ? prm.batch_samples : (total_samples >= (1ull << 30) ? (1u << 26) : total_samples >= (512ull << 20) ? (1u << 25) : (1u << 24));
+    uint64_t B = prm.batch_samples;
+    if (!B) {
+        const uint64_t cap_b = (prm.reserved[0] & 1u) ? (1ull << 26) : (1ull << 28);
+        B = 1ull << 24;
+        while (B < cap_b && B * 4 < total_samples) B <<= 1;
+    }
     B = std::max<uint64_t>(32, std::min<uint64_t>(B, 1u << 28) / 32 * 32);
     B = std::min<uint64_t>(B, std::max<uint64_t>(32, total_groups * 32));
     // maxDepth >= 130: deep paths carry their deferred radiance in extra queue planes (see k_bounce, DEFER)
@@ -1284,6 +1294,7 @@ static int render_impl(const ipt_scene* scene, const ipt_params* params, int n_g
             th.emplace_back([&, g] {
                 ipt_params p = *params;
                 p.rank = (uint32_t)g; p.world = (uint32_t)n_gpus;
+                p.reserved[0] |= 1u;   // one-shot: the ray queues live for this call only (render_typed's default batch size)
                 rcs[g] = ipt_ctx_render(ctx[g], &p, &sts[g]);
             });
         for (auto& t : th) t.join();

@@ -132,7 +132,7 @@ typedef struct ipt_params {
     uint32_t tile_w, tile_h; /* multi-GPU tile size in pixels (multiples of 8 and 4); 0 = default 64x32            */
     uint32_t rank, world;    /* this context renders the tiles t with owner(t) == rank out of `world` (world 0 = 1) */
     uint32_t batch_samples;  /* camera rays generated per wavefront batch; 0 = default                             */
-    uint32_t reserved[4];
+    uint32_t reserved[4];    /* set to 0 (reserved[0] bit 0 is used inside the library: one-shot render) */
 } ipt_params;
 
 typedef struct ipt_stats {
