@@ -538,6 +538,7 @@ struct FastScene {
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
     bool box_pairs;                          // see fast_axis_pair
+    bool any_unknown;                        // some object has a reflection value outside 0..2 (the 'teleport' ray of scatter<R>)
     float blo_x, blo_y, blo_z, bhi_x, bhi_y, bhi_z;   // plane coordinates of the lower / upper wall per axis (kernel parameters:
                                              // the 'origin between the walls' test compares against the constant bank)
 };
@@ -549,13 +550,14 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 struct FastHeader {
     uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
     uint32_t box_pairs;     // box room whose two rectangles per axis are stored lower plane first (fast_axis_pair)
+    uint32_t any_unknown;   // some object has an unknown reflection value
     float box_lo[3], box_hi[3];   // their plane coordinates
     uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
 };
 __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
     FastHeader h;
-    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_pairs = 0;
+    h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_pairs = 0; h.any_unknown = 1;
     for (int k = 0; k < 3; k++) { h.box_lo[k] = 0.f; h.box_hi[k] = 0.f; }
     h.off_sphobj = 2 + n_sph;
     h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
@@ -567,7 +569,7 @@ __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, u
 __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0;
+    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0; f.any_unknown = hd.any_unknown != 0;
     f.blo_x = hd.box_lo[0]; f.blo_y = hd.box_lo[1]; f.blo_z = hd.box_lo[2]; f.bhi_x = hd.box_hi[0]; f.bhi_y = hd.box_hi[1]; f.bhi_z = hd.box_hi[2];
     f.sph = reinterpret_cast<const float4*>(blob + 2);
     f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
@@ -736,17 +738,18 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
 {
     const uint32_t kind = code >> 28, idx = code & 0x0FFFFFFFu;
     V3<float> raw, n;
-    if (kind == 0) {
-        const float4 sp = f.sph[idx];
-        raw = normalize(mk<float>(P.x - sp.x, P.y - sp.y, P.z - sp.z));       // Sphere.cu:44
-        n = dot(in, raw) < 0.f ? -raw : raw;                                  // Sphere.cu:45
-    } else if (NO_GEN || kind != 4) {
-        // normal +-e_K: Plane.cu:73's test n.d < 0 is the sign of the ray's K component
+    {   // axis-aligned rectangle (most hits; computed for every lane, a few selects): normal +-e_K - Plane.cu:73's test
+        // n.d < 0 is the sign of the ray's K component
         const float ik = kind == 1 ? in.x : (kind == 2 ? in.y : in.z);
         const float sg = ik < 0.f ? 1.f : -1.f;
         n = mk<float>(kind == 1 ? sg : 0.f, kind == 2 ? sg : 0.f, kind == 3 ? sg : 0.f);
         raw = n;                                                              // Plane.cu:79
-    } else {
+    }
+    if (kind == 0) {
+        const float4 sp = f.sph[idx];
+        raw = normalize(mk<float>(P.x - sp.x, P.y - sp.y, P.z - sp.z));       // Sphere.cu:44
+        n = dot(in, raw) < 0.f ? -raw : raw;                                  // Sphere.cu:45
+    } else if (!NO_GEN && kind == 4) {
         const V3<float> pn = xyz(f.gen[4 * idx]);
         n = dot(in, pn) < 0.f ? pn : -pn;                                     // Plane.cu:73
         raw = n;
@@ -766,7 +769,7 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
     s.d0.x = pickSpec ? spec.x : (pickRefr ? refr.x : diff.x);
     s.d0.y = pickSpec ? spec.y : (pickRefr ? refr.y : diff.y);
     s.d0.z = pickSpec ? spec.z : (pickRefr ? refr.z : diff.z);
-    s.teleport = reflection < 0 || reflection > 2;                            // unknown material: see scatter<R>
+    s.teleport = f.any_unknown && (reflection < 0 || reflection > 2);         // unknown material: see scatter<R> (uniform flag: no scene shipped has one)
     s.has0 = !s.teleport || depth >= 2;
     if (s.teleport) { s.d0.x = 0.f; s.d0.y = 0.f; s.d0.z = 0.f; }
     s.has1 = early && (isSpec || (isRefr && refr_ok));                        // AObject.hpp:91-94, :122-125

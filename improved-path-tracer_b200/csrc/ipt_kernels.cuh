@@ -1150,7 +1150,7 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                         has0 = alive;
                         r.o = P; r.d = sp.d0; r.thr = nthr * sp.w0; r.self = h.code;
                         r.meta = mcommon | (r.meta & 0x300u);
-                        if (sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; r.meta &= ~META_ONSURF; }
+                        if (sc.any_unknown && sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; r.meta &= ~META_ONSURF; }
                     }
                 }
             }

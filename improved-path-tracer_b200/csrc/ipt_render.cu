@@ -274,6 +274,11 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
     uint32_t* p = blob.data();
     p[0] = ns; p[1] = (uint32_t)ax[0].size(); p[2] = (uint32_t)ax[1].size(); p[3] = (uint32_t)ax[2].size(); p[4] = ng; p[5] = no;
     p[6] = box_pairs ? 1u : 0u;
+    {   // p[7]: does any object carry a reflection value outside 0..2 (unknown material)?
+        bool unk = false;
+        for (uint32_t k = 0; k < no; k++) unk = unk || s->mat_reflection[k] < 0 || s->mat_reflection[k] > 2;
+        p[7] = unk ? 1u : 0u;
+    }
     p += 8;
     for (uint32_t i = 0; i < ns; i++)
         for (int k = 0; k < 4; k++) *p++ = i < ns_real ? F(s->sphere_cxyzr[4 * (size_t)i + k]) : F(k < 3 ? (double)NAN : 0.0);   // pad: NaN centre -> delta is NaN -> never a hit
@@ -556,7 +561,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->fast_words = (uint32_t)(blob.size() / 4);
         c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
-        c->fast_hd.box_pairs = blob[6];
+        c->fast_hd.box_pairs = blob[6]; c->fast_hd.any_unknown = blob[7];
         if (blob[6]) {   // plane coordinates of the wall pairs: record r of the axis lists starts at word off_axs * 4 + r * 8
             const uint32_t* ax = blob.data() + (size_t)c->fast_hd.off_axs * 4;
             for (int k = 0; k < 3; k++) { std::memcpy(&c->fast_hd.box_lo[k], ax + (2 * k) * 8, 4); std::memcpy(&c->fast_hd.box_hi[k], ax + (2 * k + 1) * 8, 4); }
