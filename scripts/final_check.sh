@@ -7,9 +7,9 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_o
 python bench.py > gpurun_out/final/bench_default.jsonl 2> gpurun_out/final/bench_default.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/final/bench_default.jsonl
 python bench.py --impl reference > gpurun_out/final/bench_reference.jsonl 2> gpurun_out/final/bench_reference.err; cut -c1-200 gpurun_out/final/bench_reference.jsonl
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-per-config"
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 290 -c 300 --csv --log-file gpurun_out/final/launches_default.csv $CMD > gpurun_out/final/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bounce_fast --launch-skip 145 --launch-count 1 -f -o gpurun_out/final/prof_deep $CMD > gpurun_out/final/ncu_deep.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bounce_fast --launch-skip 144 --launch-count 1 -f -o gpurun_out/final/prof_pass0 $CMD > gpurun_out/final/ncu_pass0.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 170 --csv --log-file gpurun_out/final/launches_default.csv $CMD > gpurun_out/final/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_bounce_fast --launch-skip 37 --launch-count 1 -f -o gpurun_out/final/prof_deep $CMD > gpurun_out/final/ncu_deep.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_bounce_fast --launch-skip 36 --launch-count 1 -f -o gpurun_out/final/prof_pass0 $CMD > gpurun_out/final/ncu_pass0.log 2>&1
 SYN="python bench.py --workload synthetic1m --spp 16 --steps 1 --warmup 1 --no-cpu-baseline --no-per-config"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 130 --csv --log-file gpurun_out/final/launches_synthetic1m.csv $SYN > gpurun_out/final/ncu_launches_syn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_extend_grid -s 4 -c 1 -f -o gpurun_out/final/prof_grid $SYN > gpurun_out/final/ncu_grid.log 2>&1
