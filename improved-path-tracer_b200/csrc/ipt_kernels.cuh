@@ -928,10 +928,9 @@ __device__ __forceinline__ void accumulate_fast(const KParams<float>& p, uint32_
 // The product kernel for brute-force scenes: same wavefront step as k_bounce<float, MODE_BRUTE, FIRST>, on the typed
 // fp32 scene lists (FastScene) with branch-free intersection and scatter.  What the ncu captures led to
 // (profiles/README.md):
-//  * slices of 32 rays are assigned to warps statically (slice = warp + k * warps): every ray costs the same here, so
-//    no work-claim atomic is needed and the next slice is known — its three 16-byte record planes are prefetched with
-//    cp.async into a per-thread shared-memory slot while the current slice is computed (double buffered, no barrier:
-//    a thread only ever reads what it fetched itself);
+//  * slices of 32 rays are claimed by warps from a per-pass counter in chunks, one chunk ahead (see the loop below), so the next
+//    slice is known early - its three 16-byte record planes are prefetched with cp.async into a per-thread shared-memory
+//    slot while the current slice is computed (double buffered, no barrier: a thread only ever reads what it fetched itself);
 //  * compaction is warp ballot + popc into a WARP-PRIVATE block of OUT_BLOCK queue slots, reserved with one atomic per
 //    block.  One atomic per warp iteration serialises on the queue counter at ~0.9 G atomics/s on B200 (which capped
 //    these scenes at ~29 Grays/s); per-CTA aggregation fixed that but cost two barriers per slice.  The unused tail of

@@ -107,8 +107,8 @@ struct ipt_ctx {
     uint32_t* grid_refs = nullptr;
     GridHeader grid_hd = {};
     WideNode* wide = nullptr;        // the 8-wide quantised tree derived from the 2-wide one (ipt_wide.h), fp32 traversal
-    uint32_t n_wide = 0, wide_stack_need = 0, wide_depth = 0;
-    uint2* wide_spill = nullptr;     // stack entries beyond the shared-memory part, per resident ray of k_extend_wide
+    uint32_t n_wide = 0, wide_depth = 0;
+    uint2* wide_spill = nullptr;     // stack entries beyond the shared-memory part, per resident lane of k_extend_cw
     size_t wide_spill_bytes = 0;
     uint4* fast_blob = nullptr;      // fp32 brute-force layout (FastScene), built when the scene has no BVH
     uint32_t fast_words = 0;
@@ -538,7 +538,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     if (b_nodes) CK(cudaMemcpyAsync(c->nodes, nd, b_nodes, cudaMemcpyHostToDevice, c->stream));
     if (b_bs) CK(cudaMemcpyAsync(c->bslot, bs, b_bs, cudaMemcpyHostToDevice, c->stream));
     if (!wt.nodes.empty()) CK(cudaMemcpyAsync(c->wide, wt.nodes.data(), wt.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
-    c->n_wide = (uint32_t)wt.nodes.size(); c->wide_stack_need = wt.stack_need; c->wide_depth = wt.depth;
+    c->n_wide = (uint32_t)wt.nodes.size(); c->wide_depth = wt.depth;
     c->grid_hd = GridHeader{};
     if (grid) {
         CK(cudaMemcpyAsync(c->grid_cells, gcells, b_cells, cudaMemcpyHostToDevice, c->stream));
@@ -554,8 +554,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
             std::fprintf(stderr, "[ipt] grid %u x %u x %u, %u references, %u big primitives: %.1f MB\n", g.res[0], g.res[1], g.res[2], s->n_grid_refs, g.n_big, (b_cells + b_refs) / 1e6);
     }
     if (std::getenv("IPT_VERBOSE") && bvh)
-        std::fprintf(stderr, "[ipt] 8-wide tree: %zu nodes (%.2f children per node), depth %u, stack need <= %u, from %u 2-wide nodes\n", wt.nodes.size(),
-                     wt.nodes.empty() ? 0.0 : wt.sum_children / wt.nodes.size(), wt.depth, wt.stack_need, s->n_bvh_nodes);
+        std::fprintf(stderr, "[ipt] 8-wide tree: %zu nodes (%.2f children per node), depth %u, from %u 2-wide nodes\n", wt.nodes.size(),
+                     wt.nodes.empty() ? 0.0 : wt.sum_children / wt.nodes.size(), wt.depth, s->n_bvh_nodes);
     c->fast_words = 0;
     if (!blob.empty()) {
         CK(cudaMemcpyAsync(c->fast_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, c->stream));

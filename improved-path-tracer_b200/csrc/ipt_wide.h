@@ -1,5 +1,5 @@
 // ipt_wide.h — the 8-wide, quantised form of the bounding volume hierarchy that the fp32 traversal kernel walks
-// (k_extend_wide, ipt_kernels.cuh), and the host routine that derives it from the 2-wide tree of the C ABI
+// (k_extend_cw, ipt_kernels.cuh; opt-in: IPT_BVH8=1), and the host routine that derives it from the 2-wide tree of the C ABI
 // (ipt_bvh_node, include/ipt_abi.h).  New work: the reference has no acceleration structure (Renderer.cu:227-243 is a
 // linear scan); what has to be preserved is the scan's answer, so every box here is a superset of the 2-wide tree's
 // (already padded) box it stands for.
@@ -37,8 +37,7 @@ struct alignas(128) WideNode {
 };
 static_assert(sizeof(WideNode) == 128, "one node per 128-byte line");
 static constexpr int32_t WIDE_EMPTY = 0x7FFFFFFF;
-// Slot s of a node is stored at position s of q[] / link[]; with LPR lanes per ray, lane l decodes slots
-// [l * 8 / LPR, (l + 1) * 8 / LPR).
+// Slot s of a node is stored at position s of q[] / link[].
 }  // namespace ipt
 
 #include <algorithm>
@@ -55,7 +54,6 @@ struct WideTree {
                                   // order (whole leaves move, so every leaf of the 2-wide tree stays a consecutive range)
     std::vector<uint32_t> inv;    // old slot -> new slot
     uint32_t depth = 0;        // levels of inner nodes on the longest root-to-leaf path
-    uint32_t stack_need = 0;   // most entries a traversal can have pending: sum over a path of (children - 1)
     double sum_children = 0;
 };
 
@@ -255,7 +253,6 @@ inline const char* wide_collapse(const ipt_bvh_node* n2, uint32_t n_nodes, uint3
         }
         const uint32_t stack_here = p.stack + (uint32_t)items.size() - 1;
         out.depth = std::max(out.depth, p.depth);
-        out.stack_need = std::max(out.stack_need, stack_here);
         out.sum_children += (double)items.size();
         // Slot assignment (Ylitie, Karras, Laine 2017): slot s stands for the corner direction (s&1 ? +x : -x, s&2 ? +y : -y,
         // s&4 ? +z : -z); children go greedily to the slots their centre (relative to the node's) points at most.  A ray
