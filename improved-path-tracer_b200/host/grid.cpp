@@ -102,6 +102,28 @@ void ipt_host_scene::build_grid()
         a = (uint32_t)std::min<double>(grid_res[k] - 1, std::max(0.0, fa));
         z = (uint32_t)std::min<double>(grid_res[k] - 1, std::max(0.0, fz));
     };
+    // a sphere is filed under the cells it actually reaches (centre-to-cell distance <= padded radius), not under every cell of its
+    // bounding box: the corner cells of the box are the ones a small sphere misses
+    std::vector<float> sph_r(n, -1.f);
+    std::vector<double> sph_c(3 * n, 0.0);
+    for (size_t s = 0; s < n; s++) {
+        const uint32_t prim = bvh_slot_prim[s];
+        if (prim & 0x80000000u || !box[s].valid || std::getenv("IPT_GRID_BOX_FILING")) continue;
+        const double* c = &sphere_cxyzr[4 * (size_t)prim];
+        sph_r[s] = (float)(std::fabs(c[3]) + 4e-3 + 1e-6 * std::max({std::fabs(c[0]), std::fabs(c[1]), std::fabs(c[2])}) + 1e-6 * std::fabs(c[3]));
+        for (int k = 0; k < 3; k++) sph_c[3 * s + k] = c[k];
+    }
+    auto reaches = [&](size_t s, uint32_t x, uint32_t y, uint32_t z) {
+        if (sph_r[s] < 0.f) return true;
+        const uint32_t idx[3] = {x, y, z};
+        double d2 = 0;
+        for (int k = 0; k < 3; k++) {
+            const double a = (double)grid_lo[k] + (double)idx[k] * (double)grid_cell[k], b = a + (double)grid_cell[k], c = sph_c[3 * s + k];
+            const double d = c < a ? a - c : (c > b ? c - b : 0.0);
+            d2 += d * d;
+        }
+        return d2 <= (double)sph_r[s] * (double)sph_r[s];
+    };
     std::vector<std::atomic<uint32_t>> count(n_cells + 1);
     parallel_for(n_cells + 1, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) count[i].store(0, std::memory_order_relaxed); });
     const uint32_t rx = grid_res[0], ry = grid_res[1];
@@ -111,7 +133,7 @@ void ipt_host_scene::build_grid()
             uint32_t x0, x1, y0, y1, z0, z1;
             range(box[s], 0, x0, x1); range(box[s], 1, y0, y1); range(box[s], 2, z0, z1);
             for (uint32_t z = z0; z <= z1; z++) for (uint32_t y = y0; y <= y1; y++) for (uint32_t x = x0; x <= x1; x++)
-                count[x + (size_t)rx * (y + (size_t)ry * z)].fetch_add(1, std::memory_order_relaxed);
+                if (reaches(s, x, y, z)) count[x + (size_t)rx * (y + (size_t)ry * z)].fetch_add(1, std::memory_order_relaxed);
         }
     });
     grid_cell_start.resize(n_cells + 1);
@@ -136,7 +158,7 @@ void ipt_host_scene::build_grid()
             uint32_t x0, x1, y0, y1, z0, z1;
             range(box[s], 0, x0, x1); range(box[s], 1, y0, y1); range(box[s], 2, z0, z1);
             for (uint32_t z = z0; z <= z1; z++) for (uint32_t y = y0; y <= y1; y++) for (uint32_t x = x0; x <= x1; x++)
-                grid_refs[count[x + (size_t)rx * (y + (size_t)ry * z)].fetch_add(1, std::memory_order_relaxed)] = (uint32_t)s;
+                if (reaches(s, x, y, z)) grid_refs[count[x + (size_t)rx * (y + (size_t)ry * z)].fetch_add(1, std::memory_order_relaxed)] = (uint32_t)s;
         }
     });
     // references of a cell in slot order: the order threads filled them in must not show anywhere (it does not change a
