@@ -106,9 +106,10 @@ void ipt_host_scene::build_grid()
     // bounding box: the corner cells of the box are the ones a small sphere misses
     std::vector<float> sph_r(n, -1.f);
     std::vector<double> sph_c(3 * n, 0.0);
-    for (size_t s = 0; s < n; s++) {
+    const bool box_filing = std::getenv("IPT_GRID_BOX_FILING") != nullptr;   // A/B knob: every cell of the bounding box
+    for (size_t s = 0; s < n && !box_filing; s++) {
         const uint32_t prim = bvh_slot_prim[s];
-        if (prim & 0x80000000u || !box[s].valid || std::getenv("IPT_GRID_BOX_FILING")) continue;
+        if (prim & 0x80000000u || !box[s].valid) continue;
         const double* c = &sphere_cxyzr[4 * (size_t)prim];
         sph_r[s] = (float)(std::fabs(c[3]) + 4e-3 + 1e-6 * std::max({std::fabs(c[0]), std::fabs(c[1]), std::fabs(c[2])}) + 1e-6 * std::fabs(c[3]));
         for (int k = 0; k < 3; k++) sph_c[3 * s + k] = c[k];
