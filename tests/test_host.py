@@ -392,7 +392,7 @@ def test_bvh_depth_is_bounded_on_a_skewed_scene(pyipt, tmp_path):
 
 def test_uniform_grid_files_every_primitive_under_the_cells_it_touches(pyipt, tmp_path):
     """host/grid.cpp: a lattice of small primitives qualifies for the uniform grid; every small primitive is referenced from
-    every cell its bounding box overlaps (so a ray that walks the cells along its path meets every primitive it can hit), cell
+    every cell it reaches (so a ray that walks the cells along its path meets every primitive it can hit), cell
     lists are sorted and start ascending, the walls and the large light are the 'big' list.  A room of large spheres is
     rejected (too many references per primitive) and keeps the tree only; IPT_NO_GRID switches the grid off."""
     import subprocess, sys
@@ -425,6 +425,11 @@ def test_uniform_grid_files_every_primitive_under_the_cells_it_touches(pyipt, tm
         for z in range(i0[2], i1[2] + 1):
             for y in range(i0[1], i1[1] + 1):
                 for x in range(i0[0], i1[0] + 1):
+                    # filed under every cell the sphere reaches (centre-to-cell distance <= radius), not the corners of its box
+                    ca = lo + np.array([x, y, z]) * cs
+                    gap = np.maximum(np.maximum(ca - c[:3], c[:3] - (ca + cs)), 0.0)
+                    if float(gap @ gap) > abs(c[3]) ** 2:
+                        continue
                     ci = x + res[0] * (y + res[1] * z)
                     if ci not in cell_sets:
                         seg = refs[start[ci]:start[ci + 1]]
