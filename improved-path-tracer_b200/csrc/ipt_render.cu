@@ -574,6 +574,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     lap_up("enqueue copies");
     CK(cudaStreamSynchronize(c->stream));
     lap_up("wait for copies");
+    struct LapAtExit { decltype(lap_up)& f; ~LapAtExit() { f("scene box, lights, frame buffers"); } } lap_at_exit{lap_up};
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->last.upload_ms = ms;
@@ -584,31 +585,50 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     {   // bounding box of all primitives (for the exact camera-ray pruning): spheres c +- |r|; rectangles: the four
         // corners of the accepted parallelogram, solved from n.r = 0, u.r = +-u_hi, v.r = +-v_hi (degenerate ones,
         // whose normal is NaN, can never be hit and are skipped)
+        // (one partial box per host thread, merged under a lock: a million primitives are 10 ms on one core)
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         bool ok = true;
-        auto grow = [&](const double* q) { for (int k = 0; k < 3; k++) { if (!(q[k] == q[k])) { ok = false; } lo[k] = std::min(lo[k], q[k]); hi[k] = std::max(hi[k], q[k]); } };
-        for (uint32_t i = 0; i < s->n_spheres; i++) {
-            const double* sp = s->sphere_cxyzr + 4 * (size_t)i;
-            const double r = std::fabs(sp[3]);
-            const double a[3] = {sp[0] - r, sp[1] - r, sp[2] - r}, b[3] = {sp[0] + r, sp[1] + r, sp[2] + r};
-            grow(a); grow(b);
-        }
-        for (uint32_t j = 0; j < s->n_rects; j++) {
-            const double *n3 = s->rect_plane + 4 * (size_t)j, *u = s->rect_u + 4 * (size_t)j, *v = s->rect_v + 4 * (size_t)j, *b = s->rect_bounds + 4 * (size_t)j;
-            if (!(n3[0] == n3[0]) || !(u[0] == u[0]) || !(v[0] == v[0])) continue;   // NaN normal: never hit
-            // solve [n; u; v] x = rhs by Cramer's rule
-            const double det = n3[0] * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * v[1] - u[1] * v[0]);
-            if (!(std::fabs(det) > 1e-12)) { ok = false; continue; }
-            for (int su = -1; su <= 1; su += 2)
-                for (int sv = -1; sv <= 1; sv += 2) {
-                    const double r0 = n3[3], r1 = u[3] + su * b[1], r2 = v[3] + sv * b[3];
-                    double q[3];
-                    q[0] = (r0 * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (r1 * v[2] - u[2] * r2) + n3[2] * (r1 * v[1] - u[1] * r2)) / det;
-                    q[1] = (n3[0] * (r1 * v[2] - u[2] * r2) - r0 * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * r2 - r1 * v[0])) / det;
-                    q[2] = (n3[0] * (u[1] * r2 - r1 * v[1]) - n3[1] * (u[0] * r2 - r1 * v[0]) + r0 * (u[0] * v[1] - u[1] * v[0])) / det;
-                    grow(q);
-                }
-        }
+        std::mutex box_lock;
+        struct Part {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            bool ok = true;
+            void grow(const double* q) { for (int k = 0; k < 3; k++) { if (!(q[k] == q[k])) ok = false; lo[k] = std::min(lo[k], q[k]); hi[k] = std::max(hi[k], q[k]); } }
+        };
+        auto merge = [&](const Part& pt) {
+            std::lock_guard<std::mutex> g(box_lock);
+            ok = ok && pt.ok;
+            for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], pt.lo[k]); hi[k] = std::max(hi[k], pt.hi[k]); }
+        };
+        parallel_ranges(s->n_spheres, [&](size_t lo_, size_t hi_) {
+            Part pt;
+            for (size_t i = lo_; i < hi_; i++) {
+                const double* sp = s->sphere_cxyzr + 4 * i;
+                const double r = std::fabs(sp[3]);
+                const double a[3] = {sp[0] - r, sp[1] - r, sp[2] - r}, b[3] = {sp[0] + r, sp[1] + r, sp[2] + r};
+                pt.grow(a); pt.grow(b);
+            }
+            merge(pt);
+        });
+        parallel_ranges(s->n_rects, [&](size_t lo_, size_t hi_) {
+            Part pt;
+            for (size_t j = lo_; j < hi_; j++) {
+                const double *n3 = s->rect_plane + 4 * j, *u = s->rect_u + 4 * j, *v = s->rect_v + 4 * j, *b = s->rect_bounds + 4 * j;
+                if (!(n3[0] == n3[0]) || !(u[0] == u[0]) || !(v[0] == v[0])) continue;   // NaN normal: never hit
+                // solve [n; u; v] x = rhs by Cramer's rule
+                const double det = n3[0] * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * v[1] - u[1] * v[0]);
+                if (!(std::fabs(det) > 1e-12)) { pt.ok = false; continue; }
+                for (int su = -1; su <= 1; su += 2)
+                    for (int sv = -1; sv <= 1; sv += 2) {
+                        const double r0 = n3[3], r1 = u[3] + su * b[1], r2 = v[3] + sv * b[3];
+                        double q[3];
+                        q[0] = (r0 * (u[1] * v[2] - u[2] * v[1]) - n3[1] * (r1 * v[2] - u[2] * r2) + n3[2] * (r1 * v[1] - u[1] * r2)) / det;
+                        q[1] = (n3[0] * (r1 * v[2] - u[2] * r2) - r0 * (u[0] * v[2] - u[2] * v[0]) + n3[2] * (u[0] * r2 - r1 * v[0])) / det;
+                        q[2] = (n3[0] * (u[1] * r2 - r1 * v[1]) - n3[1] * (u[0] * r2 - r1 * v[0]) + r0 * (u[0] * v[1] - u[1] * v[0])) / det;
+                        pt.grow(q);
+                    }
+            }
+            merge(pt);
+        });
         c->scene_box_valid = ok && lo[0] <= hi[0];
         for (int k = 0; k < 3; k++) { c->scene_lo[k] = lo[k]; c->scene_hi[k] = hi[k]; }
         c->mt_key = 0;   // a new scene invalidates the active micro-tile list
