@@ -334,7 +334,10 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
         comm.barrier()
         td = time.perf_counter()
         if rank == 0:
-            ctx.download(out=frame)
+            if args.e2e_rgb8 and not fp64:
+                rgb8 = ctx.download_rgb8()
+            else:
+                ctx.download(out=frame)
         te = time.perf_counter()
         e2e_events_ms += st["render_ms"] / steps
         for k, v in enumerate((tb - ta, tc - tb, td - tc, te - td)):
@@ -343,6 +346,11 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
     e2e_ms = comm.allmax((time.perf_counter() - t0) * 1e3) / steps
     h2d = int(st["h2d_bytes"])                            # counted by the library from the buffers it copied (last ipt_ctx_set_scene)
     d2h = int(H * W * 3 * np.dtype(out_dtype).itemsize)
+    e2e_result = "fp64 frame" if fp64 else "fp32 frame"
+    if args.e2e_rgb8 and not fp64:
+        d2h, e2e_result = int(H * W * 3), "rgb8 frame (toRgb on the device)"
+        if rank == 0:
+            ctx.download(out=frame)            # the frame check below still looks at the fp32 frame
 
     # ---- the frame that came back (RenderController.cu:58-60: what is returned is what was rendered).  Its hash must be the
     # same for every N (fixed-point accumulation: the frame does not depend on the schedule) and equal the committed one,
@@ -448,7 +456,7 @@ def measure(args, name, wl, comm, steps, warmup, fp64=False, with_cpu_baseline=F
                        "l2": "inputs larger than L2: each wavefront batch streams ray queues of up to 2 x 26 GB (batches of a quarter of the frame's samples, 16 Mi to 256 Mi, 48 B per ray), up to 8 bounces per ray between two queue round trips", "rng": "philox4x32-7 keyed by pixel/sample/bounce"},
             "e2e": {"value": tot_samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "gbounces_per_s": tot_bounces / (e2e_ms * 1e-3) / 1e9,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "result": "fp64 frame" if fp64 else "fp32 frame", "rank0_kernel_ms_events": e2e_events_ms,
+                    "result": e2e_result, "rank0_kernel_ms_events": e2e_events_ms,
                     "rank0_ms": {"set_scene": phase[0], "render_call": phase[1], "wait_for_ranks": phase[2], "download": phase[3]}},
             "gpu_launches": tot_launches,
             "frame_sha256": check["sha256"], "frame_check": check,
@@ -504,6 +512,7 @@ def main():
     ap.add_argument("--fp64", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-config", action="store_true", help="only the headline workload (the default run adds every BASELINE config as per_config)")
+    ap.add_argument("--e2e-rgb8", action="store_true", help="end-to-end leg: download the toRgb bytes (ipt_ctx_download_rgb8, what `tracer` does: a quarter of the fp32 frame's PCIe traffic) instead of the fp32 frame")
     ap.add_argument("--no-rerender", action="store_true", help="N > 1: skip rank 0's single-GPU re-render that the gathered frame is compared with")
     ap.add_argument("--dry-run", action="store_true", help="CPU only (gloo): exercise sharding, handle exchange and reductions without rendering")
     ap.add_argument("--ref-stride", type=int, default=1, help="reference arm: 1/stride of the reference's 484 thread cells are rendered per step (1 = the whole frame)")
