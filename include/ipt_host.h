@@ -29,7 +29,9 @@ const ipt_scene* ipt_host_scene_view(const ipt_host_scene* scene);
 void ipt_host_set_size(ipt_host_scene* scene, uint32_t width, uint32_t height);   /* "spheres.json at 3840x2160" */
 
 /* Builds (or drops) the BVH.  leaf_size 1..16 primitives per leaf; brute_max: scenes with at most this many
- * primitives get no BVH (every ray tests every primitive from shared memory).  Returns node count or <0. */
+ * primitives get no BVH (every ray tests every primitive from shared memory).  Returns node count or <0.
+ * Scenes that get a BVH and consist of small, evenly spread primitives also get the uniform grid of ipt_scene::grid_*
+ * (host/grid.cpp: which scenes qualify; IPT_NO_GRID=1 in the environment switches it off). */
 int ipt_host_build_bvh(ipt_host_scene* scene, uint32_t leaf_size, uint32_t brute_max);
 #define IPT_DEFAULT_LEAF_SIZE 4
 #define IPT_DEFAULT_BRUTE_MAX 192   /* measured crossover brute force vs BVH pipeline on B200: ~200 primitives */
