@@ -988,3 +988,75 @@ def test_next_event_with_many_lights_keeps_the_accumulators_in_range(pyipt, orac
         b, _ = pyipt.render(hs, 4000, 6, seed=5, flags=fp | pyipt.FLAG_NEXT_EVENT | pyipt.FLAG_FLOAT_ACCUM)
         assert np.isfinite(a).all() and a.min() >= 0 and a.max() < 1e4
         assert np.allclose(a, b, rtol=1e-6, atol=1e-9), float(np.abs(a - b).max())
+
+
+def test_acceleration_structures_from_the_caller_are_checked(pyipt, oracle, tmp_path):
+    """ipt_scene is a public struct: a tree or a grid that does not hold together is refused with IPT_ERR_BAD_ARGUMENT instead of
+    being walked (child indices must follow their parent - which also rules out cycles - leaves must stay inside the slot array,
+    cell lists inside the reference array, references inside the slots)."""
+    import sys
+    path = str(tmp_path / "syn5k.json")
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_scene.py"), path, "5000", "64", "36"], check=True)
+    hs = pyipt.HostScene.load(path)
+    good = hs.view.contents
+    assert good.n_bvh_nodes > 100 and good.grid_res[0] > 0
+    c = pyipt.Context(0)
+    L = pyipt.lib()
+
+    def try_scene(mutate):
+        sc = pyipt.Scene.from_buffer_copy(good)
+        keep = mutate(sc)                      # keeps replacement arrays alive
+        rc = L.ipt_ctx_set_scene(c.h, ctypes.byref(sc))
+        del keep
+        return rc, L.ipt_last_error().decode()
+
+    assert try_scene(lambda sc: None)[0] == 0
+
+    def bad_child(sc):
+        nodes = (pyipt.BvhNode * sc.n_bvh_nodes)()
+        ctypes.memmove(nodes, sc.bvh_nodes, ctypes.sizeof(nodes))
+        k = next(i for i in range(1, sc.n_bvh_nodes) if nodes[i].child[0] >= 0)
+        nodes[k].child[0] = 0                  # back edge to the root: a cycle
+        sc.bvh_nodes = ctypes.cast(nodes, ctypes.POINTER(pyipt.BvhNode))
+        return nodes
+    rc, msg = try_scene(bad_child)
+    assert rc == -2 and "parents first" in msg
+
+    def bad_leaf(sc):
+        nodes = (pyipt.BvhNode * sc.n_bvh_nodes)()
+        ctypes.memmove(nodes, sc.bvh_nodes, ctypes.sizeof(nodes))
+        k = next(i for i in range(sc.n_bvh_nodes) if nodes[i].child[1] < 0)
+        nodes[k].child[1] = ~(sc.n_objects - 1); nodes[k].count[1] = 4      # runs past the last slot
+        sc.bvh_nodes = ctypes.cast(nodes, ctypes.POINTER(pyipt.BvhNode))
+        return nodes
+    rc, msg = try_scene(bad_leaf)
+    assert rc == -2 and "leaf" in msg
+
+    def bad_grid_cells(sc):
+        n_cells = sc.grid_res[0] * sc.grid_res[1] * sc.grid_res[2]
+        start = (ctypes.c_uint32 * (n_cells + 1))()
+        ctypes.memmove(start, sc.grid_cell_start, ctypes.sizeof(start))
+        start[n_cells // 2] = sc.n_grid_refs + 7                            # a cell list outside the reference array
+        sc.grid_cell_start = ctypes.cast(start, ctypes.POINTER(ctypes.c_uint32))
+        return start
+    rc, msg = try_scene(bad_grid_cells)
+    assert rc == -2 and "grid" in msg
+
+    def bad_grid_ref(sc):
+        refs = (ctypes.c_uint32 * sc.n_grid_refs)()
+        ctypes.memmove(refs, sc.grid_refs, ctypes.sizeof(refs))
+        refs[sc.n_grid_refs // 3] = sc.n_objects                            # not a slot
+        sc.grid_refs = ctypes.cast(refs, ctypes.POINTER(ctypes.c_uint32))
+        return refs
+    rc, msg = try_scene(bad_grid_ref)
+    assert rc == -2 and "grid" in msg
+
+    def bad_grid_size(sc):
+        sc.grid_res[0] = 5000
+    rc, msg = try_scene(bad_grid_size)
+    assert rc == -2 and "grid" in msg
+    # and the context still renders the good scene afterwards
+    c.set_scene(hs)
+    st = c.render(2, 4, seed=1)
+    assert st["traced_bounces"] > 0 and np.isfinite(c.download(want64=False)).all()
+    c.close()
