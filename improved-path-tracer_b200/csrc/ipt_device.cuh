@@ -353,11 +353,10 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
 //      axis-aligned rectangle   a = {p_K, c_I, c_J, h_I} b = {kind 1+K, obj|RECT, h_J, -}     (as in FastScene)
 //      general rectangle        a = {-, -, -, -}         b = {kind 4, obj|RECT, -, -}          -> generic 64-B slot
 //  Ties in t across primitives are resolved by object index explicitly (traversal order is arbitrary).
-__device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t slot, const V3<float>& o, const V3<float>& d,
-                                           const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best, uint32_t& n_sphere_tests)
+// The test itself, on a record that is already in registers (`slot` is what a hit reports).
+__device__ __forceinline__ void test_brec(const SceneView<float>& sc, const float4 a, const float4 b, uint32_t slot, const V3<float>& o, const V3<float>& d,
+                                          const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best, uint32_t& n_sphere_tests)
 {
-    float4 a, b;
-    ldg256(sc.bslot + 2 * (size_t)slot, a, b);
     const uint32_t kind = __float_as_uint(b.x), obj = __float_as_uint(b.y);
     n_sphere_tests += kind == 0 ? 1u : 0u;          // work counters of ipt_stats (the flops model of bench.py)
     float t;
@@ -387,6 +386,13 @@ __device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t 
     best.t = hit ? t : best.t;
     best.slot = hit ? slot : best.slot;
     best.obj = hit ? obj : best.obj;
+}
+__device__ __forceinline__ void test_bslot(const SceneView<float>& sc, uint32_t slot, const V3<float>& o, const V3<float>& d,
+                                           const V3<float>& inv, uint32_t self, bool onSurf, Hit<float>& best, uint32_t& n_sphere_tests)
+{
+    float4 a, b;
+    ldg256(sc.bslot + 2 * (size_t)slot, a, b);
+    test_brec(sc, a, b, slot, o, d, inv, self, onSurf, best, n_sphere_tests);
 }
 
 __device__ __forceinline__ Hit<float> nearest_bvh_f32(const SceneView<float>& sc, const float4* top, uint32_t n_top, const V3<float> o,

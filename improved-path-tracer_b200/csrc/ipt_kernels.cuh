@@ -586,6 +586,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
 //  * a new ray first tests the "big" primitives (walls, large lights: up to 64 slots kept in the kernel parameters), then is
 //    clipped against the grid's box;
 //  * per cell: one 8-byte load {first reference, count}; the references are slots, tested one per lane and iteration;
+//  * the loads are taken off the critical path.  The capture of the first version (profiles/r02_ncu_grid_final.txt and its source
+//    page) had a third of all stall samples on three dependent loads inside one step: the cell entry (8.6 %), the reference
+//    (11.2 %) and the record it points at (14.0 %).  Now the walk runs one cell ahead of the cell being opened - a cell step reads
+//    the entry requested by the step before it and requests the entry of the cell after (speculatively: a ray that ends in this
+//    cell has asked for one entry too many) - and the reference a primitive step needs was requested when the cell was opened or
+//    by the primitive step before it; what is left exposed is the record load (profiles/r02_ncu_grid_ahead.txt);
 //  * a ray ends when the exit distance of the cell it has just finished is not below its nearest hit (a primitive that
 //    overlaps several cells may report a hit beyond the current cell: it stays a candidate and the walk goes on), or when
 //    it leaves the grid;
@@ -613,16 +619,37 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
     bool exhausted = false;
     uint32_t my_traced = 0;
     uint32_t w_cells = 0, w_prims = 0, w_sph = 0, w_occupied = 0;        // work counters of ipt_stats
-    bool has = false, marching = false;
+    bool has = false, marching = false;                                   // marching: a requested cell entry is waiting to be opened
+    bool ahead_in = false;                                                // the cell after it lies inside the grid
     uint32_t idx = 0, self = NO_OBJECT;
     bool onSurf = false;
     V3<float> o = mk<float>(0, 0, 0), d = o, inv = o;
-    V3<float> fi = o, tmx = o, A = o, B = o;                              // cell coordinate, next boundary per axis, t = fi * A + B
+    V3<float> fi = o, tmx = o, A = o, B = o;                              // the walk (one cell ahead): cell coordinate, next boundary per axis, t = fi * A + B
     uint32_t cell = 0;
+    uint2 ce_nx = make_uint2(0u, 0u);                                     // entry of the cell to open next (in flight)
+    float tex_nx = 0.f;                                                   // where the ray leaves that cell
+    uint32_t slot_nx = 0;                                                 // the reference at pr_cur (in flight since the cell was opened / the primitive step before)
     uint32_t pr_cur = 0, pr_end = 0;                                      // references of the current cell still to test
     float t_exit = 0.f;                                                   // where the ray leaves the current cell
     Hit<float> best;
     best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
+
+    // The walk's cell becomes the one to open next - its entry is requested now, read by the next cell step - and the walk moves on.
+    auto advance = [&]() {
+        ce_nx = __ldg(p.grid_cells + cell);
+        tex_nx = fminf(tmx.x, fminf(tmx.y, tmx.z));
+        const bool sx = tmx.x <= tmx.y && tmx.x <= tmx.z, sy = !sx && tmx.y <= tmx.z;
+        const float a_k = sx ? A.x : (sy ? A.y : A.z);                      // its sign is the direction of travel along the axis
+        const float stepf = a_k > 0.f ? 1.f : -1.f;
+        const uint32_t stride = sx ? 1u : (sy ? rx : rxy);
+        const float f = (sx ? fi.x : (sy ? fi.y : fi.z)) + stepf;
+        const float lim = (float)(sx ? p.grid.res[0] : (sy ? p.grid.res[1] : p.grid.res[2]));
+        ahead_in = f >= 0.f && f < lim;
+        const float nt = fmaf(f, a_k, sx ? B.x : (sy ? B.y : B.z));
+        fi.x = sx ? f : fi.x; fi.y = sy ? f : fi.y; fi.z = (!sx && !sy) ? f : fi.z;
+        tmx.x = sx ? nt : tmx.x; tmx.y = sy ? nt : tmx.y; tmx.z = (!sx && !sy) ? nt : tmx.z;
+        cell = a_k > 0.f ? cell + stride : cell - stride;
+    };
 
     for (;;) {
         if (has && !marching && pr_cur >= pr_end) {                       // finished (or never entered the grid)
@@ -647,7 +674,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
                     best.t = (float)IPT_INF; best.slot = NO_OBJECT; best.obj = NO_OBJECT;
                     has = true; marching = false; pr_cur = pr_end = 0;
                     my_traced++;
-                    for (uint32_t k = 0; k < p.grid.n_big; k++) { test_bslot(sc, p.grid.big[k], o, d, inv, self, onSurf, best, w_sph); w_prims++; }
                     // the grid's box: components below 1e-18 become +-1e-18, so no inf - inf arises (as the tree traversals do)
                     const V3<float> bi = mk<float>(rcp_fast(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), rcp_fast(fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
                                                    rcp_fast(fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
@@ -655,9 +681,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
                     const float ay = (p.grid.lo[1] - o.y) * bi.y, by = (p.grid.hi[1] - o.y) * bi.y;
                     const float az = (p.grid.lo[2] - o.z) * bi.z, bz = (p.grid.hi[2] - o.z) * bi.z;
                     const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-                    const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t));
-                    if (t0 <= t1) {
-                        // the cell of the entry point (clamped: an entry point on the far faces rounds to res)
+                    const float t1g = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+                    // the entry cell (clamped: an entry point on the far faces rounds to res); where the ray enters the grid does not
+                    // depend on the big primitives, so the first cell entry travels while they are tested
+                    bool enters = t0 <= t1g;
+                    if (enters) {
                         const float ex = fmaf(d.x, t0, o.x), ey = fmaf(d.y, t0, o.y), ez = fmaf(d.z, t0, o.z);
                         fi.x = fminf(fmaxf(floorf((ex - p.grid.lo[0]) * p.grid.inv_cs[0]), 0.f), (float)(p.grid.res[0] - 1u));
                         fi.y = fminf(fmaxf(floorf((ey - p.grid.lo[1]) * p.grid.inv_cs[1]), 0.f), (float)(p.grid.res[1] - 1u));
@@ -669,8 +697,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
                         B = mk<float>(fmaf(p.grid.lo[0] - o.x, bi.x, bi.x > 0.f ? A.x : 0.f), fmaf(p.grid.lo[1] - o.y, bi.y, bi.y > 0.f ? A.y : 0.f),
                                       fmaf(p.grid.lo[2] - o.z, bi.z, bi.z > 0.f ? A.z : 0.f));
                         tmx = mk<float>(fmaf(fi.x, A.x, B.x), fmaf(fi.y, A.y, B.y), fmaf(fi.z, A.z, B.z));
-                        marching = true;
+                        advance();
                     }
+                    for (uint32_t k = 0; k < p.grid.n_big; k++) { test_bslot(sc, p.grid.big[k], o, d, inv, self, onSurf, best, w_sph); w_prims++; }
+                    marching = enters && t0 <= best.t;                       // a hit on a big primitive before the grid's box: nothing to walk
                 }
             }
         }
@@ -678,8 +708,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
             if (exhausted) break;
             continue;
         }
-        // ---- cell steps: leave the finished cell (if any) and open the next one.  Up to GRID_BURST steps before the warp looks
-        // at its finished and idle lanes again; the burst ends early when few lanes still march and others hold primitives.
+        // ---- cell steps: open the cell whose entry was requested a step ago, request the next one.  Up to GRID_BURST steps before the
+        // warp looks at its finished and idle lanes again; the burst ends early when few lanes still march and others hold primitives.
 #pragma unroll 1
         for (int it = 0; it < GRID_BURST; it++) {
             const bool want_cell = has && marching && pr_cur >= pr_end;
@@ -687,24 +717,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
             if (m_cell == 0) break;
             if ((uint32_t)__popc(m_cell) < p.descend_min && __any_sync(0xffffffffu, has && pr_cur < pr_end)) break;
             if (want_cell) {
-                const uint2 ce = __ldg(p.grid_cells + cell);
-                t_exit = fminf(tmx.x, fminf(tmx.y, tmx.z));
+                const uint2 ce = ce_nx;
+                t_exit = tex_nx;
                 pr_cur = ce.x; pr_end = ce.x + ce.y;
                 w_cells++; w_occupied += ce.y ? 1u : 0u;
-                // step now: the state is cheaper to keep one cell ahead than to carry "which axis" along
-                const bool sx = tmx.x <= tmx.y && tmx.x <= tmx.z, sy = !sx && tmx.y <= tmx.z;
-                const float a_k = sx ? A.x : (sy ? A.y : A.z);              // its sign is the direction of travel along the axis
-                const float stepf = a_k > 0.f ? 1.f : -1.f;
-                const uint32_t stride = sx ? 1u : (sy ? rx : rxy);
-                const float f = (sx ? fi.x : (sy ? fi.y : fi.z)) + stepf;
-                const float lim = (float)(sx ? p.grid.res[0] : (sy ? p.grid.res[1] : p.grid.res[2]));
-                const bool inside = f >= 0.f && f < lim;
-                const float nt = fmaf(f, a_k, sx ? B.x : (sy ? B.y : B.z));
-                fi.x = sx ? f : fi.x; fi.y = sy ? f : fi.y; fi.z = (!sx && !sy) ? f : fi.z;
-                tmx.x = sx ? nt : tmx.x; tmx.y = sy ? nt : tmx.y; tmx.z = (!sx && !sy) ? nt : tmx.z;
-                cell = a_k > 0.f ? cell + stride : cell - stride;
+                if (ce.y) slot_nx = __ldg(p.grid_refs + ce.x);
                 // the walk ends with this cell when the next one lies outside, or (empty cell) when the nearest hit is before its exit
-                if (!inside || (ce.y == 0u && best.t <= t_exit)) marching = false;
+                marching = ahead_in && !(ce.y == 0u && best.t <= t_exit);
+                if (ahead_in) advance();
             }
         }
         // ---- primitive steps: one reference per lane and step
@@ -716,9 +736,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
             // few lanes hold primitives: leave them waiting only if enough lanes march for a cell step to run (progress either way)
             if ((uint32_t)__popc(m_prim) < p.leaf_min && (uint32_t)__popc(__ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end)) >= p.descend_min) break;
             if (want_prim) {
-                const uint32_t slot = __ldg(p.grid_refs + pr_cur);
+                const uint32_t slot = slot_nx;
+                float4 a, b;
+                ldg256(sc.bslot + 2 * (size_t)slot, a, b);
                 pr_cur++;
-                test_bslot(sc, slot, o, d, inv, self, onSurf, best, w_sph);
+                if (pr_cur < pr_end) slot_nx = __ldg(p.grid_refs + pr_cur);
+                test_brec(sc, a, b, slot, o, d, inv, self, onSurf, best, w_sph);
                 w_prims++;
                 // the cell is done: stop if the nearest hit lies before its exit
                 if (pr_cur >= pr_end && best.t <= t_exit) marching = false;
