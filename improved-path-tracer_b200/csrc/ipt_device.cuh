@@ -43,7 +43,10 @@ template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { retur
 template <typename R> __device__ __forceinline__ V3<R> mul(V3<R> a, V3<R> b) { return mk<R>(a.x * b.x, a.y * b.y, a.z * b.z); }
 template <typename R> __device__ __forceinline__ V3<R> xyz(const R4<R>& q) { return mk<R>(q.x, q.y, q.z); }
 
-__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+// MUFU.RSQ alone: rsqrtf() wraps the same instruction in a denormal guard (FSETP + two predicated FMUL, twice per bounce in
+// the typed-list kernel's capture) that no argument here can need - the squared lengths are >= 3 * 2^-48 (s24 draws) or ~r^2;
+// results for normal arguments are bit-identical (the committed frame hashes did not move).
+__device__ __forceinline__ float rsqrt_(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }  // Vec3.hpp:48-51: v * (1/sqrt(v.v))
 __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -89,6 +92,10 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
 //   u23(x) in (0,1) : (2k+1)/2^24, k = x>>9 — the uniform of the stochastic lobe pick (AObject.hpp:94,127)
 template <typename R> __device__ __forceinline__ R s24(uint32_t x) { return ((R)((int)(x >> 8) - 8388608) + (R)0.5) * (R)(1.0 / 8388608.0); }
 template <typename R> __device__ __forceinline__ R u23(uint32_t x) { return ((R)(x >> 9) + (R)0.5) * (R)(1.0 / 8388608.0); }
+// fp32: (k + 0.5) * 2^-23 = fma(k, 2^-23, 2^-24) - every intermediate and the result are exactly representable (|k| <= 2^23), so
+// the one rounding of the FMA returns the same number as the add and the multiply above, in one instruction instead of two
+template <> __device__ __forceinline__ float s24<float>(uint32_t x) { return fmaf((float)((int)(x >> 8) - 8388608), 1.f / 8388608.f, 1.f / 16777216.f); }
+template <> __device__ __forceinline__ float u23<float>(uint32_t x) { return fmaf((float)(x >> 9), 1.f / 8388608.f, 1.f / 16777216.f); }
 
 // ---------------------------------------------------------------------------------------------- ray record
 template <typename R> struct Ray {
