@@ -1133,6 +1133,12 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
         off = noff;
         if (off == CHUNK_RAYS) { chunk = chunk_next; chunk_next = __shfl_sync(0xffffffffu, pending, 0); pending = claim_issue(); off = 0; }
         bool has0 = live;
+        // The meta word taken apart for the bounces made in registers and put together again for the queue: the sample and lane
+        // bits never change, the depth counts up, 'starts on a surface' follows the last hit (the masks and shifts on the packed
+        // word were 5 of ~400 warp instructions per bounce).
+        const uint32_t meta_keep = r.meta & 0x0FFFF300u, sample = (r.meta >> 12) & 0xFFFFu, ctr_lane = r.meta & 0x300u;
+        uint32_t depth = r.meta & 0xFFu;
+        bool on_surf = (r.meta & META_ONSURF) != 0;
         for (uint32_t k = 0; k < nk; k++) {
             // (no vote on "has every ray of this slice ended": a closed room loses under 1 % of its rays per bounce, a leaky scene
             // gets a small nk from fast_schedule; the vote, its branch and the popc were 5 of ~410 warp instructions per bounce)
@@ -1142,8 +1148,8 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
             Ray<float> o1;
             if (in) {
                 my_traced++;
-                const uint32_t dk = FIRST ? k : (r.meta & 0xFFu);
-                const FastHit h = nearest_fast<SHAPE>(sc, r.o, r.d, r.self, (r.meta & META_ONSURF) != 0);
+                const uint32_t dk = FIRST ? k : depth;
+                const FastHit h = nearest_fast<SHAPE>(sc, r.o, r.d, r.self, on_surf);
                 if (h.code != NO_OBJECT) {
                     const uint32_t obj = fast_hit_object(sc, h.code) & ~RECT_BIT;
                     const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
@@ -1151,28 +1157,26 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                     V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
                     const bool go = dk + 1 < p.maxDepth && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);   // no probes in these queues
                     if (go) {
-                        const uint32_t lane_id = (r.meta >> 8) & 3u, sample = (r.meta >> 12) & 0xFFFFu;
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
-                        const uint4 rnd = philox4x32(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG, p.keys);
+                        const uint4 rnd = philox4x32(r.pixel, sample, ctr_lane | dk, CTR_TAG, p.keys);
                         const Spawn<float> sp = scatter_fast<(SHAPE > 0)>(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
                         bool alive = sp.has0;
                         if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
-                            const uint4 rr = philox4x32(r.pixel, sample, (lane_id << 8) | dk, CTR_TAG + 1u, p.keys);
+                            const uint4 rr = philox4x32(r.pixel, sample, ctr_lane | dk, CTR_TAG + 1u, p.keys);
                             if (u23<float>(rr.x) >= q) alive = false;
                             else nthr = nthr * (1.f / q);
                         }
                         const bool onS = (h.code >> 28) != 0 || fabsf(dot(r.d, r.d) - 1.f) < 1e-3f;
-                        const uint32_t mcommon = (r.meta & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (dk + 1);
                         if (FIRST && k < 2) {
                             has1 = sp.has1;
                             o1.o = P; o1.d = sp.d1; o1.thr = nthr * sp.w1; o1.pixel = r.pixel; o1.self = h.code;
-                            o1.meta = mcommon | (k == 0 ? (0x200u | META_PROBE) : 0x100u);
+                            o1.meta = (meta_keep & 0x0FFFF000u) | (onS ? META_ONSURF : 0u) | (dk + 1) | (k == 0 ? (0x200u | META_PROBE) : 0x100u);
                         }
                         has0 = alive;
                         r.o = P; r.d = sp.d0; r.thr = nthr * sp.w0; r.self = h.code;
-                        r.meta = mcommon | (r.meta & 0x300u);
-                        if (sc.any_unknown && sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; r.meta &= ~META_ONSURF; }
+                        depth = dk + 1; on_surf = onS;
+                        if (sc.any_unknown && sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; on_surf = false; }
                     }
                 }
             }
@@ -1193,6 +1197,7 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
             }
         }
         const uint32_t m0b = __ballot_sync(0xffffffffu, has0);
+        r.meta = meta_keep | (on_surf ? META_ONSURF : 0u) | depth;
         if (m0b) emit(has0, m0b, r);
     }
     // the unused tail of the last block: dead records (skipped by the next pass)
