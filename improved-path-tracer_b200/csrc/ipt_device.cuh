@@ -467,6 +467,11 @@ template <typename R> __device__ __forceinline__ V3<R> diffuse_dir(V3<R> n, uint
     return dot(v, n) < (R)0 ? -v : v;
 }
 
+// "some component is not zero" (+0 and -0 are zero, NaN is not): for fp32 one OR of the three bit patterns and one masked test
+// instead of three compares
+__device__ __forceinline__ bool any_nonzero(V3<float> v) { return ((__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z)) & 0x7FFFFFFFu) != 0u; }
+__device__ __forceinline__ bool any_nonzero(V3<double> v) { return v.x != 0.0 || v.y != 0.0 || v.z != 0.0; }
+
 // AObject.hpp:47-60: eta = 1/1.5 in both directions, not normalised; returns false on total internal reflection.
 template <typename R> __device__ __forceinline__ bool refract_dir(V3<R> in, V3<R> n, V3<R>& out)
 {
@@ -476,7 +481,7 @@ template <typename R> __device__ __forceinline__ bool refract_dir(V3<R> in, V3<R
     if (sin2 > (R)1) return false;
     const R cosT = sqrt_((R)1 - sin2);
     out = in * index + n * (index * cosI - cosT);
-    return !(out.x == (R)0 && out.y == (R)0 && out.z == (R)0);   // AObject.hpp:117 compares the result with Vec3()
+    return any_nonzero(out);                                     // AObject.hpp:117 compares the result with Vec3()
 }
 
 // Result of shading one hit: up to two continuation rays (the reference's RayData, RayData.hpp:12-28).
@@ -548,10 +553,10 @@ struct FastScene {
     const float4* sph; const uint32_t* sph_obj; uint32_t n_sph;
     const float4* axs;                       // the three axis lists back to back; list K starts at record ax0[K]
     uint32_t ax0_x, ax0_y, ax0_z, n_x, n_y, n_z;
+    uint32_t g_x, g_y, g_z;                  // leading records of each list that share one plane (fast_axis_group), 0 = none
     const R4<float>* gen; const uint32_t* gen_obj; uint32_t n_gen;
     const float4* mat;
     bool box_pairs;                          // see fast_axis_pair
-    bool any_unknown;                        // some object has a reflection value outside 0..2 (the 'teleport' ray of scatter<R>)
     float blo_x, blo_y, blo_z, bhi_x, bhi_y, bhi_z;   // plane coordinates of the lower / upper wall per axis (kernel parameters:
                                              // the 'origin between the walls' test compares against the constant bank)
 };
@@ -563,15 +568,16 @@ __host__ __device__ inline uint32_t fast_blob_words(uint32_t n_sph, uint32_t nx,
 struct FastHeader {
     uint32_t n_sph, n_x, n_y, n_z, n_gen, n_obj;
     uint32_t box_pairs;     // box room whose two rectangles per axis are stored lower plane first (fast_axis_pair)
-    uint32_t any_unknown;   // some object has an unknown reflection value
+    uint32_t any_unknown;   // some object has an unknown reflection value: the typed-list kernel is not used (the generic one knows the case)
     float box_lo[3], box_hi[3];   // their plane coordinates
+    uint32_t group[3];            // per axis list: its first group[K] records lie on one plane (0: no such group)
     uint32_t off_sphobj, off_axs, off_gen, off_genobj, off_mat;   // 16-byte word offsets of the lists inside the blob
 };
 __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen, uint32_t n_obj)
 {
     FastHeader h;
     h.n_sph = n_sph; h.n_x = nx; h.n_y = ny; h.n_z = nz; h.n_gen = n_gen; h.n_obj = n_obj; h.box_pairs = 0; h.any_unknown = 1;
-    for (int k = 0; k < 3; k++) { h.box_lo[k] = 0.f; h.box_hi[k] = 0.f; }
+    for (int k = 0; k < 3; k++) { h.box_lo[k] = 0.f; h.box_hi[k] = 0.f; h.group[k] = 0; }
     h.off_sphobj = 2 + n_sph;
     h.off_axs = h.off_sphobj + (n_sph + 3) / 4;
     h.off_gen = h.off_axs + 2 * (nx + ny + nz);
@@ -582,12 +588,13 @@ __host__ __device__ inline FastHeader fast_header(uint32_t n_sph, uint32_t nx, u
 __device__ __forceinline__ FastScene fast_view(const uint4* blob, const FastHeader& hd)
 {
     FastScene f;
-    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0; f.any_unknown = hd.any_unknown != 0;
+    f.n_sph = hd.n_sph; f.n_x = hd.n_x; f.n_y = hd.n_y; f.n_z = hd.n_z; f.n_gen = hd.n_gen; f.box_pairs = hd.box_pairs != 0;
     f.blo_x = hd.box_lo[0]; f.blo_y = hd.box_lo[1]; f.blo_z = hd.box_lo[2]; f.bhi_x = hd.box_hi[0]; f.bhi_y = hd.box_hi[1]; f.bhi_z = hd.box_hi[2];
     f.sph = reinterpret_cast<const float4*>(blob + 2);
     f.sph_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_sphobj);
     f.axs = reinterpret_cast<const float4*>(blob + hd.off_axs);
     f.ax0_x = 0; f.ax0_y = hd.n_x; f.ax0_z = hd.n_x + hd.n_y;
+    f.g_x = hd.group[0]; f.g_y = hd.group[1]; f.g_z = hd.group[2];
     f.gen = reinterpret_cast<const R4<float>*>(blob + hd.off_gen);
     f.gen_obj = reinterpret_cast<const uint32_t*>(blob + hd.off_genobj);
     f.mat = reinterpret_cast<const float4*>(blob + hd.off_mat);
@@ -619,9 +626,34 @@ __device__ __forceinline__ void fast_axis_list(const float4* __restrict__ axs, u
             const float ei = fabsf(fmaf(di, t, oi) - a.y), ej = fabsf(fmaf(dj, t, oj) - a.z);
             const bool hit = t > (float)IPT_MARGIN && t < best.t && ei <= a.w && ej <= hj;
             best.t = hit ? t : best.t;
-            best.code = hit ? (((uint32_t)(K + 1) << 28) | (s + u)) : best.code;
+            best.code = hit ? (((uint32_t)(K + 1) << 28) + (s + u)) : best.code;   // '+', not '|': one predicated add with an immediate per record
         }
     }
+}
+
+// The records [first, first + g) of a list lie on ONE plane: t and the hit point are computed once, a record costs its two edge
+// tests.  Walked backwards with an unconditional overwrite, so the lowest record that contains the point wins - what the loop
+// above does for equal t (after the first hit `t < best.t` is false for the rest of the plane); same arithmetic per record.
+template <int K>
+__device__ __forceinline__ void fast_axis_group(const float4* __restrict__ axs, uint32_t first, uint32_t g, const V3<float>& o,
+                                                const V3<float>& d, float inv_dk, FastHit& best)
+{
+    constexpr int I = K == 0 ? 1 : 0, J = K == 2 ? 1 : 2;
+    const float ok = comp<K>(o), oi = comp<I>(o), oj = comp<J>(o), di = comp<I>(d), dj = comp<J>(d);
+    const float t = (axs[2 * first].x - ok) * inv_dk;
+    const float pi = fmaf(di, t, oi), pj = fmaf(dj, t, oj);
+    uint32_t found = NO_OBJECT;
+    const float4* rec = axs + 2 * (first + g);
+#pragma unroll 4
+    for (uint32_t s = first + g; s-- > first;) {
+        rec -= 2;
+        const float4 a = rec[0];
+        const float hj = rec[1].x;
+        found = (fabsf(pi - a.y) <= a.w && fabsf(pj - a.z) <= hj) ? s : found;
+    }
+    const bool hit = t > (float)IPT_MARGIN && t < best.t && found != NO_OBJECT;
+    best.t = hit ? t : best.t;
+    best.code = hit ? (((uint32_t)(K + 1) << 28) + found) : best.code;
 }
 
 // The same for a list whose position and (even) length are compile-time constants: straight-line code, record loads
@@ -680,7 +712,8 @@ __device__ __forceinline__ void fast_sphere(const float4 sp, uint32_t s, uint32_
     best.code = hit ? s : best.code;
 }
 
-// SHAPE: 0 = list lengths at run time (loops); k = 1..5 = "box room": exactly two rectangles per axis list (a closed
+// SHAPE: 0 = list lengths at run time (loops); -1 = the same with a coplanar group in front of some list (fast_axis_group);
+// k = 1..5 = "box room": exactly two rectangles per axis list (a closed
 // axis-aligned box, padded records included), no general rectangles and k-1 spheres.  Those lengths being compile-time
 // constants, the whole scan is straight-line code (spheres.json and every Cornell-box-like scene).
 __host__ __device__ inline int fast_shape(uint32_t n_sph, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t n_gen)
@@ -712,9 +745,20 @@ __device__ __forceinline__ FastHit nearest_fast(const FastScene& f, const V3<flo
     }
 #pragma unroll 2
     for (uint32_t s = 0; s < f.n_sph; s++) fast_sphere(f.sph[s], s, self_sphere, o, d, best);
-    fast_axis_list<0>(f.axs, f.ax0_x, f.n_x, o, d, rcp_fast(d.x), best);
-    fast_axis_list<1>(f.axs, f.ax0_y, f.n_y, o, d, rcp_fast(d.y), best);
-    fast_axis_list<2>(f.axs, f.ax0_z, f.n_z, o, d, rcp_fast(d.z), best);
+    if (SHAPE < 0) {    // some list starts with a coplanar group (its own instantiation: carried by every list scene, the extra
+                        // branches and loop bounds cost mirrors.json 5 %)
+        const float ix = rcp_fast(d.x), iy = rcp_fast(d.y), iz = rcp_fast(d.z);
+        if (f.g_x) fast_axis_group<0>(f.axs, f.ax0_x, f.g_x, o, d, ix, best);
+        fast_axis_list<0>(f.axs, f.ax0_x + f.g_x, f.n_x - f.g_x, o, d, ix, best);
+        if (f.g_y) fast_axis_group<1>(f.axs, f.ax0_y, f.g_y, o, d, iy, best);
+        fast_axis_list<1>(f.axs, f.ax0_y + f.g_y, f.n_y - f.g_y, o, d, iy, best);
+        if (f.g_z) fast_axis_group<2>(f.axs, f.ax0_z, f.g_z, o, d, iz, best);
+        fast_axis_list<2>(f.axs, f.ax0_z + f.g_z, f.n_z - f.g_z, o, d, iz, best);
+    } else {
+        fast_axis_list<0>(f.axs, f.ax0_x, f.n_x, o, d, rcp_fast(d.x), best);
+        fast_axis_list<1>(f.axs, f.ax0_y, f.n_y, o, d, rcp_fast(d.y), best);
+        fast_axis_list<2>(f.axs, f.ax0_z, f.n_z, o, d, rcp_fast(d.z), best);
+    }
     for (uint32_t s = 0; s < f.n_gen; s++) {
         Hit<float> h;
         h.t = best.t; h.obj = NO_OBJECT; h.slot = NO_OBJECT;     // obj = max: strict '<' within this (ordered) list
@@ -782,9 +826,9 @@ __device__ __forceinline__ Spawn<float> scatter_fast(const FastScene& f, uint32_
     s.d0.x = pickSpec ? spec.x : (pickRefr ? refr.x : diff.x);
     s.d0.y = pickSpec ? spec.y : (pickRefr ? refr.y : diff.y);
     s.d0.z = pickSpec ? spec.z : (pickRefr ? refr.z : diff.z);
-    s.teleport = f.any_unknown && (reflection < 0 || reflection > 2);         // unknown material: see scatter<R> (uniform flag: no scene shipped has one)
-    s.has0 = !s.teleport || depth >= 2;
-    if (s.teleport) { s.d0.x = 0.f; s.d0.y = 0.f; s.d0.z = 0.f; }
+    // no unknown materials here (the 'teleport' ray of scatter<R>): a scene that has one is rendered by the generic kernel
+    // (FastHeader::any_unknown, ipt_render.cu) - as a flag inside this kernel the case cost eight selects per bounce
+    s.teleport = false; s.has0 = true;
     s.has1 = early && (isSpec || (isRefr && refr_ok));                        // AObject.hpp:91-94, :122-125
     s.w0 = s.has1 ? (isSpec ? 0.92f : 0.95f) : 1.f;
     s.w1 = isSpec ? 0.08f : 0.05f;

@@ -1039,7 +1039,7 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 #endif
 template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? IPT_FIRST_CTAS : IPT_FAST_CTAS; };
 
-template <bool FIRST, int SHAPE = 0>
+template <bool FIRST, int SHAPE = 0, bool RR = false>
 __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS) k_bounce_fast(const __grid_constant__ KParams<float> p)
 {
     constexpr int BLOCK_THREADS = FastCfg<FIRST>::THREADS;   // shadows the file-wide constant inside this kernel
@@ -1155,13 +1155,14 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                     const float4 m0 = sc.mat[2 * obj], m1 = sc.mat[2 * obj + 1];
                     if (m1.w != 0.f) accumulate_fast(p, r.pixel, mul(r.thr, mk<float>(m1.x, m1.y, m1.z)));
                     V3<float> nthr = mul(r.thr, mk<float>(m0.x, m0.y, m0.z));
-                    const bool go = dk + 1 < p.maxDepth && (nthr.x != 0.f || nthr.y != 0.f || nthr.z != 0.f);   // no probes in these queues
+                    const bool go = dk + 1 < p.maxDepth && any_nonzero(nthr);   // no probes in these queues
                     if (go) {
                         const V3<float> P = fast_hit_point(sc, h.code, r.o, r.d, h.t);
                         const uint4 rnd = philox4x32(r.pixel, sample, ctr_lane | dk, CTR_TAG, p.keys);
                         const Spawn<float> sp = scatter_fast<(SHAPE > 0)>(sc, h.code, (int)m0.w, P, r.d, FIRST ? dk : 2u, rnd);
                         bool alive = sp.has0;
-                        if ((p.flags & 0x8u) && dk >= 3 && alive) {   // IPT_FLAG_RUSSIAN_ROULETTE (extension)
+                        if (RR && dk >= 3 && alive) {                 // IPT_FLAG_RUSSIAN_ROULETTE (extension): its own instantiations - as a
+                                                                      // flag tested in the loop it cost 3 instructions per bounce and 8 registers
                             const float q = fminf(1.f, fmaxf(0.05f, fmaxf(nthr.x, fmaxf(nthr.y, nthr.z))));
                             const uint4 rr = philox4x32(r.pixel, sample, ctr_lane | dk, CTR_TAG + 1u, p.keys);
                             if (u23<float>(rr.x) >= q) alive = false;
@@ -1176,7 +1177,6 @@ __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS)
                         has0 = alive;
                         r.o = P; r.d = sp.d0; r.thr = nthr * sp.w0; r.self = h.code;
                         depth = dk + 1; on_surf = onS;
-                        if (sc.any_unknown && sp.teleport) { r.o = mk<float>(0.f, 0.f, 0.f); r.self = NO_OBJECT; on_surf = false; }
                     }
                 }
             }

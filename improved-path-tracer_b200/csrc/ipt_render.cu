@@ -228,8 +228,9 @@ static size_t frame64_offset(size_t px) { return (px * 12 + 255) & ~(size_t)255;
 
 // fp32 brute-force layout (see FastScene in ipt_device.cuh): spheres, axis-aligned rectangles per normal axis,
 // general rectangles, materials.  Built in fp64 from the flattened scene, rounded once to fp32.
-static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
+static std::vector<uint32_t> build_fast_blob(const ipt_scene* s, uint32_t group[3])
 {
+    group[0] = group[1] = group[2] = 0;
     struct AxRect { float pk, cI, cJ, hI, hJ; uint32_t obj; };
     std::vector<AxRect> ax[3];
     std::vector<uint32_t> gen;
@@ -263,9 +264,24 @@ static std::vector<uint32_t> build_fast_blob(const ipt_scene* s)
         if (ax[k][1].pk < ax[k][0].pk) std::swap(ax[k][0], ax[k][1]);
         box_pairs = ax[k][0].pk < ax[k][1].pk;
     }
-    // the axis lists are padded to an even length with a record that can never be hit (their device loops step by 2)
+    // Coplanar groups (maze.json: 23 of its 25 z rectangles lie on z = 200): the largest set of rectangles of a list that share
+    // their plane goes to the front of the list, in its JSON order; the kernel computes t and the hit point of that plane once
+    // and only the edge tests per rectangle (fast_axis_group).  Rectangles on different planes of one axis never tie in t, so
+    // moving the group in front of the others changes no answer (Renderer.cu:235's tie rule concerns equal t).  IPT_NO_GROUP=1: A/B.
+    for (int k = 0; k < 3 && !box_pairs && !std::getenv("IPT_NO_GROUP"); k++) {
+        size_t best_n = 0; float best_p = 0.f;
+        for (const AxRect& r : ax[k]) {
+            size_t n_same = 0;
+            for (const AxRect& q : ax[k]) n_same += q.pk == r.pk;
+            if (n_same > best_n) { best_n = n_same; best_p = r.pk; }
+        }
+        if (best_n < 4) continue;
+        std::stable_partition(ax[k].begin(), ax[k].end(), [&](const AxRect& r) { return r.pk == best_p; });
+        group[k] = (uint32_t)best_n;
+    }
+    // the part of an axis list that the two-records-per-trip loop walks is padded to an even length with a record that can never be hit
     for (int k = 0; k < 3; k++)
-        if (ax[k].size() & 1) ax[k].push_back(AxRect{3.0e38f, 0.f, 0.f, -1.f, -1.f, NO_OBJECT});
+        if ((ax[k].size() - group[k]) & 1) ax[k].push_back(AxRect{3.0e38f, 0.f, 0.f, -1.f, -1.f, NO_OBJECT});
     const uint32_t ns_real = s->n_spheres, ns = ns_real, ng = (uint32_t)gen.size(), no = s->n_objects;
     const uint32_t words = fast_blob_words(ns, (uint32_t)ax[0].size(), (uint32_t)ax[1].size(), (uint32_t)ax[2].size(), ng, no);
     std::vector<uint32_t> blob((size_t)words * 4, 0u);
@@ -478,7 +494,8 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
     });
     if (bad.load()) { set_err(bad.load()); return IPT_ERR_BAD_ARGUMENT; }
     std::vector<uint32_t> blob;
-    if (!bvh) { blob = build_fast_blob(s); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
+    uint32_t fast_group[3] = {0, 0, 0};
+    if (!bvh) { blob = build_fast_blob(s, fast_group); if (blob.size() * 4 > 200 * 1024) blob.clear(); }
     // fp32 BVH leaf records: typed 32-byte entries in leaf (slot) order
     lap_up("pack geometry + tree");
     if (bvh) {
@@ -562,6 +579,7 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
         c->fast_words = (uint32_t)(blob.size() / 4);
         c->fast_hd = fast_header(blob[0], blob[1], blob[2], blob[3], blob[4], blob[5]);
         c->fast_hd.box_pairs = blob[6]; c->fast_hd.any_unknown = blob[7];
+        for (int k = 0; k < 3; k++) c->fast_hd.group[k] = fast_group[k];
         if (blob[6]) {   // plane coordinates of the wall pairs: record r of the axis lists starts at word off_axs * 4 + r * 8
             const uint32_t* ax = blob.data() + (size_t)c->fast_hd.off_axs * 4;
             for (int k = 0; k < 3; k++) { std::memcpy(&c->fast_hd.box_lo[k], ax + (2 * k) * 8, 4); std::memcpy(&c->fast_hd.box_hi[k], ax + (2 * k + 1) * 8, 4); }
@@ -671,10 +689,10 @@ extern "C" int ipt_ctx_set_scene(ipt_ctx* c, const ipt_scene* s)
 
 template <typename R> static V3<R> hv(const double* p) { V3<R> v; v.x = (R)p[0]; v.y = (R)p[1]; v.z = (R)p[2]; return v; }
 
-template <bool FIRST, int SHAPE = 0>
+template <bool FIRST, int SHAPE, bool RR>
 static int launch_bounce_fast(ipt_ctx* c, const KParams<float>& kp, int* grid_cache)
 {
-    auto kern = k_bounce_fast<FIRST, SHAPE>;
+    auto kern = k_bounce_fast<FIRST, SHAPE, RR>;
     constexpr int threads = FastCfg<FIRST>::THREADS;
     const size_t smem = (size_t)kp.fast_words * 16 + (size_t)2 * 3 * threads * 16;   // scene lists + double-buffered ray staging
     if (*grid_cache == 0) {
@@ -960,7 +978,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
     kp.leaf_min = std::getenv("IPT_LEAF_MIN") ? (uint32_t)std::atoi(std::getenv("IPT_LEAF_MIN")) : (grid_walk ? 16u : 8u);
     kp.static_slices = std::getenv("IPT_STATIC_SLICES") ? 1u : 0u;
     // fp32 + no BVH: the typed-list kernel (k_bounce_fast); IPT_GENERIC_KERNEL=1 forces the generic one (A/B runs)
-    const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !std::getenv("IPT_GENERIC_KERNEL");
+    // (a scene with an unknown reflection value - none shipped has one - goes through the generic kernel, which carries that case)
+    const bool use_fast = sizeof(R) == 4 && !bvh && !defer && !nee && c->fast_blob && c->fast_words > 0 && !c->fast_hd.any_unknown && !std::getenv("IPT_GENERIC_KERNEL");
     kp.fast_blob = c->fast_blob; kp.fast_words = c->fast_words; kp.fast_hd = c->fast_hd;
     const bool sync_passes = std::getenv("IPT_SYNC_PASSES") != nullptr;   // diagnostic: drain the GPU between passes
     // A/B knob: fixed number of bounces per pass for the fast kernel's passes from depth 2 on (default 0 = adaptive)
@@ -974,7 +993,8 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
                                        : std::min(prm.max_depth - first, FAST_LATER_LAUNCHES));
     }
     kp.fast_hint = c->fast_hint;
-    const int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
+    int shape = std::getenv("IPT_NO_SHAPE") ? 0 : fast_shape(c->fast_hd.n_sph, c->fast_hd.n_x, c->fast_hd.n_y, c->fast_hd.n_z, c->fast_hd.n_gen);   // A/B knob
+    if (shape == 0 && (c->fast_hd.group[0] | c->fast_hd.group[1] | c->fast_hd.group[2])) shape = -1;   // list scene with a coplanar group (build_fast_blob)
     CK(cudaMemsetAsync(c->frame, 0, c->frame_pixels * 24, c->stream));
     CK(cudaMemsetAsync(c->traced, 0, 64, c->stream));   // [0] casts, [1] queue records moved, [2..6] traversal work (add_work)
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -1052,17 +1072,22 @@ static int render_typed(ipt_ctx* c, const ipt_params& prm, uint32_t tile_w, uint
             if (use_fast) {
                 const KParams<float>& kf = (const KParams<float>&)kp;
                 // box rooms (fast_shape): the scan is straight-line code, one instantiation per sphere count
-#define IPT_FAST_BY_SHAPE(FIRST, GRID)                                                                 \
+                // (Russian roulette, an extension, has its own instantiations: the default ones carry no code for it)
+#define IPT_FAST_BY_SHAPE(FIRST, RR, GRID)                                                             \
     switch (shape) {                                                                                   \
-        case 1: rc = launch_bounce_fast<FIRST, 1>(c, kf, GRID); break;                                 \
-        case 2: rc = launch_bounce_fast<FIRST, 2>(c, kf, GRID); break;                                 \
-        case 3: rc = launch_bounce_fast<FIRST, 3>(c, kf, GRID); break;                                 \
-        case 4: rc = launch_bounce_fast<FIRST, 4>(c, kf, GRID); break;                                 \
-        case 5: rc = launch_bounce_fast<FIRST, 5>(c, kf, GRID); break;                                 \
-        default: rc = launch_bounce_fast<FIRST, 0>(c, kf, GRID); break;                                \
+        case 1: rc = launch_bounce_fast<FIRST, 1, RR>(c, kf, GRID); break;                             \
+        case 2: rc = launch_bounce_fast<FIRST, 2, RR>(c, kf, GRID); break;                             \
+        case 3: rc = launch_bounce_fast<FIRST, 3, RR>(c, kf, GRID); break;                             \
+        case 4: rc = launch_bounce_fast<FIRST, 4, RR>(c, kf, GRID); break;                             \
+        case 5: rc = launch_bounce_fast<FIRST, 5, RR>(c, kf, GRID); break;                             \
+        case -1: rc = launch_bounce_fast<FIRST, -1, RR>(c, kf, GRID); break;                           \
+        default: rc = launch_bounce_fast<FIRST, 0, RR>(c, kf, GRID); break;                            \
     }
-                if (pass == 0) IPT_FAST_BY_SHAPE(true, &grid_first)
-                else IPT_FAST_BY_SHAPE(false, &grid_next)
+                const bool roulette = (kf.flags & 0x8u) != 0;
+                if (pass == 0 && roulette) IPT_FAST_BY_SHAPE(true, true, &grid_first)
+                else if (pass == 0) IPT_FAST_BY_SHAPE(true, false, &grid_first)
+                else if (roulette) IPT_FAST_BY_SHAPE(false, true, &grid_next)
+                else IPT_FAST_BY_SHAPE(false, false, &grid_next)
 #undef IPT_FAST_BY_SHAPE
             }
             else if (defer && d == 0) rc = bvh ? launch_bounce<R, MODE_BVH, true, true>(c, kp, smem, &grid_first) : launch_bounce<R, MODE_BRUTE, true, true>(c, kp, smem, &grid_first);

@@ -636,6 +636,34 @@ def test_box_room_shapes_match_the_list_kernel_and_the_oracle(pyipt, oracle, tmp
     assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 2e-3 * cnt["casts_needed"]
 
 
+def test_coplanar_groups_do_not_change_the_frame(pyipt, oracle, tmp_path, monkeypatch):
+    """Rectangles of one axis list that share their plane are walked as a group (fast_axis_group: t and the hit point once per
+    plane, k_bounce_fast<..., SHAPE = -1>): maze.json (23 rectangles on z = 200), and a room with six OVERLAPPING coplanar
+    tiles of different colours, where every hit on the plane is an exact tie in t that the lowest JSON index must win
+    (Renderer.cu:235).  Frames and cast counts equal those of the plain list loops (IPT_NO_GROUP=1) bit for bit, and the
+    oracle's frame within the fp32 tolerance."""
+    from scene_util import room_objects, vec, write_scene
+    objs = room_objects()
+    for i in range(6):    # overlapping tiles on y = 500, each shifted by a third of its width
+        objs.append({"type": "plane", "position": vec((300 + 110 * i, 500, 300 + 20 * i)), "north": vec((0, 0, 160)), "east": vec((170, 0, 0)),
+                     "color": vec((.15 + .14 * i, .9 - .12 * i, .3 + .1 * (i % 3))), "emission": vec((0, 0, 0)), "reflection": i % 2})
+    scene = {"width": 256, "height": 144, "camera": {"position": vec((640, 0, 360)), "direction": vec((0, 1, 0)), "orientation": vec((-1, 0, 0))},
+             "objects": objs}
+    tiles = write_scene(tmp_path / "tiles.json", scene)
+    for path, W, H in ((oracle.scene_path("maze"), 256, 144), (tiles, 256, 144)):
+        hs = pyipt.HostScene.load(path, width=W, height=H)
+        img, st = pyipt.render(hs, 6, 8, seed=17, want64=False)
+        monkeypatch.setenv("IPT_NO_GROUP", "1")
+        hs2 = pyipt.HostScene.load(path, width=W, height=H)
+        plain, st2 = pyipt.render(hs2, 6, 8, seed=17, want64=False)
+        monkeypatch.delenv("IPT_NO_GROUP")
+        assert img.any() and np.array_equal(img, plain) and st["traced_bounces"] == st2["traced_bounces"]
+        ref, cnt = oracle.render(oracle.Scene.load(path, W, H), 6, 8, rng=oracle.RNG_COUNTER, seed=17)
+        print("MEASURED coplanar groups:", frac_within(img, ref, 1e-3))
+        assert frac_within(img, ref, 1e-3) >= 0.99
+        assert abs(st["traced_bounces"] - cnt["casts_needed"]) <= 3e-3 * cnt["casts_needed"]
+
+
 @pytest.mark.parametrize("which,depth", [("spheres", 10), ("spheres", 40), ("leaky", 40), ("leaky", 5), ("maze", 3)])
 def test_bounces_per_pass_do_not_change_the_frame(pyipt, oracle, tmp_path, monkeypatch, which, depth):
     """From depth 2 on the typed-list kernel advances rays several bounces per pass, the count chosen on the device from
