@@ -607,6 +607,15 @@ static constexpr int GRID_BURST = IPT_GRID_BURST;
 #ifndef IPT_GRID_CTAS
 #define IPT_GRID_CTAS 4
 #endif
+// Lanes that make a refill / a cell step / a primitive step worth running (measured on config 5, profiles/README.md: 12 / 12 / 16).
+// Compile-time constants (-DIPT_GRID_REFILL_MIN=... for A/B builds): as kernel parameters each test in the loop was a constant-bank
+// load and a register compare instead of a compare with an immediate.
+#ifndef IPT_GRID_REFILL_MIN
+#define IPT_GRID_REFILL_MIN 12
+#define IPT_GRID_CELL_MIN 12
+#define IPT_GRID_PRIM_MIN 16
+#endif
+static constexpr uint32_t GRID_REFILL_MIN = IPT_GRID_REFILL_MIN, GRID_CELL_MIN = IPT_GRID_CELL_MIN, GRID_PRIM_MIN = IPT_GRID_PRIM_MIN;
 __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(const __grid_constant__ KParams<float> p)
 {
     const SceneView<float> sc = p.sc;
@@ -658,7 +667,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
         }
         // ---- refill
         const uint32_t idle = __ballot_sync(0xffffffffu, !has);
-        if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= p.refill_min)) {
+        if (!exhausted && (idle == 0xffffffffu || (uint32_t)__popc(idle) >= GRID_REFILL_MIN)) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(work, (uint32_t)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -715,7 +724,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
             const bool want_cell = has && marching && pr_cur >= pr_end;
             const uint32_t m_cell = __ballot_sync(0xffffffffu, want_cell);
             if (m_cell == 0) break;
-            if ((uint32_t)__popc(m_cell) < p.descend_min && __any_sync(0xffffffffu, has && pr_cur < pr_end)) break;
+            if ((uint32_t)__popc(m_cell) < GRID_CELL_MIN && __any_sync(0xffffffffu, has && pr_cur < pr_end)) break;
             if (want_cell) {
                 const uint2 ce = ce_nx;
                 t_exit = tex_nx;
@@ -734,7 +743,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
             const uint32_t m_prim = __ballot_sync(0xffffffffu, want_prim);
             if (m_prim == 0) break;
             // few lanes hold primitives: leave them waiting only if enough lanes march for a cell step to run (progress either way)
-            if ((uint32_t)__popc(m_prim) < p.leaf_min && (uint32_t)__popc(__ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end)) >= p.descend_min) break;
+            if ((uint32_t)__popc(m_prim) < GRID_PRIM_MIN && (uint32_t)__popc(__ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end)) >= GRID_CELL_MIN) break;
             if (want_prim) {
                 const uint32_t slot = slot_nx;
                 float4 a, b;
