@@ -600,8 +600,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
 //    the boxes the host filed the primitives under;
 //  * cell steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (descend_min,
 //    leaf_min) or nobody wants the other.
+// Steps of one kind before the warp looks at its finished and idle lanes again.  4 was right for the first version of the kernel
+// (2.6 -> 3.2 Gbounces/s); since the steps run only when enough lanes want them (GRID_CELL_MIN, GRID_PRIM_MIN) a burst's second
+// trip mostly found too few lanes and left again - 6 % of the kernel's instructions: 1 / 2 / 4 give 3.88 / 3.63 / 3.64 Gbounces/s.
 #ifndef IPT_GRID_BURST
-#define IPT_GRID_BURST 4
+#define IPT_GRID_BURST 1
 #endif
 static constexpr int GRID_BURST = IPT_GRID_BURST;
 #ifndef IPT_GRID_CTAS
