@@ -598,15 +598,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 5) k_extend_bvh(const __grid_co
 //  * the next boundary along an axis is evaluated from the integer cell coordinate, t = i * (cell / d) + (lo - o) / d, not
 //    accumulated: no drift over hundreds of steps; what is left (~1e-4 at |x| ~ 1e3) is covered 40 times by the padding of
 //    the boxes the host filed the primitives under;
-//  * cell steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (descend_min,
-//    leaf_min) or nobody wants the other.
-// Steps of one kind before the warp looks at its finished and idle lanes again.  4 was right for the first version of the kernel
-// (2.6 -> 3.2 Gbounces/s); since the steps run only when enough lanes want them (GRID_CELL_MIN, GRID_PRIM_MIN) a burst's second
-// trip mostly found too few lanes and left again - 6 % of the kernel's instructions: 1 / 2 / 4 give 3.88 / 3.63 / 3.64 Gbounces/s.
-#ifndef IPT_GRID_BURST
-#define IPT_GRID_BURST 1
-#endif
-static constexpr int GRID_BURST = IPT_GRID_BURST;
+//  * cell steps and primitive tests are warp-synchronous blocks, each run when enough lanes want it (GRID_CELL_MIN,
+//    GRID_PRIM_MIN) or nobody wants the other.
+// (The first version ran bursts of up to 4 steps of one kind before the warp looked at its finished and idle lanes again: 2.6 ->
+// 3.2 Gbounces/s then; since steps run only when enough lanes want them, a burst's second trip mostly found too few and left again:
+// 1 / 2 / 4 steps gave 3.88 / 3.63 / 3.64 Gbounces/s, and the bursts went.)
 #ifndef IPT_GRID_CTAS
 #define IPT_GRID_CTAS 4
 #endif
@@ -716,18 +712,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, has) == 0) {
-            if (exhausted) break;
+        // ---- what the lanes want: a lane with a ray wants a cell step, a primitive step, or has finished (written out at the top
+        // of the next trip).  One vote each; who runs is decided from the two masks.
+        const bool want_cell = has && marching && pr_cur >= pr_end;
+        bool want_prim = has && pr_cur < pr_end;
+        const uint32_t m_cell = __ballot_sync(0xffffffffu, want_cell);
+        uint32_t m_prim = __ballot_sync(0xffffffffu, want_prim);
+        if ((m_cell | m_prim) == 0) {
+            if (exhausted && __ballot_sync(0xffffffffu, has) == 0) break;
             continue;
         }
-        // ---- cell steps: open the cell whose entry was requested a step ago, request the next one.  Up to GRID_BURST steps before the
-        // warp looks at its finished and idle lanes again; the burst ends early when few lanes still march and others hold primitives.
-#pragma unroll 1
-        for (int it = 0; it < GRID_BURST; it++) {
-            const bool want_cell = has && marching && pr_cur >= pr_end;
-            const uint32_t m_cell = __ballot_sync(0xffffffffu, want_cell);
-            if (m_cell == 0) break;
-            if ((uint32_t)__popc(m_cell) < GRID_CELL_MIN && __any_sync(0xffffffffu, has && pr_cur < pr_end)) break;
+        // ---- cell step: open the cell whose entry was requested a step ago, request the next one - when enough lanes want it, or
+        // nobody holds primitives
+        const bool run_cell = m_cell != 0 && ((uint32_t)__popc(m_cell) >= GRID_CELL_MIN || m_prim == 0);
+        if (run_cell) {
             if (want_cell) {
                 const uint2 ce = ce_nx;
                 t_exit = tex_nx;
@@ -738,26 +736,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS, IPT_GRID_CTAS) k_extend_grid(co
                 marching = ahead_in && !(ce.y == 0u && best.t <= t_exit);
                 if (ahead_in) advance();
             }
+            want_prim = has && pr_cur < pr_end;                           // the lanes that opened an occupied cell hold primitives now
+            m_prim = __ballot_sync(0xffffffffu, want_prim);
         }
-        // ---- primitive steps: one reference per lane and step
-#pragma unroll 1
-        for (int it = 0; it < GRID_BURST; it++) {
-            const bool want_prim = has && pr_cur < pr_end;
-            const uint32_t m_prim = __ballot_sync(0xffffffffu, want_prim);
-            if (m_prim == 0) break;
-            // few lanes hold primitives: leave them waiting only if enough lanes march for a cell step to run (progress either way)
-            if ((uint32_t)__popc(m_prim) < GRID_PRIM_MIN && (uint32_t)__popc(__ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end)) >= GRID_CELL_MIN) break;
-            if (want_prim) {
-                const uint32_t slot = slot_nx;
-                float4 a, b;
-                ldg256(sc.bslot + 2 * (size_t)slot, a, b);
-                pr_cur++;
-                if (pr_cur < pr_end) slot_nx = __ldg(p.grid_refs + pr_cur);
-                test_brec(sc, a, b, slot, o, d, inv, self, onSurf, best, w_sph);
-                w_prims++;
-                // the cell is done: stop if the nearest hit lies before its exit
-                if (pr_cur >= pr_end && best.t <= t_exit) marching = false;
-            }
+        // ---- primitive step: one reference per lane.  Few lanes hold primitives: they wait only if enough lanes march for a cell
+        // step to run next (progress either way)
+        bool run_prim = m_prim != 0;
+        if (run_prim && (uint32_t)__popc(m_prim) < GRID_PRIM_MIN) {
+            const uint32_t m_cell_now = run_cell ? __ballot_sync(0xffffffffu, has && marching && pr_cur >= pr_end) : m_cell;
+            run_prim = (uint32_t)__popc(m_cell_now) < GRID_CELL_MIN;
+        }
+        if (run_prim && want_prim) {
+            const uint32_t slot = slot_nx;
+            float4 a, b;
+            ldg256(sc.bslot + 2 * (size_t)slot, a, b);
+            pr_cur++;
+            if (pr_cur < pr_end) slot_nx = __ldg(p.grid_refs + pr_cur);
+            test_brec(sc, a, b, slot, o, d, inv, self, onSurf, best, w_sph);
+            w_prims++;
+            // the cell is done: stop if the nearest hit lies before its exit
+            if (pr_cur >= pr_end && best.t <= t_exit) marching = false;
         }
     }
     my_traced = __reduce_add_sync(0xffffffffu, my_traced);
