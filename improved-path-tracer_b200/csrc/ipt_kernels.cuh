@@ -1033,9 +1033,14 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 }
 
 // Threads per CTA and CTAs per SM of the passes after pass 0 (pass 0 uses BLOCK_THREADS x 3)
+// (round 1, at 80 registers: 256 x 3 beat 224 x 4 and 128 x 7 by 2-3 %; since the kernel needs 71 the compiler fits it into the 73 of
+// 128 x 7 without spills and the four extra warps per SM give +0.8 % on the default bench, +2 % on mirrors.json, scripts/r02_gpu56.sh)
 #ifndef IPT_FAST_THREADS
-#define IPT_FAST_THREADS 256
-#define IPT_FAST_CTAS 3
+#define IPT_FAST_THREADS 128
+#define IPT_FAST_CTAS 7
+#endif
+#ifndef IPT_FIRST_THREADS
+#define IPT_FIRST_THREADS BLOCK_THREADS
 #endif
 #ifndef IPT_FIRST_CTAS
 #define IPT_FIRST_CTAS 3
@@ -1047,7 +1052,7 @@ __device__ __forceinline__ bool fast_schedule(const P& p, uint32_t& nk)
 #ifndef IPT_DEEP_CHUNK
 #define IPT_DEEP_CHUNK 2u
 #endif
-template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? BLOCK_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? IPT_FIRST_CTAS : IPT_FAST_CTAS; };
+template <bool FIRST> struct FastCfg { static constexpr int THREADS = FIRST ? IPT_FIRST_THREADS : IPT_FAST_THREADS, CTAS = FIRST ? IPT_FIRST_CTAS : IPT_FAST_CTAS; };
 
 template <bool FIRST, int SHAPE = 0, bool RR = false>
 __global__ void __launch_bounds__(FastCfg<FIRST>::THREADS, FastCfg<FIRST>::CTAS) k_bounce_fast(const __grid_constant__ KParams<float> p)
