@@ -102,6 +102,7 @@ struct Builder {
                     if (cost < bestCost) { bestCost = cost; bestAx = ax; bestK = k; }
                 }
             }
+            if (bestAx < 0) return first + count / 2;   // no finite cost (boxes of +-FLT_MAX extent): split by index
             Prim tmp[SMALL];
             for (uint32_t i = 0; i < count; i++) tmp[i] = prims[order[bestAx][i]];
             for (uint32_t i = 0; i < count; i++) prims[first + i] = tmp[i];
@@ -190,6 +191,19 @@ struct Builder {
     }
 };
 
+// Objects arrive as the caller's bytes (ipt_render_objects): coordinates may be infinite or NaN.  The reference's scan just
+// never hits such an object or hits it everywhere; here the builder must stay well defined: centroids become finite
+// (NaN -> 0), box bounds are clamped to +-FLT_MAX (a NaN coordinate never enters a box: std::min/max keep the other operand).
+inline float finite_or(float v, float other) { return std::isnan(v) ? other : std::min(FLT_MAX, std::max(-FLT_MAX, v)); }
+void sanitize(Prim& p)
+{
+    for (int k = 0; k < 3; k++) {
+        p.c[k] = finite_or(p.c[k], 0.0f);
+        p.box.lo[k] = std::max(p.box.lo[k], -FLT_MAX);
+        p.box.hi[k] = std::min(p.box.hi[k], FLT_MAX);
+    }
+}
+
 inline float down(double v, double pad) { return std::nextafterf((float)(v - pad), -INFINITY); }
 inline float up(double v, double pad) { return std::nextafterf((float)(v + pad), INFINITY); }
 inline double dabs(float v) { return std::fabs((double)v); }
@@ -223,6 +237,7 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         p.box.grow(lo); p.box.grow(hi);
         for (int k = 0; k < 3; k++) p.c[k] = (float)c[k];
         p.ref = i;
+        sanitize(p);
     }
     for (uint32_t j = 0; j < nr; j++) {
         const double *c = &s->rect_center[3 * (size_t)j], *N = &s->rect_north[3 * (size_t)j], *E = &s->rect_east[3 * (size_t)j];
@@ -235,6 +250,7 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
             }
         for (int k = 0; k < 3; k++) p.c[k] = (float)c[k];
         p.ref = 0x80000000u | j;
+        sanitize(p);
     }
     // fork threads on the top levels of large scenes (2^par_depth subtrees in flight)
     int par_depth = 0;

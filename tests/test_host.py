@@ -145,6 +145,42 @@ def test_loader_missing_and_malformed_file(pyipt, tmp_path):
         pyipt.HostScene.load(str(p))
 
 
+def test_loader_survives_mutated_scenes(pyipt, oracle, tmp_path):
+    """SceneData.cpp:61-96 answers any unreadable scene with a message and no scene (nlohmann throws, the reference
+    catches); the pull parser must do the same on truncated, spliced and byte-flipped copies of spheres.json: every load
+    either fails with a message or yields a scene whose BVH builds. (400 seeded mutations here; 21 000 were run once.)"""
+    import random
+    src = open(oracle.scene_path("spheres"), "rb").read()
+    rnd = random.Random(20261019)
+    toks = [b"{", b"}", b"[", b"]", b",", b":", b'"', b"-", b"e", b".", b"null", b"true", b"1e999", b"\\", b"\\u00",
+            b"0", b" ", b'"objects"', b'"camera"', b"-0", b"1e-999", b"99999999999999999999999"]
+    loaded = failed = 0
+    p = tmp_path / "mutant.json"
+    for _ in range(400):
+        b = bytearray(src)
+        for _ in range(rnd.randint(1, 2)):
+            k, at = rnd.random(), rnd.randrange(max(1, len(b)))
+            if k < 0.3:
+                del b[at:at + rnd.randint(1, 40)]
+            elif k < 0.6:
+                b[at:at] = rnd.choice(toks)
+            elif k < 0.8 and b:
+                b[min(at, len(b) - 1)] = rnd.randrange(256)
+            elif k < 0.9:
+                b = b[:at]
+            else:
+                q = rnd.randrange(max(1, len(b)))
+                b[at:at] = b[q:q + rnd.randint(1, 200)]
+        p.write_bytes(bytes(b))
+        try:
+            pyipt.HostScene.load(str(p), brute_max=0)
+            loaded += 1
+        except pyipt.IptError as e:
+            assert str(e)
+            failed += 1
+    assert loaded + failed == 400 and failed > 100 and loaded > 0, (loaded, failed)
+
+
 def test_loader_ignores_unknown_keys_and_key_order(pyipt, tmp_path):
     scene = synthetic_scene(5, 2)
     a = pyipt.HostScene.load(write_scene(tmp_path / "a.json", scene)).arrays()
@@ -153,6 +189,31 @@ def test_loader_ignores_unknown_keys_and_key_order(pyipt, tmp_path):
     b = pyipt.HostScene.load(write_scene(tmp_path / "b.json", scene2)).arrays()
     for k in ("sphere_cxyzr", "rect_plane", "rect_bounds", "mat_color", "mat_reflection"):
         assert np.array_equal(a[k], b[k])
+
+
+def test_builders_survive_non_finite_objects(pyipt, oracle, tmp_path):
+    """ipt_render_objects takes the caller's ObjectData bytes (ObjectData.hpp:15-31) as they are; the reference's scan
+    (Renderer.cu:227-243) never faults on NaN or infinite coordinates, so the BVH and grid builders must not either
+    (a NaN cost once left the exact-SAH split of a small range without an axis)."""
+    rnd = np.random.default_rng(5)
+    # random bytes: whatever object kinds and coordinates they happen to spell
+    for i in range(60):
+        n = int(rnd.integers(1, 300))
+        raw = rnd.integers(0, 256, 144 * n, dtype=np.uint8).tobytes()
+        if i % 3 == 0:
+            raw = rnd.normal(0, 100, 18 * n).tobytes()
+        pyipt.HostScene.from_objects(raw, n, 64, 48, list(rnd.normal(0, 1, 9)), brute_max=0)
+    # a scene large enough for the uniform grid, with special values poked into it
+    sc = oracle.Scene.load(write_scene(tmp_path / "s.json", synthetic_scene(3000, 3)))
+    cs = sc.c_scene()
+    raw0 = ctypes.string_at(cs.objects, 144 * cs.n_objects)
+    special = [np.nan, np.inf, -np.inf, 1e300, -1e300, 3.5e38, -3.5e38, 1e-320, 0.0, -0.0, 1e20]
+    for i in range(20):
+        a = np.frombuffer(bytearray(raw0), dtype=np.float64).copy()
+        k = int(rnd.integers(1, 50))
+        a[rnd.integers(0, a.size, k)] = rnd.choice(special, k)
+        h = pyipt.HostScene.from_objects(a.tobytes(), cs.n_objects, sc.width, sc.height, list(cs.camera))
+        assert h.arrays()["mat_color"].shape[0] == cs.n_objects
 
 
 def test_from_objects_equals_loader(pyipt, oracle):
