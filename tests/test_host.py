@@ -292,6 +292,26 @@ def test_png_roundtrip(pyipt, tmp_path):
     assert got.shape == (37, 53, 3) and got.dtype == np.uint8
     want = np.clip((img.astype(np.float64) * 255).astype(np.int64), 0, 255)
     assert np.array_equal(got, want)
+    # a frame large enough for several deflate bands (they are compressed on separate threads and concatenated):
+    # chunk CRCs, one zlib stream, its Adler-32 over all bands (zlib.decompress raises otherwise), the same pixels
+    import struct
+    import zlib
+    for w, h in ((1280, 720), (1, 1), (5000, 3), (2, 1500)):
+        img = rng.uniform(-0.2, 1.4, (h, w, 3)).astype(np.float32)
+        assert pyipt.lib().ipt_host_write_png(p.encode(), img.ctypes.data, w, h) == 0
+        d = open(p, "rb").read()
+        pos, idat = 8, b""
+        while pos < len(d):
+            n, = struct.unpack(">I", d[pos:pos + 4])
+            typ, data = d[pos + 4:pos + 8], d[pos + 8:pos + 8 + n]
+            assert zlib.crc32(typ + data) & 0xffffffff == struct.unpack(">I", d[pos + 8 + n:pos + 12 + n])[0], typ
+            idat += data if typ == b"IDAT" else b""
+            pos += 12 + n
+        raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+        assert not raw[:, 0].any()                                # filter type 0 on every row
+        want = np.clip((img.astype(np.float64) * 255).astype(np.int64), 0, 255)
+        assert np.array_equal(raw[:, 1:].reshape(h, w, 3), want)
+        assert np.array_equal(np.asarray(Image.open(p)), want)
 
 
 def test_time_string_and_benchmark_record(pyipt, tmp_path):

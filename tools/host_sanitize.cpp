@@ -1,7 +1,7 @@
 // host_sanitize.cpp - the host layer (scene_loader, bvh, grid, output, cli) under AddressSanitizer + UBSan, CPU only:
 //   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -Iinclude tools/host_sanitize.cpp improved-path-tracer_b200/host/{scene_loader,bvh,grid,output,cli}.cpp -o /tmp/host_sanitize -lz -lpthread
 //   /tmp/host_sanitize scene.json ...   (loads each file, builds the BVH + grid at leaf sizes 4, 1, 16, frees it)
-// Round 2: clean on the three shipped scenes, the 1M-primitive scene of config 5 and 3000 mutated copies of spheres.json / maze.json.
+// Round 2: clean (and clean under -fsanitize=thread) on the three shipped scenes, the 1M-primitive scene of config 5 and 3000 mutated copies of spheres.json / maze.json.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,5 +20,11 @@ int main(int argc, char** argv) {
         ipt_host_set_size(s, 33, 17);
         ipt_host_free_scene(s);
     }
+    // the banded PNG encoder (several deflate streams on threads, one zlib stream out)
+    const uint32_t W = 1280, H = 720;
+    std::vector<float> img((size_t)W * H * 3);
+    for (size_t i = 0; i < img.size(); i++) img[i] = (float)((i * 2654435761u >> 8) & 0xffff) / 50000.f - 0.1f;
+    std::printf("png: %d\n", ipt_host_write_png("/tmp/host_sanitize.png", img.data(), W, H));
+    std::printf("png 1x1: %d\n", ipt_host_write_png("/tmp/host_sanitize_1.png", img.data(), 1, 1));
     return 0;
 }
