@@ -111,6 +111,10 @@ def lib():
         L.or_render.restype = ctypes.c_int
         L.or_nearest_hit.argtypes = [ctypes.POINTER(OrScene), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         L.or_nearest_hit.restype = None
+        L.or_render_accel.argtypes = L.or_render.argtypes
+        L.or_render_accel.restype = ctypes.c_int
+        L.or_nearest_hit_accel.argtypes = L.or_nearest_hit.argtypes
+        L.or_nearest_hit_accel.restype = None
         dp = ctypes.POINTER(ctypes.c_double)
         L.or_sphere_intersect.argtypes = [ctypes.c_double, dp, dp, dp]
         L.or_sphere_intersect.restype = ctypes.c_double
@@ -159,27 +163,30 @@ def ref():
     return _ref
 
 
-def render(scene, samples, depth, rng=RNG_COUNTER, seed=0, begin=0, end=-1, nthreads=None, out=None):
-    """Oracle render. Returns (image float64 [H,W,3], counts dict)."""
+def render(scene, samples, depth, rng=RNG_COUNTER, seed=0, begin=0, end=-1, nthreads=None, out=None, accel=False):
+    """Oracle render. Returns (image float64 [H,W,3], counts dict).  accel=True: nearest hits through the oracle's own box
+    tree (SURVEY.md §8c Route 3, for scenes the reference's scan cannot finish) - bit-identical frames, see restate.cpp."""
     cs = scene.c_scene()
     if out is None:
         out = np.zeros((scene.height, scene.width, 3), dtype=np.float64)
     cnt = OrCounts()
-    rc = lib().or_render(ctypes.byref(cs), samples, depth, rng, seed, begin, end, nthreads or os.cpu_count() or 1,
-                         out.ctypes.data, ctypes.byref(cnt))
+    fn = lib().or_render_accel if accel else lib().or_render
+    rc = fn(ctypes.byref(cs), samples, depth, rng, seed, begin, end, nthreads or os.cpu_count() or 1,
+            out.ctypes.data, ctypes.byref(cnt))
     if rc != 0:
         raise RuntimeError("or_render failed")
     return out, {"samples": cnt.samples, "casts_reference": cnt.casts_reference, "casts_needed": cnt.casts_needed}
 
 
-def nearest_hit(scene, rays):
-    """rays: float64 [n,6] (origin, direction) -> (index int32 [n], t float64 [n]); Renderer.cu:227-243."""
+def nearest_hit(scene, rays, accel=False):
+    """rays: float64 [n,6] (origin, direction) -> (index int32 [n], t float64 [n]); Renderer.cu:227-243.
+    accel=True: the same through the oracle's own box tree (Route 3)."""
     cs = scene.c_scene()
     rays = np.ascontiguousarray(rays, dtype=np.float64)
     n = rays.shape[0]
     idx = np.zeros(n, dtype=np.int32)
     t = np.zeros(n, dtype=np.float64)
-    lib().or_nearest_hit(ctypes.byref(cs), rays.ctypes.data, n, idx.ctypes.data, t.ctypes.data)
+    (lib().or_nearest_hit_accel if accel else lib().or_nearest_hit)(ctypes.byref(cs), rays.ctypes.data, n, idx.ctypes.data, t.ctypes.data)
     return idx, t
 
 

@@ -59,6 +59,13 @@ int or_render(const or_scene* scene, uint32_t samples, uint32_t max_depth, int r
 /* Renderer::getHitObjectAndDistance (Renderer.cu:227-243) for n_rays rays (o,d as 6 doubles each). */
 void or_nearest_hit(const or_scene* scene, const double* rays, uint32_t n_rays, int32_t* out_index, double* out_t);
 
+/* SURVEY.md §8(c) Route 3 - the same two calls through the oracle's own median-split box tree, for scenes the scan cannot
+ * finish (config 5's million objects).  Not in the reference; same object and bit-identical t as the scan (checked in
+ * tests/test_oracle_pin.py), so frames are bit-identical to or_render's. */
+int or_render_accel(const or_scene* scene, uint32_t samples, uint32_t max_depth, int rng_mode, uint64_t seed,
+                    int begin, int end, int nthreads, double* out_rgb, or_counts* counts);
+void or_nearest_hit_accel(const or_scene* scene, const double* rays, uint32_t n_rays, int32_t* out_index, double* out_t);
+
 /* Function-level entry points mirroring oracle/ref_shim.cpp's ref_* ones. */
 double or_sphere_intersect(double radius, const double* c, const double* o, const double* d);
 double or_plane_intersect(const double* north, const double* east, const double* c, const double* o, const double* d);

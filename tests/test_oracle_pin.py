@@ -126,3 +126,34 @@ def test_counter_and_reference_streams_agree_statistically(oracle):
         means.append(b.mean())
     sigma = np.std(means, ddof=1)
     assert abs(a.mean() - np.mean(means)) < 4 * sigma * np.sqrt(1 + 1 / 6), (a.mean(), np.mean(means), sigma)
+
+
+def test_route3_box_tree_equals_the_scan(oracle, tmp_path):
+    """SURVEY.md 8c Route 3: the oracle's own acceleration structure (restate.cpp, a median-split tree of padded boxes; not in the
+    reference) changes which objects are tested, never the answer: same object and bit-identical t as the scan of
+    Renderer.cu:227-243 on random rays (unit, shorter than unit, axis-parallel, zero), bit-identical frames and cast counts with
+    both random streams.  Checked once on config 5's million objects as well (3000 rays: identical)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from scene_util import synthetic_scene, write_scene
+    for name in ("spheres", "mirrors", "maze"):
+        sc = oracle.Scene.load(name, 96, 54)
+        for rng_mode, spp, depth in ((oracle.RNG_COUNTER, 4, 10), (oracle.RNG_REFERENCE, 2, 6)):
+            a, ca = oracle.render(sc, spp, depth, rng=rng_mode, seed=5)
+            b, cb = oracle.render(sc, spp, depth, rng=rng_mode, seed=5, accel=True)
+            assert np.array_equal(a, b) and ca == cb, name
+    sc = oracle.Scene.load(write_scene(tmp_path / "syn.json", synthetic_scene(4000, 2, width=96, height=54)))
+    a, ca = oracle.render(sc, 4, 10, seed=7)
+    b, cb = oracle.render(sc, 4, 10, seed=7, accel=True)
+    assert np.array_equal(a, b) and ca == cb and a.mean() > 0
+    rng = np.random.default_rng(3)
+    m = 4000
+    o = rng.uniform([-100, -600, -100], [1400, 800, 800], size=(m, 3))
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[::9] *= rng.uniform(0.34, 1.0, (len(d[::9]), 1))       # refracted rays are shorter than unit (AObject.hpp:59)
+    d[5::50, 0] = 0; d[7::70, 1:] = 0                          # axis-parallel
+    d[11::400] = 0                                             # the zero ray of an unknown reflection value
+    rays = np.concatenate([o, d], axis=1)
+    oi, ot = oracle.nearest_hit(sc, rays)
+    ai, at = oracle.nearest_hit(sc, rays, accel=True)
+    assert np.array_equal(oi, ai) and np.array_equal(ot, at) and 0.3 < np.mean(oi >= 0) <= 1.0
