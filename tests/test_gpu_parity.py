@@ -852,32 +852,6 @@ def test_config5_nearest_hit_on_the_real_scene(pyipt, oracle, million):
         mp.undo()
 
 
-def test_config5_frame_rows_match_the_oracle(pyipt, oracle, million):
-    """Config 5 at full size against the CPU oracle itself (SURVEY.md 8c, Route 3): the reference's scan cannot finish a frame of
-    a million objects, so the oracle finds its nearest hits through its own median-split box tree - same object and bit-identical t
-    as the scan, frames bit-identical to the scan's (tests/test_oracle_pin.py) - and renders 24 rows of the 1280x720 frame
-    (three bands, top / middle / bottom); the fp64 kernels, which walk the product's SAH tree, must give the same pixels."""
-    sc = oracle.Scene.load(million)
-    hs = pyipt.HostScene.load(million)
-    assert (hs.width, hs.height) == (sc.width, sc.height) == (1280, 720)
-    spp, depth, seed = 8, 10, 3
-    bands = (60, 356, 650)
-    ref = np.zeros((sc.height, sc.width, 3))
-    for z0 in bands:
-        oracle.render(sc, spp, depth, rng=oracle.RNG_COUNTER, seed=seed, begin=z0, end=z0 + 8, out=ref, accel=True)
-    rows = np.concatenate([np.arange(z0, z0 + 8) for z0 in bands])
-    c = pyipt.Context(0); c.set_scene(hs)
-    c.render(spp, depth, seed=seed, flags=pyipt.FLAG_FP64); img = c.download()
-    c.close()
-    a, b = img[rows], ref[rows]
-    lit = b.sum(axis=2) != 0                       # 0.1 % of the primitives emit: most pixels are exactly 0 at 8 spp
-    assert lit.mean() > 0.05
-    same = np.all(np.abs(a - b) <= 1e-9 * np.maximum(1e-3, np.abs(b)), axis=2)
-    print("MEASURED config5_rows_vs_oracle: lit", float(lit.mean()), "same on lit", float(same[lit].mean()), "same on dark", float(same[~lit].mean()))
-    assert same[lit].mean() >= 0.99 and same[~lit].mean() >= 0.999
-    assert abs(a.sum() - b.sum()) <= 1e-3 * b.sum()
-
-
 def test_config5_statistical_parity_fp32_vs_fp64(pyipt, oracle, million):
     """Config 5 at full size, 1280x720: the fp32 product kernels against the fp64 parity kernels (which are tied to the
     oracle per pixel on smaller BVH scenes and per ray above).  Same counter stream: most pixels agree to 1e-3; and the
@@ -1114,3 +1088,29 @@ def test_acceleration_structures_from_the_caller_are_checked(pyipt, oracle, tmp_
     st = c.render(2, 4, seed=1)
     assert st["traced_bounces"] > 0 and np.isfinite(c.download(want64=False)).all()
     c.close()
+
+
+def test_config5_frame_rows_match_the_oracle(pyipt, oracle, million):
+    """Config 5 at full size against the CPU oracle itself (SURVEY.md 8c, Route 3): the reference's scan cannot finish a frame of
+    a million objects, so the oracle finds its nearest hits through its own median-split box tree - same object and bit-identical t
+    as the scan, frames bit-identical to the scan's (tests/test_oracle_pin.py) - and renders 24 rows of the 1280x720 frame
+    (three bands, top / middle / bottom); the fp64 kernels, which walk the product's SAH tree, must give the same pixels."""
+    sc = oracle.Scene.load(million)
+    hs = pyipt.HostScene.load(million)
+    assert (hs.width, hs.height) == (sc.width, sc.height) == (1280, 720)
+    spp, depth, seed = 8, 10, 3
+    bands = (60, 356, 650)
+    ref = np.zeros((sc.height, sc.width, 3))
+    for z0 in bands:
+        oracle.render(sc, spp, depth, rng=oracle.RNG_COUNTER, seed=seed, begin=z0, end=z0 + 8, out=ref, accel=True)
+    rows = np.concatenate([np.arange(z0, z0 + 8) for z0 in bands])
+    c = pyipt.Context(0); c.set_scene(hs)
+    c.render(spp, depth, seed=seed, flags=pyipt.FLAG_FP64); img = c.download()
+    c.close()
+    a, b = img[rows], ref[rows]
+    lit = b.sum(axis=2) != 0                       # 0.1 % of the primitives emit: most pixels are exactly 0 at 8 spp
+    assert lit.mean() > 0.05
+    same = np.all(np.abs(a - b) <= 1e-9 * np.maximum(1e-3, np.abs(b)), axis=2)
+    print("MEASURED config5_rows_vs_oracle: lit", float(lit.mean()), "same on lit", float(same[lit].mean()), "same on dark", float(same[~lit].mean()))
+    assert same[lit].mean() >= 0.99 and same[~lit].mean() >= 0.999
+    assert abs(a.sum() - b.sum()) <= 1e-3 * b.sum()
