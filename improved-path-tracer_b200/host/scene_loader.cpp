@@ -5,6 +5,7 @@
 // polymorphic objects from it (Renderer.cu:69-86, Plane.cu:32-45).  Here a small pull parser reads the file once
 // without building a DOM (a 1M-object scene is a ~200 MB file) and the per-rectangle constants are computed once,
 // in fp64, on the host.
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -84,10 +85,14 @@ struct Reader {
 
 struct Vec3Opt {
     bool present = false;        // key exists
-    bool has[3] = {false, false, false};
+    bool key[3] = {false, false, false};   // "xx" / "yy" / "zz" exist in it, whatever their values are
+    bool has[3] = {false, false, false};   // ... and are numbers
     double v[3] = {0, 0, 0};
-    bool valid2() const { return present && has[0] && has[1]; }   // validateVec3tor checks xx, yy (and yy again): SceneData.cpp:30-33
-    bool valid3() const { return valid2() && has[2]; }
+    // validateVec3tor checks that xx and yy (and yy again) EXIST: SceneData.cpp:30-33.  That is all the reference checks before it
+    // prints one of its messages; a missing zz or a component that is not a number makes nlohmann throw or assert later, when the
+    // Vec3 is built (:143-145, :196-199, :218-224), and the program dies there without a message.
+    bool valid2() const { return present && key[0] && key[1]; }
+    bool valid3() const { return valid2() && has[0] && has[1] && has[2]; }
 };
 
 bool read_vec(Reader& r, Vec3Opt& out)
@@ -101,6 +106,7 @@ bool read_vec(Reader& r, Vec3Opt& out)
         std::string k;
         if (!r.string(k) || !r.eat(':')) return r.fail();
         const int i = k == "xx" ? 0 : k == "yy" ? 1 : k == "zz" ? 2 : -1;
+        if (i >= 0) { out.key[i] = true; out.has[i] = false; }      // (a repeated key: the last one counts, as in nlohmann)
         if (i >= 0 && (r.peek() == '-' || r.peek() == '+' || (r.peek() >= '0' && r.peek() <= '9'))) {
             if (!r.number(out.v[i])) return false;
             out.has[i] = true;
@@ -111,6 +117,7 @@ bool read_vec(Reader& r, Vec3Opt& out)
 
 struct ObjTmp {
     bool hasType = false, typeIsString = false, hasRefl = false, hasRadius = false;
+    bool reflIsNumber = false, radiusIsNumber = false;   // anything else makes nlohmann's get<>() throw upstream (uncaught: the reference dies)
     std::string type;
     double refl = 0, radius = 0;
     Vec3Opt color, emission, position, north, east;
@@ -126,8 +133,8 @@ bool read_object(Reader& r, ObjTmp& o)
         std::string k;
         if (!r.string(k) || !r.eat(':')) return r.fail();
         if (k == "type") { o.hasType = true; if (r.peek() == '"') { o.typeIsString = true; if (!r.string(o.type)) return false; } else if (!r.skip()) return false; }
-        else if (k == "reflection") { o.hasRefl = true; const char c = r.peek(); if (c == '-' || (c >= '0' && c <= '9')) { if (!r.number(o.refl)) return false; } else if (!r.skip()) return false; }
-        else if (k == "radius") { o.hasRadius = true; const char c = r.peek(); if (c == '-' || (c >= '0' && c <= '9')) { if (!r.number(o.radius)) return false; } else if (!r.skip()) return false; }
+        else if (k == "reflection") { o.hasRefl = true; const char c = r.peek(); o.reflIsNumber = c == '-' || (c >= '0' && c <= '9'); if (o.reflIsNumber) { if (!r.number(o.refl)) return false; } else if (!r.skip()) return false; }
+        else if (k == "radius") { o.hasRadius = true; const char c = r.peek(); o.radiusIsNumber = c == '-' || (c >= '0' && c <= '9'); if (o.radiusIsNumber) { if (!r.number(o.radius)) return false; } else if (!r.skip()) return false; }
         else if (k == "color") { if (!read_vec(r, o.color)) return false; }
         else if (k == "emission") { if (!read_vec(r, o.emission)) return false; }
         else if (k == "position") { if (!read_vec(r, o.position)) return false; }
@@ -255,7 +262,34 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
                 if (!okc || !r.eat('}')) { parsed = false; break; }
             } else if (k == "objects") {
                 hasObjects = true;
-                if (r.peek() != '[') { if (!r.skip()) { parsed = false; break; } continue; }
+                if (r.peek() == '{') {
+                    // not an array but an object: the reference's range-for (SceneData.cpp:158) walks its VALUES, in nlohmann's
+                    // std::map order (sorted by key, a repeated key keeps its last value)
+                    r.p++;
+                    std::vector<std::pair<std::string, ObjTmp>> kv;
+                    bool okm = true;
+                    if (!r.eat('}')) {
+                        do {
+                            std::string key;
+                            ObjTmp t;
+                            if (!r.string(key) || !r.eat(':') || !read_object(r, t)) { okm = false; break; }
+                            auto it = std::find_if(kv.begin(), kv.end(), [&](const std::pair<std::string, ObjTmp>& e) { return e.first == key; });
+                            if (it != kv.end()) it->second = t; else kv.emplace_back(key, t);
+                        } while (r.eat(','));
+                        if (okm && !r.eat('}')) okm = false;
+                    }
+                    if (!okm) { parsed = false; break; }
+                    std::stable_sort(kv.begin(), kv.end(), [](const std::pair<std::string, ObjTmp>& a, const std::pair<std::string, ObjTmp>& b) { return a.first < b.first; });
+                    for (auto& e : kv) objs.push_back(e.second);
+                    continue;
+                }
+                if (r.peek() != '[') {
+                    // a scalar: nlohmann iterates it as ONE element (which then fails validateObject), null as none
+                    const bool is_null = r.peek() == 'n';
+                    if (!r.skip()) { parsed = false; break; }
+                    if (!is_null) objs.emplace_back();
+                    continue;
+                }
                 objectsIsArray = true;
                 r.p++;
                 if (r.eat(']')) continue;
@@ -315,7 +349,8 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     if (!hasH || !hasW) { msg(message, message_len, "Missing height or witdh data!"); return nullptr; }            // :98-111
     if (!hasCamera) { msg(message, message_len, "No camera data!"); return nullptr; }                              // :119-123
     if (!camDir.present || !camPos.present || !camOri.present) { msg(message, message_len, "Camera data could not be read!"); return nullptr; }   // :126-131
-    if (!camDir.valid3() || !camPos.valid3() || !camOri.valid3()) { msg(message, message_len, "Camera data could not be parsed!"); return nullptr; }   // :137-141 (zz is read unchecked upstream)
+    if (!camDir.valid2() || !camPos.valid2() || !camOri.valid2()) { msg(message, message_len, "Camera data could not be parsed!"); return nullptr; }   // :137-141
+    if (!camDir.valid3() || !camPos.valid3() || !camOri.valid3()) { msg(message, message_len, "Camera data could not be parsed!"); return nullptr; }   // upstream dies in :143-145 (zz unchecked, values unchecked)
     if (!hasObjects) { msg(message, message_len, "No objects data!"); return nullptr; }                            // :152-156
     (void)objectsIsArray;
 
@@ -327,12 +362,17 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     for (const ObjTmp& o : objs) {
         const char* err = nullptr;
         if (!o.color.present || !o.emission.present || !o.position.present || !o.hasRefl || !o.hasType ||
-            !o.color.valid3() || !o.emission.valid3() || !o.position.valid3())
+            !o.color.valid2() || !o.emission.valid2() || !o.position.valid2())
             err = "Could not validate object data!";                                                               // :35-51,:160-164
         else if (!o.typeIsString || (o.type != "sphere" && o.type != "plane")) err = "Unknown object type";        // :166-177
         else if (o.type == "sphere" && !o.hasRadius) err = "Broken sphere object! ";                               // :185-189
+        // a "radius" / "reflection" that is not a number: upstream nlohmann throws type_error out of main (the program dies
+        // without a message, :196-199, :218-224); here the file is refused with the message of the check next to it
+        else if (o.type == "sphere" && !o.radiusIsNumber) err = "Broken sphere object! ";
         else if (o.type == "plane" && (!o.north.present || !o.east.present)) err = "Broken plane object! ";        // :205-209
+        // from here on the reference has no message: it dies building the object (missing zz, values that are not numbers)
         else if (o.type == "plane" && (!o.north.valid3() || !o.east.valid3())) err = "Broken plane object! ";
+        else if (!o.color.valid3() || !o.emission.valid3() || !o.position.valid3() || !o.reflIsNumber) err = "Could not validate object data!";
         if (err) { msg(message, message_len, err); delete s; return nullptr; }
         if (o.type == "sphere") s->add(0, o.radius, zero, zero, o.position.v, o.emission.v, o.color.v, (int)o.refl);
         else s->add(1, 0.0, o.north.v, o.east.v, o.position.v, o.emission.v, o.color.v, (int)o.refl);

@@ -155,6 +155,9 @@ def ref():
         L.ref_scatter.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_ulonglong, dp]
         L.ref_scatter.restype = None
         L.ref_xorwow_kat.argtypes = [ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+        if hasattr(L, "ref_scene_load_text"):
+            L.ref_scene_load_text.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
+            L.ref_scene_load_text.restype = ctypes.c_int
         if hasattr(L, "ref_scene_objects"):
             L.ref_scene_objects.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
@@ -202,6 +205,33 @@ def ref_scene_objects(path):
     cam = ctypes.create_string_buffer(72)
     ref().ref_scene_objects(os.fsencode(path), objs, n, cam, ctypes.byref(W), ctypes.byref(H))
     return objs.raw, cam.raw, W.value, H.value, n
+
+
+def ref_scene_load_texts(paths):
+    """For every file: (number of objects or -1, what SceneData::initScene printed), or None where the reference's own loader
+    aborts the process (nlohmann's const operator[] asserts on a missing key: undefined behaviour upstream).  Runs in child
+    processes for that reason; a child that dies is restarted behind the file that killed it."""
+    import json, subprocess, sys
+    child = ("import sys, json, ctypes\n"
+             "sys.path.insert(0, %r)\n"
+             "import oracle as O\n"
+             "buf = ctypes.create_string_buffer(8192)\n"
+             "for p in json.loads(sys.stdin.read()):\n"
+             "    n = O.ref().ref_scene_load_text(p.encode(), buf, 8192)\n"
+             "    print(json.dumps([n, buf.value.decode(errors='replace')]), flush=True)\n") % HERE
+    out, at = [], 0
+    paths = [os.fspath(p) for p in paths]
+    while at < len(paths):
+        r = subprocess.run([sys.executable, "-c", child], input=json.dumps(paths[at:]), capture_output=True, text=True)
+        lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("[")]
+        out += [tuple(l) for l in lines]
+        at += len(lines)
+        if at < len(paths) and r.returncode != 0:
+            out.append(None)                      # the reference died on paths[at]
+            at += 1
+        elif at < len(paths):
+            raise RuntimeError("reference loader child stopped early: " + r.stderr[-500:])
+    return out
 
 
 def ref_render(path, samples, depth, width=0, height=0, cell_begin=0, cell_end=-1, nthreads=None):

@@ -81,7 +81,7 @@ struct Loaded {
     std::vector<ObjectData> objs;
 };
 
-Loaded load(const char* path, int W_override, int H_override)
+Loaded load(const char* path, int W_override, int H_override, std::string* printed = nullptr)
 {
     Loaded l;
     // SceneData prints "Loading Scene Data..." etc. on std::cout: silence it.  Swapping cout's buffer is not thread
@@ -101,6 +101,7 @@ Loaded load(const char* path, int W_override, int H_override)
         }
     } catch (...) { l.ok = false; }
     std::cout.rdbuf(old);
+    if (printed) *printed = sink.str();
     if (W_override > 0) l.W = (uint32_t)W_override;
     if (H_override > 0) l.H = (uint32_t)H_override;
     return l;
@@ -144,6 +145,16 @@ int ref_scene_objects(const char* path, void* out_objects, int max_objects, void
     if (W) *W = (int)l.W;
     if (H) *H = (int)l.H;
     return n;
+}
+
+// What SceneData::initScene (SceneData.cpp:61-96) prints for `path` and whether it accepts the file: the differential test of
+// the host layer's scene loader compares its verdict and message with this (tests/test_host.py).
+int ref_scene_load_text(const char* path, char* out_text, int out_len)
+{
+    std::string printed;
+    Loaded l = load(path, 0, 0, &printed);
+    if (out_text && out_len > 0) std::snprintf(out_text, (size_t)out_len, "%s", printed.c_str());
+    return l.ok ? (int)l.objs.size() : -1;
 }
 
 // Number of "CUDA threads" (cells) the reference launches: min(H,22) blocks x min(W,22) threads

@@ -146,8 +146,9 @@ def test_loader_missing_and_malformed_file(pyipt, tmp_path):
 
 
 def test_loader_survives_mutated_scenes(pyipt, oracle, tmp_path):
-    """SceneData.cpp:61-96 answers any unreadable scene with a message and no scene (nlohmann throws, the reference
-    catches); the pull parser must do the same on truncated, spliced and byte-flipped copies of spheres.json: every load
+    """SceneData.cpp:61-96 answers an unreadable scene with a message and no scene - where nlohmann does not throw: a parse or
+    type error leaves main() uncaught upstream and the program dies.  The pull parser answers all of them with a message, on
+    truncated, spliced and byte-flipped copies of spheres.json: every load
     either fails with a message or yields a scene whose BVH builds. (400 seeded mutations here; 21 000 were run once.)"""
     import random
     src = open(oracle.scene_path("spheres"), "rb").read()
@@ -179,6 +180,94 @@ def test_loader_survives_mutated_scenes(pyipt, oracle, tmp_path):
             assert str(e)
             failed += 1
     assert loaded + failed == 400 and failed > 100 and loaded > 0, (loaded, failed)
+
+
+def test_loader_matches_the_reference_loader(pyipt, oracle, tmp_path):
+    """Differential test against the reference's OWN loader: SceneData.cpp, unmodified, inside oracle/_ref/libref_host.so
+    (ref_scene_load_text / ref_scene_objects), run in child processes because it aborts on some inputs.  Seeded mutants of
+    mirrors.json - keys removed, renamed or duplicated, values replaced by wrong types, empty containers, huge numbers - and
+    byte-level mutants.  Where the reference accepts a file, the host layer must too, with the same objects and camera; where
+    the reference prints a message, the same message; where the reference dies (uncaught nlohmann exception, or an
+    assertion inside nlohmann) the host layer must refuse the file with a message."""
+    import copy, random
+    if not oracle.ref_available() or not hasattr(oracle.ref(), "ref_scene_load_text"):
+        pytest.skip("oracle/_ref/libref_host.so without ref_scene_load_text (make -C oracle ref where the reference tree is)")
+    rnd = random.Random(11)
+    base = json.load(open(oracle.scene_path("mirrors")))
+    junk = [None, True, "abc", -1, 0, 1e400, [], {}, [1, 2, 3], {"xx": 1}, "sphere", "plane", "cube", 3.5, -0.0, "", 2 ** 40, {"xx": 1, "yy": 2, "zz": 3}]
+
+    def all_paths(node, path=()):
+        out = [path]
+        if isinstance(node, dict):
+            for k, v in node.items():
+                out += all_paths(v, path + (k,))
+        elif isinstance(node, list):
+            for i, v in enumerate(node):
+                out += all_paths(v, path + (i,))
+        return out
+
+    files = []
+    for i in range(260):
+        sc = copy.deepcopy(base)
+        for _ in range(rnd.randint(1, 2)):
+            p = rnd.choice([q for q in all_paths(sc) if q])
+            parent = sc
+            for k in p[:-1]:
+                parent = parent[k]
+            k, r = p[-1], rnd.random()
+            if r < 0.4:
+                if isinstance(parent, dict):
+                    parent.pop(k)
+                else:
+                    del parent[k]
+            elif r < 0.8:
+                parent[k] = copy.deepcopy(rnd.choice(junk))
+            elif isinstance(parent, dict):
+                parent[k + "_"] = parent.pop(k)
+            else:
+                parent.append(copy.deepcopy(parent[k]))
+        f = tmp_path / f"m{i}.json"
+        f.write_text(json.dumps(sc))
+        files.append(str(f))
+    src = open(oracle.scene_path("mirrors"), "rb").read()
+    for i in range(80):
+        b = bytearray(src)
+        at = rnd.randrange(len(b))
+        k = rnd.random()
+        if k < 0.4:
+            del b[at:at + rnd.randint(1, 30)]
+        elif k < 0.8:
+            b[at:at] = rnd.choice([b"{", b"}", b"[", b",", b'"', b"-", b"1e999", b"null", b" "])
+        else:
+            b[at] = rnd.randrange(32, 127)
+        f = tmp_path / f"b{i}.json"
+        f.write_bytes(bytes(b))
+        files.append(str(f))
+    verdicts = oracle.ref_scene_load_texts(files)
+    both_ok = same_message = refused = 0
+    for f, v in zip(files, verdicts):
+        try:
+            ours, message = pyipt.HostScene.load(f, brute_max=100000), None
+        except pyipt.IptError as e:
+            ours, message = None, str(e)
+        lines = [] if v is None else [l for l in v[1].split("\n") if l.strip()]
+        if v is not None and v[0] >= 0:                                  # the reference accepts the file
+            assert ours is not None, (f, message)
+            raw, cam, W, H, n = oracle.ref_scene_objects(f)
+            theirs = pyipt.HostScene.from_objects(raw, n, W, H, list(np.frombuffer(cam, np.float64)), brute_max=100000)
+            a, b = ours.arrays(), theirs.arrays()
+            for key in ("sphere_cxyzr", "sphere_object", "rect_plane", "rect_u", "rect_v", "rect_bounds", "rect_object", "mat_color", "mat_emission", "mat_reflection"):
+                assert np.array_equal(a[key], b[key], equal_nan=True), (f, key)
+            vo, vt = ours.view.contents, theirs.view.contents
+            assert (vo.width, vo.height) == (W, H) and list(vo.cam_origin) + list(vo.cam_dir) + list(vo.cam_orient) == list(vt.cam_origin) + list(vt.cam_dir) + list(vt.cam_orient)
+            both_ok += 1
+        elif v is not None and len(lines) >= 2:                          # the reference prints why it refuses it
+            assert ours is None and message.strip() == lines[-1].strip(), (f, lines, message)
+            same_message += 1
+        else:                                                            # the reference dies: uncaught exception or abort
+            assert ours is None and message, f
+            refused += 1
+    assert both_ok >= 10 and same_message >= 80 and refused >= 80, (both_ok, same_message, refused)
 
 
 def test_loader_ignores_unknown_keys_and_key_order(pyipt, tmp_path):
@@ -379,6 +468,86 @@ def test_cli_grammar(pyipt, oracle, capfd, tmp_path):
         assert lines[3] == "tracer [arguments] [path_to_scene]"
     ok, _, out = _cli(pyipt, ["--help"], capfd)
     assert ok == 0 and out.startswith("tracer [arguments] [path_to_scene]") and "between 4 and 65535" in out and "between 3 and 255" in out
+
+
+def test_cli_matches_the_reference_parser(pyipt, tmp_path):
+    """Differential test of the command-line grammar against the reference's OWN parser: InputParser.cpp, unmodified, compiled
+    by oracle/Makefile into oracle/_ref/libref_cli.so (oracle/ref_cli_shim.cpp).  For seeded random argument lists - known and
+    unknown keys, one to three dashes anywhere, missing / doubled '=', out-of-range, negative, hexadecimal, padded and
+    non-numeric values, files with dots, dashes and '=' in their names, directories, missing paths, --help, 0 to 4 arguments -
+    the two agree on validity, on the parsed samples / depth / path / scene name, and on every byte printed
+    (22 000 lists were run once: no difference)."""
+    import random
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_cli.so")
+    if not os.path.isfile(so):
+        pytest.skip("oracle/_ref/libref_cli.so not built (needs the reference tree: make -C oracle ref)")
+    R = ctypes.CDLL(so)
+    L = pyipt.lib()
+    files = [str(tmp_path / n) for n in ("a.json", "my.scene.v2.json", "noext", "with-dash.json", "k=v.json", ".hidden", "x.")]
+    for f in files:
+        open(f, "w").write("{}")
+    sub = tmp_path / "sub.dir"
+    sub.mkdir()
+    (sub / "inner").write_text("{}")
+    paths = files + [str(sub / "inner"), str(tmp_path), str(sub), "/no/such/file.json", "--help", "", "-s=4", "relative.json"]
+    keys = ["-s", "--samples", "-d", "--depth", "s", "d", "-x", "--foo", "samples", "-samples", "--s", "---s", "-s-", "--d", "-depth", "- s", ""]
+    vals = ["4", "3", "65535", "65536", "-8", "abc", "", "1e3", "40.5", " 7", "99999999999999", "0x10", "+9", "255", "256", "2", "10", "--5", "4=5", "007"]
+    seps = ["=", "=", "=", "==", "", ":", " = "]
+
+    def run_ref(args):
+        argv = (ctypes.c_char_p * (len(args) + 2))(b"tracer", *[a.encode() for a in args], None)
+        sp, sn = ctypes.create_string_buffer(4096), ctypes.create_string_buffer(1024)
+        ns, nd = ctypes.c_int(), ctypes.c_int()
+        ok = R.ref_parse_cli(len(args) + 1, argv, sp, 4096, sn, 1024, ctypes.byref(ns), ctypes.byref(nd))
+        return ok, sp.value, sn.value, ns.value, nd.value
+
+    def run_ours(args):
+        argv = (ctypes.c_char_p * (len(args) + 2))(b"tracer", *[a.encode() for a in args], None)
+        o = pyipt.Cli()
+        ok = L.ipt_host_parse_cli(len(args) + 1, argv, ctypes.byref(o))
+        return ok, o.scene_path, o.scene_name, o.samples, o.max_depth
+
+    def captured(fn, args):      # both libraries print through their own std::cout: catch file descriptor 1 itself
+        import sys
+        sys.stdout.flush()
+        r, w = os.pipe()
+        saved = os.dup(1)
+        os.dup2(w, 1)
+        os.close(w)
+        try:
+            res = fn(args)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        os.set_blocking(r, False)
+        out = b""
+        try:
+            while True:
+                chunk = os.read(r, 65536)
+                if not chunk:
+                    break
+                out += chunk
+        except BlockingIOError:
+            pass
+        os.close(r)
+        return res, out
+
+    rnd = random.Random(7)
+    valid = invalid = 0
+    for _ in range(600):
+        n = rnd.choice([0, 1, 1, 2, 2, 2, 3, 3, 3, 4])
+        args = [rnd.choice(keys) + rnd.choice(seps) + rnd.choice(vals) if rnd.random() < 0.9 else rnd.choice(paths) for _ in range(max(0, n - 1))]
+        if n >= 1:
+            args.append(rnd.choice(paths) if rnd.random() < 0.9 else rnd.choice(keys) + "=" + rnd.choice(vals))
+        a, printed_a = captured(run_ref, args)
+        b, printed_b = captured(run_ours, args)
+        assert a[0] == b[0] and printed_a == printed_b, (args, a, b, printed_a, printed_b)
+        if a[0]:
+            assert a == b, (args, a, b)
+            valid += 1
+        else:
+            invalid += 1
+    assert valid > 20 and invalid > 200, (valid, invalid)
 
 
 def test_tile_schedule_is_a_balanced_partition(pyipt):
