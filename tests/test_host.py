@@ -415,6 +415,34 @@ def test_time_string_and_benchmark_record(pyipt, tmp_path):
     assert open(f).read() == "spheresD10S40;00:00:05.7;mazeD10S40;00:01:00.12;"   # no newline (Measurements.cpp:53)
 
 
+def test_time_string_and_benchmark_record_match_the_reference(pyipt, tmp_path, monkeypatch):
+    """Differential: getTimeString and saveBenchmark of the reference's own Measurements.cpp (unmodified, reached through
+    oracle/_ref/libref_cli.so) against ipt_host_time_string / ipt_host_append_benchmark, on edge and random durations and a
+    sequence of records appended to a fresh and to an existing file."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_cli.so")
+    if not os.path.isfile(so) or not hasattr(ctypes.CDLL(so), "ref_time_string"):
+        pytest.skip("oracle/_ref/libref_cli.so not built (needs the reference tree: make -C oracle ref)")
+    R = ctypes.CDLL(so)
+    R.ref_time_string.argtypes = [ctypes.c_ulonglong, ctypes.c_char_p, ctypes.c_int]
+    R.ref_save_benchmark.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    L = pyipt.lib()
+    rng = np.random.default_rng(9)
+    cases = [0, 1, 9, 10, 99, 100, 999, 1000, 1001, 9999, 59999, 60000, 60001, 599999, 3599999, 3600000, 3600001, 35999999,
+             36000000, 86399999, 86400000, 359999999, 360000000, 2 ** 32 - 1, 2 ** 32, 2 ** 40]
+    cases += [int(x) for x in rng.integers(0, 4 * 3600000, 2000)] + [int(x) for x in rng.integers(0, 2 ** 36, 500)]
+    a, b = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+    for ms in cases:
+        R.ref_time_string(ms, a, 64)
+        L.ipt_host_time_string(ms, b, 64)
+        assert a.value == b.value, ms
+    monkeypatch.chdir(tmp_path)                                        # the reference always writes ./benchmark.txt
+    ours = str(tmp_path / "ours.txt").encode()
+    for ident, t in ((b"spheresD10S40", b"00:00:05.7"), (b"mazeD10S40", b"00:01:00.12"), (b"my.scene.v2D255S65535", b"10:01:01.1"), (b"", b"")):
+        R.ref_save_benchmark(ident, t)
+        L.ipt_host_append_benchmark(ours, ident, t)
+        assert open(tmp_path / "benchmark.txt", "rb").read() == open(ours, "rb").read()
+
+
 def _cli(pyipt, args, capfd):
     argv = (ctypes.c_char_p * (len(args) + 1))(b"tracer", *[a.encode() for a in args])
     out = pyipt.Cli()
