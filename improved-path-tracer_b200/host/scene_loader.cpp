@@ -7,8 +7,10 @@
 // in fp64, on the host.
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -59,6 +61,15 @@ struct Reader {
         p = r.ptr;
         return true;
     }
+    // width and height are read into uint32_t upstream (SceneData.cpp:113-114): nlohmann's conversion to an arithmetic type other
+    // than its own number types also takes true / false as 1 / 0.  Doubles (radius, vector components) and the enum do not.
+    bool arithmetic(double& v)
+    {
+        const char c = peek();
+        if (c == 't' && end - p >= 4 && !std::memcmp(p, "true", 4)) { p += 4; v = 1.0; return true; }
+        if (c == 'f' && end - p >= 5 && !std::memcmp(p, "false", 5)) { p += 5; v = 0.0; return true; }
+        return number(v);
+    }
     bool skip()   // any value
     {
         const char c = peek();
@@ -107,7 +118,7 @@ bool read_vec(Reader& r, Vec3Opt& out)
         if (!r.string(k) || !r.eat(':')) return r.fail();
         const int i = k == "xx" ? 0 : k == "yy" ? 1 : k == "zz" ? 2 : -1;
         if (i >= 0) { out.key[i] = true; out.has[i] = false; }      // (a repeated key: the last one counts, as in nlohmann)
-        if (i >= 0 && (r.peek() == '-' || r.peek() == '+' || (r.peek() >= '0' && r.peek() <= '9'))) {
+        if (i >= 0 && (r.peek() == '-' || (r.peek() >= '0' && r.peek() <= '9'))) {
             if (!r.number(out.v[i])) return false;
             out.has[i] = true;
         } else if (!r.skip()) return false;
@@ -223,6 +234,8 @@ void ipt_host_scene::refresh_view()
 extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, size_t message_len)
 {
     msg(message, message_len, "");
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (std::getenv("IPT_VERBOSE")) std::fprintf(stderr, "[load] %s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count()); };
     std::FILE* f = path ? std::fopen(path, "rb") : nullptr;
     if (!f) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }   // SceneData.cpp:66-70
     std::string buf;
@@ -231,6 +244,7 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     std::fseek(f, 0, SEEK_SET);
     if (sz > 0) { buf.resize((size_t)sz); if (std::fread(&buf[0], 1, (size_t)sz, f) != (size_t)sz) buf.clear(); }
     std::fclose(f);
+    lap("read");
 
     Reader r{buf.data(), buf.data() + buf.size()};
     bool hasW = false, hasH = false, hasCamera = false, hasObjects = false, objectsIsArray = false;
@@ -243,8 +257,8 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
         do {
             std::string k;
             if (!r.string(k) || !r.eat(':')) { parsed = false; break; }
-            if (k == "width") { hasW = true; if (!r.number(W)) { parsed = false; break; } }
-            else if (k == "height") { hasH = true; if (!r.number(H)) { parsed = false; break; } }
+            if (k == "width") { hasW = true; if (!r.arithmetic(W)) { parsed = false; break; } }
+            else if (k == "height") { hasH = true; if (!r.arithmetic(H)) { parsed = false; break; } }
             else if (k == "camera") {
                 hasCamera = true;
                 if (r.peek() != '{') { if (!r.skip()) { parsed = false; break; } continue; }
@@ -294,36 +308,90 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
                 r.p++;
                 if (r.eat(']')) continue;
                 bool oko = true;
-                if (buf.size() < (8u << 20)) {
+                const size_t parallel_min = std::getenv("IPT_PARSE_PARALLEL_MIN") ? (size_t)std::atoll(std::getenv("IPT_PARSE_PARALLEL_MIN")) : (size_t)(8u << 20);
+                if (buf.size() < parallel_min) {
                     do { objs.emplace_back(); oko = read_object(r, objs.back()); } while (oko && r.eat(','));
                 } else {
-                    // large scene (a 1M-object file is ~200 MB): one structural scan finds where every array element
-                    // starts, then the elements are parsed on all host threads into their slots (order preserved)
-                    std::vector<const char*> starts;
-                    const char* q = r.p;
-                    for (;;) {
-                        while (q < r.end && (*q == ' ' || *q == '\n' || *q == '\t' || *q == '\r')) q++;
-                        if (q >= r.end) { oko = false; break; }
-                        starts.push_back(q);
-                        int depth = 0;
-                        bool in_str = false;
-                        for (; q < r.end; q++) {               // skip one JSON value
+                    // large scene (a 1M-object file is ~200 MB): a structural scan finds where every array element starts, then
+                    // the elements are parsed on all host threads into their slots (order preserved).  The scan itself runs on
+                    // all threads too (it was 40 % of the load): the rest of the file is cut into equal parts, every part is
+                    // scanned as if it began outside a string and keeps the commas at the lowest nesting depth it reaches (the
+                    // depth at its first byte is not known yet, but the commas between array elements are the ones at the lowest
+                    // depth that occurs before the array ends); one serial pass then chains the parts - a part whose assumption
+                    // was wrong (it began inside a string, or the array ends inside it) is scanned again with its true state.
+                    const char* const a0 = r.p;
+                    unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+                    if (const char* e = std::getenv("IPT_HOST_THREADS")) T = (unsigned)std::max(1, std::min(256, std::atoi(e)));
+                    // Whether a part begins inside a string is not known either (a third of the bytes of a scene file are inside
+                    // strings), so every part is scanned for both cases at once: a quote flips both, a structural byte counts
+                    // for the case in which it lies outside a string.
+                    struct Acc { std::vector<const char*> commas; int depth = 0, lowest = 0; };
+                    struct Part { Acc acc[2]; bool in_str0 = false; const char* next = nullptr; };   // acc[1]: the part began inside a string
+                    const unsigned NP = T * 4;             // a part scanned again (the one the array ends in) costs 1 / NP of the scan
+                    std::vector<Part> parts(NP);
+                    auto cut = [&](unsigned t) { return a0 + (size_t)(r.end - a0) * t / NP; };
+                    auto scan_guess = [&](unsigned t) {
+                        Part& P = parts[t];
+                        const char* q = cut(t);
+                        const char* const e = cut(t + 1);
+                        bool in0 = false;                  // inside a string, if the part began outside one
+                        for (; q < e; q++) {
+                            const char ch = *q;
+                            if (ch == '\\') { q++; continue; }      // escapes the next byte (valid only inside a string, whichever case is true)
+                            if (ch == '"') { in0 = !in0; continue; }
+                            Acc& A = P.acc[in0 ? 1 : 0];
+                            if (ch == '{' || ch == '[') A.depth++;
+                            else if (ch == '}' || ch == ']') { if (--A.depth < A.lowest) { A.lowest = A.depth; A.commas.clear(); } }
+                            else if (ch == ',' && A.depth == A.lowest) A.commas.push_back(q);
+                        }
+                        P.in_str0 = in0; P.next = q;       // q > e: the first byte of the next part is escaped
+                    };
+                    {
+                        std::vector<std::thread> th;
+                        for (unsigned w = 0; w < T; w++) th.emplace_back([&, w] { for (unsigned t = w; t < NP; t += T) scan_guess(t); });
+                        for (auto& x : th) x.join();
+                    }
+                    lap("scan (parts)");
+                    std::vector<const char*> commas;
+                    const char* close = nullptr;          // the array's closing bracket
+                    const char* q = a0;                    // everything before q is accounted for
+                    int depth = 0;
+                    bool in_str = false;
+                    unsigned rescans = 0;
+                    for (unsigned t = 0; t < NP && !close; t++) {
+                        const Part& P = parts[t];
+                        const Acc& A = P.acc[in_str ? 1 : 0];
+                        const char* const e = cut(t + 1);
+                        if (q == cut(t) && depth + A.lowest >= 0) {                     // the array goes on beyond this part
+                            if (depth + A.lowest == 0) commas.insert(commas.end(), A.commas.begin(), A.commas.end());
+                            depth += A.depth; in_str = in_str ? !P.in_str0 : P.in_str0; q = P.next;
+                            continue;
+                        }
+                        rescans++;
+                        for (; q < e; q++) {                                            // byte by byte, with the true state
                             const char ch = *q;
                             if (in_str) { if (ch == '\\') q++; else if (ch == '"') in_str = false; continue; }
                             if (ch == '"') in_str = true;
                             else if (ch == '{' || ch == '[') depth++;
-                            else if (ch == '}' || ch == ']') { if (depth == 0) break; depth--; }
-                            else if (ch == ',' && depth == 0) break;
+                            else if (ch == '}' || ch == ']') { if (depth == 0) { close = q; break; } depth--; }
+                            else if (ch == ',' && depth == 0) commas.push_back(q);
                         }
-                        if (q >= r.end) { oko = false; break; }
-                        if (*q == ',') { q++; continue; }
-                        break;                                 // the array's closing bracket
                     }
+                    std::vector<const char*> starts;
+                    auto after_ws = [&](const char* c) { while (c < r.end && (*c == ' ' || *c == '\n' || *c == '\t' || *c == '\r')) c++; return c; };
+                    if (!close) oko = false;
+                    else {
+                        starts.reserve(commas.size() + 2);
+                        starts.push_back(after_ws(a0));
+                        for (const char* c : commas) starts.push_back(after_ws(c + 1));
+                    }
+                    q = close;
+                    if (std::getenv("IPT_VERBOSE")) std::fprintf(stderr, "[load] %u parts, %u scanned again, %zu elements\n", NP, rescans, starts.size());
+                    lap("scan");
                     if (oko) {
                         starts.push_back(q);
                         const size_t n = starts.size() - 1;
                         objs.resize(n);
-                        const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
                         std::vector<char> okv(T, 1);
                         std::vector<std::thread> th;
                         for (unsigned t = 0; t < T; t++)
@@ -331,6 +399,9 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
                                 for (size_t i = n * t / T; i < n * (t + 1) / T; i++) {
                                     Reader e{starts[i], starts[i + 1]};
                                     if (!read_object(e, objs[i]) || !e.ok) { okv[t] = 0; return; }
+                                    e.ws();                                   // nothing but the separating comma may follow
+                                    if (e.p < e.end && *e.p == ',') { e.p++; e.ws(); }
+                                    if (e.p != e.end) { okv[t] = 0; return; }
                                 }
                             });
                         for (auto& x : th) x.join();
@@ -344,6 +415,7 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
         if (parsed && !r.eat('}')) parsed = false;
     }
     if (!parsed || !r.ok) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }
+    lap("parse");
 
     // validation in the reference's order: basic data, camera, objects (SceneData.cpp:72-94)
     if (!hasH || !hasW) { msg(message, message_len, "Missing height or witdh data!"); return nullptr; }            // :98-111
@@ -379,6 +451,7 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     }
     if (s->mat_reflection.empty()) { msg(message, message_len, "Object list empty! Cannot build scene"); delete s; return nullptr; }   // :87-91
     s->refresh_view();
+    lap("flatten");
     return s;
 }
 

@@ -305,6 +305,47 @@ def test_builders_survive_non_finite_objects(pyipt, oracle, tmp_path):
         assert h.arrays()["mat_color"].shape[0] == cs.n_objects
 
 
+def test_parallel_parse_equals_serial_parse(pyipt, tmp_path, monkeypatch):
+    """Files above 8 MB (config 5's is 200 MB) are cut into parts that are scanned for the array's element boundaries on all host
+    threads - without knowing, at a part's first byte, the nesting depth or whether it lies inside a string - and the elements
+    are parsed in parallel.  Forced on small files here (IPT_PARSE_PARALLEL_MIN=0) with part counts from 4 to 256: the same
+    arrays as the serial parse for a scene whose extra keys carry braces, brackets, commas, quotes and backslashes inside
+    strings, nested arrays and objects; the same verdict on truncated copies."""
+    scene = synthetic_scene(700, 5)
+    nasty = ['}{', '],[', 'a,b', 'q\\"uote', 'back\\\\slash\\\\', '"', '\\', '{"xx":1}', '[[[', ']]]}}}', ',,,,', 'x' * 300, '']
+    for i, o in enumerate(scene["objects"]):
+        o["note" + nasty[i % len(nasty)]] = nasty[(i * 7) % len(nasty)]
+        if i % 3 == 0:
+            o["extra"] = {"list": [1, [2, {"k": "]}"}], "}"], "s": nasty[(i * 5) % len(nasty)]}
+    path = write_scene(tmp_path / "nasty.json", scene)
+    text = open(path).read()
+    keys = ("sphere_cxyzr", "sphere_object", "rect_plane", "rect_u", "rect_v", "rect_bounds", "rect_object", "mat_color", "mat_emission", "mat_reflection")
+    serial = pyipt.HostScene.load(path).arrays()
+    cuts = [len(text) * k // 23 for k in range(1, 23)]
+    verdict = {}
+    for c in cuts:
+        (tmp_path / "cut.json").write_text(text[:c])
+        try:
+            pyipt.HostScene.load(str(tmp_path / "cut.json"))
+            verdict[c] = "ok"
+        except pyipt.IptError as e:
+            verdict[c] = str(e)
+    monkeypatch.setenv("IPT_PARSE_PARALLEL_MIN", "0")
+    for threads in (1, 2, 5, 16, 64):
+        monkeypatch.setenv("IPT_HOST_THREADS", str(threads))
+        par = pyipt.HostScene.load(path).arrays()
+        for k in keys:
+            assert np.array_equal(serial[k], par[k]), (threads, k)
+        for c in cuts:
+            (tmp_path / "cut.json").write_text(text[:c])
+            try:
+                pyipt.HostScene.load(str(tmp_path / "cut.json"))
+                got = "ok"
+            except pyipt.IptError as e:
+                got = str(e)
+            assert got == verdict[c], (threads, c)
+
+
 def test_from_objects_equals_loader(pyipt, oracle):
     """ipt_host_from_objects (the reference's ObjectData[] AoS) flattens to the same arrays as the JSON loader."""
     sc = oracle.Scene.load("mirrors")
