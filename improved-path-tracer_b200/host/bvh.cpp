@@ -229,7 +229,17 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
     auto lap = [&](const char* what) { if (std::getenv("IPT_VERBOSE")) std::fprintf(stderr, "[bvh] %s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count()); };
     leaf_size = std::min(16u, std::max(1u, leaf_size));
     std::vector<Prim> prims(n);
-    for (uint32_t i = 0; i < ns; i++) {
+    // boxes of a million primitives: 0.15 s on one thread, so spread over the host threads (independent slots)
+    auto parallel_for = [](uint32_t count, auto body) {
+        unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("IPT_HOST_THREADS")) nt = (unsigned)std::max(1, std::min(256, std::atoi(e)));
+        if (count < 65536 || nt == 1) { body(0u, count); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back([=] { body((uint32_t)((uint64_t)count * t / nt), (uint32_t)((uint64_t)count * (t + 1) / nt)); });
+        for (auto& x : th) x.join();
+    };
+    parallel_for(ns, [&](uint32_t i0, uint32_t i1) {
+    for (uint32_t i = i0; i < i1; i++) {
         const double* c = &s->sphere_cxyzr[4 * (size_t)i];
         const double r = std::fabs(c[3]);
         Prim& p = prims[i];
@@ -239,7 +249,9 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         p.ref = i;
         sanitize(p);
     }
-    for (uint32_t j = 0; j < nr; j++) {
+    });
+    parallel_for(nr, [&](uint32_t j0, uint32_t j1) {
+    for (uint32_t j = j0; j < j1; j++) {
         const double *c = &s->rect_center[3 * (size_t)j], *N = &s->rect_north[3 * (size_t)j], *E = &s->rect_east[3 * (size_t)j];
         Prim& p = prims[ns + j];
         for (int sn = -1; sn <= 1; sn += 2)
@@ -252,6 +264,7 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
         p.ref = 0x80000000u | j;
         sanitize(p);
     }
+    });
     // fork threads on the top levels of large scenes (2^par_depth subtrees in flight)
     int par_depth = 0;
     for (unsigned hw = std::max(1u, std::thread::hardware_concurrency()); (1u << par_depth) < hw && par_depth < 5;) par_depth++;

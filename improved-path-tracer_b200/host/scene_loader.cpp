@@ -431,6 +431,15 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     norm3(camDir.v); norm3(camOri.v);                                                                             // :143-145
     std::memcpy(s->view.cam_origin, camPos.v, 24); std::memcpy(s->view.cam_dir, camDir.v, 24); std::memcpy(s->view.cam_orient, camOri.v, 24);
     const double zero[3] = {0, 0, 0};
+    {   // room for everything at once: a million objects would otherwise grow sixteen arrays by doubling
+        size_t n_sph = 0;
+        for (const ObjTmp& o : objs) n_sph += o.type == "sphere";
+        const size_t n_rec = objs.size() - n_sph;
+        s->mat_color.reserve(3 * objs.size()); s->mat_emission.reserve(3 * objs.size()); s->mat_reflection.reserve(objs.size());
+        s->sphere_cxyzr.reserve(4 * n_sph); s->sphere_object.reserve(n_sph);
+        s->rect_plane.reserve(4 * n_rec); s->rect_u.reserve(4 * n_rec); s->rect_v.reserve(4 * n_rec); s->rect_bounds.reserve(4 * n_rec);
+        s->rect_object.reserve(n_rec); s->rect_center.reserve(3 * n_rec); s->rect_north.reserve(3 * n_rec); s->rect_east.reserve(3 * n_rec);
+    }
     for (const ObjTmp& o : objs) {
         const char* err = nullptr;
         if (!o.color.present || !o.emission.present || !o.position.present || !o.hasRefl || !o.hasType ||
