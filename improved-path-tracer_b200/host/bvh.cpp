@@ -218,7 +218,7 @@ void put_box(const Box& b, float* lo, float* hi)
 
 }  // namespace
 
-extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_t brute_max)
+static int build_bvh_impl(ipt_host_scene* s, uint32_t leaf_size, uint32_t brute_max)
 {
     if (!s) return -1;
     s->bvh_nodes.clear(); s->bvh_slot_prim.clear();
@@ -318,4 +318,13 @@ extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_
     lap("grid");
     s->refresh_view();
     return (int)s->bvh_nodes.size();
+}
+
+extern "C" int ipt_host_build_bvh(ipt_host_scene* s, uint32_t leaf_size, uint32_t brute_max)
+{
+    try { return build_bvh_impl(s, leaf_size, brute_max); }
+    catch (...) {                                   // out of memory: nothing is thrown across the C ABI; the scene keeps no half-built tree
+        if (s) { s->bvh_nodes.clear(); s->bvh_slot_prim.clear(); s->grid_cell_start.clear(); s->grid_refs.clear(); s->grid_big.clear(); s->refresh_view(); }
+        return -1;
+    }
 }

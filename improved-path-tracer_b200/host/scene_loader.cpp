@@ -5,6 +5,11 @@
 // polymorphic objects from it (Renderer.cu:69-86, Plane.cu:32-45).  Here a small pull parser reads the file once
 // without building a DOM (a 1M-object scene is a ~200 MB file) and the per-rectangle constants are computed once,
 // in fp64, on the host.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <charconv>
 #include <chrono>
@@ -231,22 +236,57 @@ void ipt_host_scene::refresh_view()
     view.grid_big = grid && !grid_big.empty() ? grid_big.data() : nullptr;
 }
 
+namespace {
+// The bytes of a scene file: regular files are mapped (config 5's file is 200 MB: reading it into a string cost a zero fill and
+// a copy, 0.17 s), anything else that can be read (a pipe, /proc) is read in pieces up to 1 GB; a directory is not a scene.
+struct FileBytes {
+    const char* data = nullptr;
+    size_t size = 0;
+    void* mapped = nullptr;
+    std::string owned;
+    bool open(const char* path)
+    {
+        const int fd = path ? ::open(path, O_RDONLY) : -1;
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) { ::close(fd); return false; }
+        if (S_ISREG(st.st_mode) && st.st_size > 0) {
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) { mapped = m; data = (const char*)m; size = (size_t)st.st_size; ::close(fd); return true; }
+        }
+        char piece[1 << 16];
+        for (;;) {
+            const ssize_t n = ::read(fd, piece, sizeof(piece));
+            if (n <= 0) break;
+            owned.append(piece, (size_t)n);
+            if (owned.size() > ((size_t)1 << 30)) { ::close(fd); return false; }
+        }
+        ::close(fd);
+        data = owned.data(); size = owned.size();
+        return true;
+    }
+    ~FileBytes() { if (mapped) munmap(mapped, size); }
+};
+ipt_host_scene* load_scene(const char* path, char* message, size_t message_len);
+}  // namespace
+
 extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, size_t message_len)
+{
+    try { return load_scene(path, message, message_len); }
+    catch (...) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }   // nothing is thrown across the C ABI
+}
+
+namespace {
+ipt_host_scene* load_scene(const char* path, char* message, size_t message_len)
 {
     msg(message, message_len, "");
     const auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (std::getenv("IPT_VERBOSE")) std::fprintf(stderr, "[load] %s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count()); };
-    std::FILE* f = path ? std::fopen(path, "rb") : nullptr;
-    if (!f) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }   // SceneData.cpp:66-70
-    std::string buf;
-    std::fseek(f, 0, SEEK_END);
-    const long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    if (sz > 0) { buf.resize((size_t)sz); if (std::fread(&buf[0], 1, (size_t)sz, f) != (size_t)sz) buf.clear(); }
-    std::fclose(f);
+    FileBytes buf;
+    if (!buf.open(path)) { msg(message, message_len, "Could not load provided json file!"); return nullptr; }   // SceneData.cpp:66-70
     lap("read");
 
-    Reader r{buf.data(), buf.data() + buf.size()};
+    Reader r{buf.data, buf.data + buf.size};
     bool hasW = false, hasH = false, hasCamera = false, hasObjects = false, objectsIsArray = false;
     double W = 0, H = 0;
     Vec3Opt camDir, camPos, camOri;
@@ -309,7 +349,7 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
                 if (r.eat(']')) continue;
                 bool oko = true;
                 const size_t parallel_min = std::getenv("IPT_PARSE_PARALLEL_MIN") ? (size_t)std::atoll(std::getenv("IPT_PARSE_PARALLEL_MIN")) : (size_t)(8u << 20);
-                if (buf.size() < parallel_min) {
+                if (buf.size < parallel_min) {
                     do { objs.emplace_back(); oko = read_object(r, objs.back()); } while (oko && r.eat(','));
                 } else {
                     // large scene (a 1M-object file is ~200 MB): a structural scan finds where every array element starts, then
@@ -463,8 +503,9 @@ extern "C" ipt_host_scene* ipt_host_load_scene(const char* path, char* message, 
     lap("flatten");
     return s;
 }
+}  // namespace
 
-extern "C" ipt_host_scene* ipt_host_from_objects(const void* objects, uint32_t n, uint32_t width, uint32_t height, const double* cam)
+static ipt_host_scene* from_objects_impl(const void* objects, uint32_t n, uint32_t width, uint32_t height, const double* cam)
 {
     if (!objects || !cam || n == 0) return nullptr;
     auto* s = new ipt_host_scene();
@@ -486,3 +527,9 @@ extern "C" ipt_host_scene* ipt_host_from_objects(const void* objects, uint32_t n
 extern "C" void ipt_host_free_scene(ipt_host_scene* s) { delete s; }
 extern "C" const ipt_scene* ipt_host_scene_view(const ipt_host_scene* s) { return s ? &s->view : nullptr; }
 extern "C" void ipt_host_set_size(ipt_host_scene* s, uint32_t w, uint32_t h) { if (s) { s->view.width = w; s->view.height = h; } }
+
+extern "C" ipt_host_scene* ipt_host_from_objects(const void* objects, uint32_t n, uint32_t width, uint32_t height, const double* cam)
+{
+    try { return from_objects_impl(objects, n, width, height, cam); }
+    catch (...) { return nullptr; }                 // nothing is thrown across the C ABI
+}

@@ -143,6 +143,24 @@ def test_loader_missing_and_malformed_file(pyipt, tmp_path):
     p.write_text('{"width": 10, "height": ')
     with pytest.raises(pyipt.IptError):
         pyipt.HostScene.load(str(p))
+    # not a file at all: a message, never an exception across the C ABI (a directory once ended the process in std::length_error)
+    for special in (str(tmp_path), "/dev/null", "/proc/self/status"):
+        with pytest.raises(pyipt.IptError) as e:
+            pyipt.HostScene.load(special)
+        assert str(e.value) == "Could not load provided json file!"
+    (tmp_path / "empty.json").write_text("")
+    with pytest.raises(pyipt.IptError):
+        pyipt.HostScene.load(str(tmp_path / "empty.json"))
+    # a scene that is not a regular file (read in pieces instead of mapped)
+    import threading
+    fifo = str(tmp_path / "scene.fifo")
+    os.mkfifo(fifo)
+    text = json.dumps(synthetic_scene(40, 1))
+    w = threading.Thread(target=lambda: open(fifo, "w").write(text))
+    w.start()
+    hs = pyipt.HostScene.load(fifo)
+    w.join()
+    assert hs.view.contents.n_objects == len(json.loads(text)["objects"])
 
 
 def test_loader_survives_mutated_scenes(pyipt, oracle, tmp_path):
