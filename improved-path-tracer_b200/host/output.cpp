@@ -55,9 +55,16 @@ void chunk(std::vector<unsigned char>& out, const char* type, const unsigned cha
 // The zlib stream is deflated in bands of rows on several threads (a 4K frame took 0.67 s on one thread, longer than its
 // render): every band is a raw deflate stream of its own that ends on a byte boundary (Z_SYNC_FLUSH; Z_FINISH for the
 // last), the bands are concatenated behind one zlib header and the Adler-32 of the whole is combined from the bands'.
+static int write_png_rgb8(const char* path, const uint8_t* rgb8, uint32_t W, uint32_t H);
 extern "C" int ipt_host_write_png_rgb8(const char* path, const uint8_t* rgb8, uint32_t W, uint32_t H)
 {
-    if (!path || !rgb8 || !W || !H) return -1;
+    if (!path || !rgb8 || !W || !H || (uint64_t)W * H > (1ull << 29)) return -1;   // one IDAT chunk: below 2 GB of deflate output
+    try { return write_png_rgb8(path, rgb8, W, H); }
+    catch (...) { return -1; }                       // out of memory: nothing is thrown across the C ABI
+}
+
+static int write_png_rgb8(const char* path, const uint8_t* rgb8, uint32_t W, uint32_t H)
+{
     const size_t stride = 1 + (size_t)W * 3;
     const unsigned nt = host_threads();
     // bands of at least ~256 KB so that the lost history between bands costs nothing measurable
@@ -115,10 +122,12 @@ extern "C" int ipt_host_write_png_rgb8(const char* path, const uint8_t* rgb8, ui
 
 extern "C" int ipt_host_write_png(const char* path, const float* rgb, uint32_t W, uint32_t H)
 {
-    if (!path || !rgb || !W || !H) return -1;
-    std::vector<uint8_t> bytes((size_t)W * H * 3);
-    parallel_for(bytes.size(), [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) bytes[i] = (uint8_t)ipt_host_to_rgb((double)rgb[i]); });
-    return ipt_host_write_png_rgb8(path, bytes.data(), W, H);
+    if (!path || !rgb || !W || !H || (uint64_t)W * H > (1ull << 29)) return -1;
+    try {
+        std::vector<uint8_t> bytes((size_t)W * H * 3);
+        parallel_for(bytes.size(), [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) bytes[i] = (uint8_t)ipt_host_to_rgb((double)rgb[i]); });
+        return ipt_host_write_png_rgb8(path, bytes.data(), W, H);
+    } catch (...) { return -1; }
 }
 
 // Measurements.cpp:21-41: every unit is "00" when zero, zero-padded to two digits below 10; the milliseconds are
