@@ -285,7 +285,8 @@ Scatter scatter(const Obj& o, const V& P, const V& in, Rng& rng, int depth)
 // ------------------------------------------------------------------------------------------------ renderer
 struct Accel;
 struct Ctx {
-    std::vector<Obj> objs;
+    std::shared_ptr<const std::vector<Obj>> objs_shared;   // one copy for all the threads of a render (a million objects: 200 MB)
+    const std::vector<Obj>& objs_ref() const { return *objs_shared; }
     uint32_t W, H, samples, maxDepth;
     V camO, camD, camX, vecZ;
     uint64_t casts_reference = 0, casts_needed = 0;
@@ -427,10 +428,11 @@ Hit nearest_accel(const std::vector<Obj>& objs, const Accel& A, const RayT& r)
 // Renderer.cu:227-243: linear scan, strict '<', so the lowest index wins ties; t == 0 means "no hit"
 Hit nearest(const Ctx& c, const RayT& r)
 {
-    if (c.accel) return nearest_accel(c.objs, *c.accel, r);
+    if (c.accel) return nearest_accel(c.objs_ref(), *c.accel, r);
     Hit h{-1, INF};
-    for (size_t i = 0; i < c.objs.size(); i++) {
-        const double t = intersect(c.objs[i], r);
+    const std::vector<Obj>& objs = c.objs_ref();
+    for (size_t i = 0; i < objs.size(); i++) {
+        const double t = intersect(objs[i], r);
         if (t != 0.0 && t < h.t) { h.t = t; h.index = (int)i; }
     }
     return h;
@@ -450,7 +452,7 @@ V deep_layers(Ctx& c, RayT ray, uint8_t depth, Rng& rng, uint32_t lane, V thr, b
         if (needed && !is_zero(thr)) c.casts_needed++;
         const Hit h = nearest(c, ray);
         if (h.index == -1) break;
-        const Obj& o = c.objs[h.index];
+        const Obj& o = c.objs_ref()[h.index];
         const V P = ray.o + ray.d * h.t;
         rng.node(lane, depth);
         const Scatter s = scatter(o, P, ray.d, rng, depth);
@@ -472,7 +474,7 @@ V second_layer(Ctx& c, const RayT& ray, uint8_t& depth, Rng& rng, uint32_t lane,
     if (!is_zero(thr)) c.casts_needed++;
     const Hit h = nearest(c, ray);
     if (h.index == -1) return V();
-    const Obj& o = c.objs[h.index];
+    const Obj& o = c.objs_ref()[h.index];
     const V P = ray.o + ray.d * h.t;
     rng.node(lane, depth);
     const Scatter s = scatter(o, P, ray.d, rng, depth);
@@ -494,7 +496,7 @@ V first_layer(Ctx& c, const RayT& ray, Rng& rng)
     c.casts_needed++;
     const Hit h = nearest(c, ray);
     if (h.index == -1) return V();
-    const Obj& o = c.objs[h.index];
+    const Obj& o = c.objs_ref()[h.index];
     const V P = ray.o + ray.d * h.t;
     rng.node(0, depth);
     const Scatter s = scatter(o, P, ray.d, rng, depth);
@@ -551,8 +553,10 @@ Ctx make_ctx(const or_scene* s, uint32_t samples, uint32_t maxDepth)
     c.W = s->width; c.H = s->height; c.samples = samples; c.maxDepth = maxDepth;
     c.camO = V(s->camera); c.camD = V(s->camera + 3); c.camX = V(s->camera + 6);
     c.vecZ = norm(cross(c.camD, c.camX));                          // RenderController.cu:39
-    c.objs.reserve(s->n_objects);
-    for (uint32_t i = 0; i < s->n_objects; i++) c.objs.push_back(make_obj(s->objects[i]));
+    auto objs = std::make_shared<std::vector<Obj>>();
+    objs->reserve(s->n_objects);
+    for (uint32_t i = 0; i < s->n_objects; i++) objs->push_back(make_obj(s->objects[i]));
+    c.objs_shared = objs;
     return c;
 }
 
@@ -565,7 +569,7 @@ static int render_impl(const or_scene* scene, uint32_t samples, uint32_t max_dep
 {
     if (!scene || !out_rgb || max_depth < 1 || max_depth > 255 || samples < 1) return -1;
     Ctx base0 = make_ctx(scene, samples, max_depth);
-    if (accel) base0.accel = build_accel(base0.objs);
+    if (accel) base0.accel = build_accel(base0.objs_ref());
     const Ctx& base = base0;
     const uint32_t W = base.W, H = base.H;
     const uint32_t nT = W <= BLOCK ? W : BLOCK, nB = H <= BLOCK ? H : BLOCK;   // RenderController.cu:53-54
@@ -573,7 +577,7 @@ static int render_impl(const or_scene* scene, uint32_t samples, uint32_t max_dep
     if (begin < 0) begin = 0;
     if (end < 0 || end > nUnits) end = nUnits;
     if (nthreads < 1) nthreads = 1;
-    if (nthreads > end - begin) nthreads = std::max(1, end - begin);   // every thread works on a copy of the scene
+    if (nthreads > end - begin) nthreads = std::max(1, end - begin);
     std::atomic<int> next{begin};
     std::atomic<uint64_t> castsRef{0}, castsNeeded{0}, nSamples{0};
     std::vector<std::thread> pool;
@@ -635,7 +639,7 @@ void or_nearest_hit_accel(const or_scene* scene, const double* rays, uint32_t n_
 static void nearest_hit_impl(const or_scene* scene, const double* rays, uint32_t n_rays, int32_t* out_index, double* out_t, bool accel)
 {
     Ctx c = make_ctx(scene, 1, 3);
-    if (accel) c.accel = build_accel(c.objs);
+    if (accel) c.accel = build_accel(c.objs_ref());
     // rays are independent: spread over the host cores (the scan of a million-primitive scene takes ~10 ms per ray)
     const unsigned hw = std::thread::hardware_concurrency();
     const uint32_t nt = std::max(1u, std::min<uint32_t>(hw ? hw : 1u, n_rays / 16u + 1u));
